@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json): decode tok/s and % of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is one decode step of the workload's batch through the whole model (all layers + lm_head + arg-max).
+Default workload: Mistral-7B-v0.1 bf16, batch 1, 2k context (the configuration the headline metric is quoted on).
+  value  = whole-job tokens/s, device-resident greedy loop (CUDA graph per step), CUDA-event timed on the library's stream
+  e2e    = the same metric through the reference-facing call fl_forward(): host ids in (H2D), f32 logits out (D2H),
+           host arg-max, exactly the per-token traffic of the reference's generate loop (models/mod.rs:411-453)
+  roofline = the GEMV family (dominant kernels), algorithmic weight bytes / CUDA-event duration, live in this run
+  cpu_baseline = the oracle port (numpy f32 restatement of candle's CPU path) on this box's host cores, bounded sample
+`--impl reference` times that CPU port alone.  Weights are synthetic (device-generated, bit-identical to oracle/synth.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (arch key, batch, context, description)
+    "mistral7b_b1": ("mistral7b", 1, 2048, "Mistral-7B-v0.1 bf16 decode, batch 1, 2k context"),
+    "mistral7b_b8": ("mistral7b", 8, 2048, "Mistral-7B-v0.1 bf16 decode, batch 8, 2k context"),
+    "tinyllama_b1": ("tinyllama", 1, 128, "TinyLlama-1.1B bf16 decode, batch 1, 128-token prompt"),
+    "qwen25_7b_b1": ("qwen25_7b", 1, 2048, "Qwen2.5-7B bf16 decode, batch 1, 2k context"),
+}
+
+
+def oracle_config(key):
+    """CPU legs only (cpu_baseline / --impl reference): the oracle's config for the workload."""
+    from oracle import causal_lm as ocl
+    return {"mistral7b": ocl.MISTRAL_7B, "tinyllama": ocl.TINYLLAMA, "qwen25_7b": ocl.QWEN25_7B}[key]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bounded sample, extrapolated to the full layer count)
+# --------------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """A `sample_layers`-layer slice of the model at KV length `ctx` on the host cores (oracle port, numpy f32 / BLAS).
+    One step = one decode step of the slice + one lm_head; extrapolated: T_full = L * T_layer + T_head."""
+
+    def __init__(self, cfg, batch, ctx, sample_layers=2, max_steps=64):
+        from dataclasses import replace
+        from oracle import causal_lm as ocl
+        self.cfg, self.batch, self.ctx, self.sample_layers = cfg, batch, ctx, sample_layers
+        self.small = replace(cfg, num_hidden_layers=sample_layers, max_position_embeddings=ctx + max_steps + 8)
+        self.w = ocl.synth_weights(self.small, 0, 0.02)
+        self.m = ocl.CausalLM(self.small, self.w)
+        self.rng = np.random.default_rng(0)
+        self.ids = np.full((batch, 1), 5, dtype=np.uint32)
+        self.x = self.rng.standard_normal((batch, self.small.hidden_size), dtype=np.float32)
+        self.pos = ctx
+        self.reset_kv()
+
+    def reset_kv(self):
+        d, nkv = self.small.head_dim, self.small.num_key_value_heads
+        self.m.kv = [(self.rng.standard_normal((self.batch, nkv, self.ctx, d), dtype=np.float32) * 0.5,
+                      self.rng.standard_normal((self.batch, nkv, self.ctx, d), dtype=np.float32) * 0.5)
+                     for _ in range(self.sample_layers)]
+        self.pos = self.ctx
+
+    def step(self):
+        """-> extrapolated seconds per full-model decode step."""
+        from oracle import candle_ops as ops
+        t0 = time.perf_counter()
+        self.m.forward(self.ids, self.pos)
+        t_total = time.perf_counter() - t0
+        self.pos += 1
+        t0 = time.perf_counter()
+        ops.linear(ops.rms_norm(self.x, self.w["model.norm.weight"], self.small.rms_norm_eps), self.w["lm_head.weight"])
+        t_head = time.perf_counter() - t0
+        t_layer = max(t_total - t_head, 1e-9) / self.sample_layers
+        return self.cfg.num_hidden_layers * t_layer + t_head
+
+    def threads(self):
+        try:
+            from threadpoolctl import threadpool_info
+            return max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count() or 1])
+        except Exception:
+            return os.cpu_count() or 1
+
+    def describe(self, n):
+        return (f"{n} decode steps of {self.sample_layers}/{self.cfg.num_hidden_layers} layers + lm_head at KV length {self.ctx}, "
+                f"f32 numpy/BLAS port of candle's CPU path, extrapolated to {self.cfg.num_hidden_layers} layers")
+
+
+def cpu_decode_sample(cfg, batch, ctx, n_steps=3, warmup=1, budget_s=60.0):
+    cs = CpuSample(cfg, batch, ctx, max_steps=n_steps + warmup)
+    for _ in range(warmup):
+        cs.step()
+    ts, t0 = [], time.perf_counter()
+    for _ in range(n_steps):
+        ts.append(cs.step())
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return batch / float(np.mean(ts)), cs.describe(len(ts)), cs.threads(), len(ts)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    arch, batch, ctx, desc = WORKLOADS[args.workload]
+    v, sample, threads, n = cpu_decode_sample(oracle_config(arch), batch, ctx, args.steps, max(1, min(args.warmup, 3)), 150.0)
+    line = {"impl": "reference", "metric": "decode_tokens_per_s", "value": v, "unit": "tok/s", "n_gpus": args.gpus, "steps": n,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch": batch, "context": ctx, "parallelism": "host cores"},
+            "cpu_baseline": {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from fastllm_b200 import models, presets
+    arch, batch, ctx, desc = WORKLOADS[args.workload]
+    cls, cf = presets.PRESETS[arch]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model, _ = cls.initialize_model(cf, None, "bf16", local_rank, random_seed=0, std=0.02)
+    K, W = args.steps, args.warmup
+    cap = ctx + max(K, W, 16) + 8
+    cache = models.DeviceCache(model.dev, batch, cap)
+    first = np.full((batch,), 5, dtype=np.uint32)
+    launches0 = models.launch_count()
+
+    # ---- device-resident decode: W warm-up steps, then exactly K timed steps -------------------------------------------
+    cache.fill_synthetic(batch, ctx)
+    cache.decode_greedy_loop(first, ctx, W)
+    cache.fill_synthetic(batch, ctx)                      # back to KV length = ctx for the timed region
+    barrier()
+    l0 = models.launch_count()
+    with ClockSampler(local_rank) as clk:
+        _, ms = cache.decode_greedy_loop(first, ctx, K)
+        barrier()
+    gpu_launches = models.launch_count() - l0
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * batch * K / (ms / 1e3)
+
+    # ---- end to end through the reference-facing call: host ids -> fl_forward -> host logits -> host arg-max ------------
+    cache.fill_synthetic(batch, ctx)
+    ids = first.reshape(batch, 1).copy()
+    for s in range(min(W, 4)):
+        logits = cache.forward(ids, ctx + s)
+    cache.fill_synthetic(batch, ctx)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        logits = cache.forward(ids, ctx + s)                                   # H2D ids + D2H logits inside
+        ids = np.array([[models.sample_argmax(r)] for r in logits], dtype=np.uint32)   # LogitsProcessor arg-max on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e = world * batch * K / float(t_e.item())
+
+    if rank != 0:
+        barrier()
+        return
+
+    # ---- roofline of the dominant kernel family (GEMV weight streaming), measured live with CUDA events ----------------
+    cache.fill_synthetic(batch, ctx)
+    models.prof_begin()
+    cache.decode_greedy_loop(first, ctx, 4)
+    prof = models.prof_end()
+    gemv = [p for p in prof if p["kernel"].startswith("gemv_")]
+    gemv_ms = sum(p["ms"] for p in gemv)
+    gemv_bytes = sum(p["bytes"] for p in gemv)
+    all_ms = sum(p["ms"] for p in prof)
+    peak, peak_src = peaks()
+    achieved = gemv_bytes / (gemv_ms / 1e3) / 1e9 if gemv_ms > 0 else 0.0
+    streamed = model.dev.streamed_bytes()
+    head_dim = cf.hidden_size // cf.num_attention_heads
+    kv_bytes = batch * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 2 * 2
+    step_bytes = streamed + kv_bytes
+    step_gbs = step_bytes / (ms / K / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "gemv_kernel<M,CPT,PRO,EPI> family (qkv+rope, o+resid, gate/up+silu, down+resid, lm_head)",
+                "peak_source": peak_src, "kernel_share_of_step": gemv_ms / all_ms if all_ms else None,
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
+                               "frac_of_nominal_8tbs": step_gbs / 8000.0},
+                "per_kernel": prof}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, sample, threads, _ = cpu_decode_sample(oracle_config(arch), batch, ctx, 4, 1, 40.0)
+        cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
+
+    line = {"metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": desc, "batch": batch, "context": ctx, "l2": "inputs larger than L2 (weights streamed once per step)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (batch-data-parallel)",
+                       "kv_cache": "bf16 paged, synthetic prefill", "weights": "synthetic N(0,0.02^2)-like bf16, seed 0"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": int(batch * 4), "d2h_bytes_per_step": int(batch * cf.vocab_size * 4)},
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--workload", default="mistral7b_b1", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import __graft_entry__ as g
+    if rank == 0 or not os.path.exists(os.path.join(ROOT, "fastllm_b200", "libfastllm_b200.so")):
+        g.build()
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,85 @@
+// Small glue kernels of the decode step (token gather, arg-max finalisation, step-state advance), sm_100a.
+#pragma once
+#include "common.cuh"
+#include "gemv.cuh"
+
+namespace fl {
+
+// K1: Embedding::forward = index_select.  resid[m, :] = f32(embed[ids[row_base + m], :])   (bf16 table, f32 residual stream)
+__global__ void embed_gather_kernel(const uint16_t* __restrict__ table, const uint32_t* __restrict__ ids, int row_base, int H,
+                                    int vocab, float* __restrict__ resid) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int m = blockIdx.y;
+    uint32_t id = ids[row_base + m];
+    if (id >= (uint32_t)vocab) id = vocab - 1;   // candle would raise; ids are validated on the host before launch
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)id * H);
+    float* dst = resid + (size_t)m * H;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < H / 8; c += gridDim.x * blockDim.x) {
+        const uint4 w = src[c];
+        float4 a = make_float4(bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y));
+        float4 b = make_float4(bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w));
+        reinterpret_cast<float4*>(dst + c * 8)[0] = a;
+        reinterpret_cast<float4*>(dst + c * 8)[1] = b;
+    }
+}
+
+// K18 on device: merge the per-CTA arg-max partials of the lm_head GEMV (last index wins ties, like candle's
+// LogitsProcessor::sample_argmax) and write next_ids[seq] for rows that are the last token of their sequence.
+__global__ void argmax_finalize_kernel(const float* __restrict__ val, const int* __restrict__ idx, int nparts, int M, int row_base,
+                                       int t, uint32_t* __restrict__ next_ids) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    for (int m = 0; m < M; ++m) {
+        float v = -INFINITY;
+        int i = -1;
+        for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
+            const float ov = val[m * nparts + p];
+            const int oi = idx[m * nparts + p];
+            if (ov > v || (ov == v && oi > i)) { v = ov; i = oi; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, i, o);
+            if (ov > v || (ov == v && oi > i)) { v = ov; i = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = i; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (sv[w] > v || (sv[w] == v && si[w] > i)) { v = sv[w]; i = si[w]; }
+            const int rg = row_base + m;
+            if (rg % t == t - 1) next_ids[rg / t] = (uint32_t)i;
+        }
+        __syncthreads();
+    }
+}
+
+// End of a forward call: kv_base[seq] += t.  In the device-resident greedy loop also rope_pos += 1 and ids <- next_ids.
+__global__ void advance_state_kernel(StepState* st, int b, int t, int rope_inc, uint32_t* ids, const uint32_t* next_ids, int feedback,
+                                     uint32_t* trace, int* trace_pos) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = threadIdx.x;
+    if (i < b) {
+        st->kv_base[i] += t;
+        if (feedback) ids[i] = next_ids[i];
+        if (trace != nullptr) trace[(size_t)(*trace_pos) * b + i] = next_ids[i];
+    }
+    __syncthreads();
+    if (i == 0) {
+        st->rope_pos += rope_inc;
+        if (trace != nullptr) *trace_pos += 1;
+    }
+}
+
+__global__ void set_state_kernel(StepState* st, int rope_pos) { st->rope_pos = rope_pos; }
+__global__ void reset_state_kernel(StepState* st, int kv_len) {
+    for (int i = threadIdx.x; i < kMaxBatch; i += blockDim.x) st->kv_base[i] = kv_len;
+    if (threadIdx.x == 0) st->rope_pos = 0;
+}
+
+}  // namespace fl

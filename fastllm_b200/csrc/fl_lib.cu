@@ -1,0 +1,858 @@
+// fastllm_b200: C-ABI entry points + causal-LM decode/prefill orchestration (sm_100a).
+// See include/fastllm_b200.h for the reference interface each entry point replaces.
+#include <cmath>
+#include <sstream>
+
+#include "attn_decode.cuh"
+#include "elementwise.cuh"
+#include "gemv.cuh"
+#include "model.cuh"
+#include "synth.cuh"
+
+namespace fl {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+Profiler g_prof;
+static std::atomic<int> g_device{-1};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static uint16_t host_f32_to_bf16(float f) {
+    uint32_t b;
+    std::memcpy(&b, &f, 4);
+    return (uint16_t)((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
+}
+static float host_f16_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h >> 15) << 31;
+    int exp = (h >> 10) & 0x1F;
+    uint32_t man = h & 0x3FF;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else {
+            exp = 1;
+            while (!(man & 0x400)) { man <<= 1; --exp; }
+            man &= 0x3FF;
+            bits = sign | ((uint32_t)(exp + 112) << 23) | (man << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7F800000u | (man << 13);
+    } else {
+        bits = sign | ((uint32_t)(exp + 112) << 23) | (man << 13);
+    }
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GEMV dispatch
+// ------------------------------------------------------------------------------------------------------------------
+struct GemvPlan {
+    int cpt, threads, grid;
+};
+
+static GemvPlan plan_gemv(int N, int K) {
+    FL_CHECK(K % 8 == 0 && N % 2 == 0, FL_ERR_INVALID, "GEMV needs K % 8 == 0 and N % 2 == 0");
+    const int K8 = K / 8;
+    GemvPlan p;
+    p.cpt = (K8 + 511) / 512;
+    FL_CHECK(p.cpt <= 5, FL_ERR_UNSUPPORTED, "GEMV K too large (K <= 20480)");
+    p.threads = (int)align_up((size_t)(K8 + p.cpt - 1) / p.cpt, 32);
+    int cps = 512 / p.threads;   // CTAs per SM so that 512 threads stream on every SM
+    if (cps < 1) cps = 1;
+    if (cps > 4) cps = 4;
+    p.grid = kNumSMs * cps;
+    if (p.grid > N / 2) p.grid = N / 2;
+    return p;
+}
+
+template <int M, int PRO, int EPI>
+static void launch_gemv_cpt(LaunchCtx& lc, const char* tag, const GemvPlan& p, const GemvArgs& a) {
+    const uint64_t bytes = (uint64_t)a.N * a.K * 2;
+    dim3 g(p.grid), b(p.threads);
+    switch (p.cpt) {
+        case 1: launch(lc, tag, bytes, gemv_kernel<M, 1, PRO, EPI>, g, b, 0, a); break;
+        case 2: launch(lc, tag, bytes, gemv_kernel<M, 2, PRO, EPI>, g, b, 0, a); break;
+        case 3: launch(lc, tag, bytes, gemv_kernel<M, 3, PRO, EPI>, g, b, 0, a); break;
+        case 4: launch(lc, tag, bytes, gemv_kernel<M, 4, PRO, EPI>, g, b, 0, a); break;
+        default: launch(lc, tag, bytes, gemv_kernel<M, 5, PRO, EPI>, g, b, 0, a); break;
+    }
+}
+
+template <int PRO, int EPI>
+static void launch_gemv(LaunchCtx& lc, const char* tag, int M, const GemvPlan& p, const GemvArgs& a) {
+    if (M == 1)
+        launch_gemv_cpt<1, PRO, EPI>(lc, tag, p, a);
+    else
+        launch_gemv_cpt<2, PRO, EPI>(lc, tag, p, a);
+}
+
+static size_t attn_smem_bytes(int d, int n_rep) {
+    const size_t ring = (size_t)4 * kKvPage * d * 2;
+    const size_t red = (size_t)1024 * n_rep * 4;
+    return ring > red ? ring : red;
+}
+
+static void launch_attn(LaunchCtx& lc, int d, int nsplit, int nkv, int rows, size_t smem, uint64_t bytes, const AttnArgs& a) {
+    dim3 g(nsplit, nkv, rows), b(kAttnThreads);
+    switch (d) {
+        case 16: launch(lc, "attn_decode", bytes, attn_decode_kernel<16>, g, b, smem, a); break;
+        case 32: launch(lc, "attn_decode", bytes, attn_decode_kernel<32>, g, b, smem, a); break;
+        case 64: launch(lc, "attn_decode", bytes, attn_decode_kernel<64>, g, b, smem, a); break;
+        case 128: launch(lc, "attn_decode", bytes, attn_decode_kernel<128>, g, b, smem, a); break;
+        default: throw Error(FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weights
+// ------------------------------------------------------------------------------------------------------------------
+static void validate_config(const fl_config& c) {
+    FL_CHECK(c.arch >= FL_ARCH_LLAMA && c.arch <= FL_ARCH_BERT, FL_ERR_INVALID, "unknown arch");
+    FL_CHECK(c.hidden_size > 0 && c.num_attention_heads > 0 && c.num_hidden_layers > 0 && c.vocab_size > 0 &&
+                 c.intermediate_size > 0,
+             FL_ERR_INVALID, "config sizes must be positive");
+    const int d = c.hidden_size / c.num_attention_heads;
+    // the reference panics on these: mistral.rs:109-127, models/config.rs:20-54
+    FL_CHECK(d * c.num_attention_heads == c.hidden_size, FL_ERR_INVALID, "hidden_size must be divisible by num_attention_heads");
+    FL_CHECK(d % 2 == 0, FL_ERR_INVALID, "head_dim must be even for RoPE embeddings");
+    const int nkv = c.num_key_value_heads > 0 ? c.num_key_value_heads : c.num_attention_heads;
+    FL_CHECK(c.num_attention_heads % nkv == 0, FL_ERR_INVALID, "num_attention_heads must be divisible by num_key_value_heads");
+    FL_CHECK(c.num_attention_heads / nkv <= kAttnMaxRep, FL_ERR_UNSUPPORTED, "GQA group size > 8 not supported");
+    FL_CHECK(c.hidden_size % 8 == 0 && c.intermediate_size % 8 == 0, FL_ERR_UNSUPPORTED, "hidden/intermediate size must be a multiple of 8");
+    FL_CHECK(c.max_position_embeddings > 0, FL_ERR_INVALID, "max_position_embeddings must be positive");
+}
+
+static void build_weights(Weights& w) {
+    const fl_config& c = w.cfg;
+    w.H = c.hidden_size; w.I = c.intermediate_size; w.V = c.vocab_size; w.L = c.num_hidden_layers;
+    w.nh = c.num_attention_heads;
+    w.nkv = c.num_key_value_heads > 0 ? c.num_key_value_heads : c.num_attention_heads;
+    w.d = w.H / w.nh;
+    w.max_pos = c.max_position_embeddings;
+    w.nqkv = (w.nh + 2 * w.nkv) * w.d;
+    FL_CHECK(w.d == 16 || w.d == 32 || w.d == 64 || w.d == 128, FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
+    FL_CHECK(c.arch != FL_ARCH_BERT && c.arch != FL_ARCH_MIXTRAL, FL_ERR_UNSUPPORTED, "arch not built yet in this round");
+
+    const size_t A = 256;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, A); return o; };
+    const size_t H = w.H, I = w.I, V = w.V, nq = (size_t)w.nh * w.d;
+    const size_t o_embed = take(V * H * 2), o_head = take(V * H * 2), o_fnorm = take(H * 4);
+    struct LO { size_t wqkv, bqkv, wo, wgu, wdown, ln1, ln2; };
+    std::vector<LO> lo(w.L);
+    for (int l = 0; l < w.L; ++l) {
+        lo[l].wqkv = take((size_t)w.nqkv * H * 2);
+        lo[l].bqkv = c.qkv_bias ? take((size_t)w.nqkv * 4) : (size_t)-1;
+        lo[l].wo = take(H * nq * 2);
+        lo[l].wgu = take(2 * I * H * 2);
+        lo[l].wdown = take(H * I * 2);
+        lo[l].ln1 = take(H * 4);
+        lo[l].ln2 = take(H * 4);
+    }
+    const size_t o_cos = take((size_t)w.max_pos * (w.d / 2) * 4), o_sin = take((size_t)w.max_pos * (w.d / 2) * 4);
+    w.slab.alloc(off, /*zero=*/true);
+    uint8_t* base = w.slab.p;
+    w.embed = (uint16_t*)(base + o_embed);
+    w.lm_head = (uint16_t*)(base + o_head);
+    w.final_norm = (float*)(base + o_fnorm);
+    w.layers.resize(w.L);
+    for (int l = 0; l < w.L; ++l) {
+        w.layers[l].wqkv = (uint16_t*)(base + lo[l].wqkv);
+        w.layers[l].bqkv = c.qkv_bias ? (float*)(base + lo[l].bqkv) : nullptr;
+        w.layers[l].wo = (uint16_t*)(base + lo[l].wo);
+        w.layers[l].wgu = (uint16_t*)(base + lo[l].wgu);
+        w.layers[l].wdown = (uint16_t*)(base + lo[l].wdown);
+        w.layers[l].ln1 = (float*)(base + lo[l].ln1);
+        w.layers[l].ln2 = (float*)(base + lo[l].ln2);
+    }
+    w.rope_cos = (float*)(base + o_cos);
+    w.rope_sin = (float*)(base + o_sin);
+    // bytes one decode step must stream: every parameter except the embedding table
+    w.streamed_bytes = 2 * ((uint64_t)w.L * ((uint64_t)w.nqkv * H + H * nq + 3 * I * H) + V * H) +
+                       4 * ((uint64_t)w.L * (2 * H + (c.qkv_bias ? w.nqkv : 0)) + H);
+}
+
+struct TensorRoute {
+    enum Kind { BF16_MAT, F32_VEC } kind;
+    void* base;
+    int64_t rows, cols;   // logical shape expected ([rows, cols] or [rows])
+    RowMap map;
+};
+
+static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
+    const int64_t H = w.H, I = w.I, V = w.V, d = w.d, nq = (int64_t)w.nh * d, nk = (int64_t)w.nkv * d;
+    auto mat = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m) { r = {TensorRoute::BF16_MAT, base, rows, cols, m}; return true; };
+    auto vec = [&](float* base, int64_t rows, RowMap m) { r = {TensorRoute::F32_VEC, base, rows, 1, m}; return true; };
+    const RowMap ident{0, 0, 0, 0};
+    if (name == "model.embed_tokens.weight") return mat(w.embed, V, H, ident);
+    if (name == "lm_head.weight") return mat(w.lm_head, V, H, ident);
+    if (name == "model.norm.weight") return vec(w.final_norm, H, ident);
+    const std::string pre = "model.layers.";
+    if (name.compare(0, pre.size(), pre) != 0) return false;
+    size_t dot = name.find('.', pre.size());
+    if (dot == std::string::npos) return false;
+    int li = -1;
+    try { li = std::stoi(name.substr(pre.size(), dot - pre.size())); } catch (...) { return false; }
+    if (li < 0 || li >= w.L) return false;
+    LayerW& lw = w.layers[li];
+    const std::string rest = name.substr(dot + 1);
+    const RowMap ropeq{0, 1, (int32_t)d, 0}, ropek{nq, 1, (int32_t)d, 0}, vmap{nq + nk, 0, 0, 0};
+    if (rest == "input_layernorm.weight") return vec(lw.ln1, H, ident);
+    if (rest == "post_attention_layernorm.weight") return vec(lw.ln2, H, ident);
+    if (rest == "self_attn.q_proj.weight") return mat(lw.wqkv, nq, H, ropeq);
+    if (rest == "self_attn.k_proj.weight") return mat(lw.wqkv, nk, H, ropek);
+    if (rest == "self_attn.v_proj.weight") return mat(lw.wqkv, nk, H, vmap);
+    if (w.cfg.qkv_bias) {
+        if (rest == "self_attn.q_proj.bias") return vec(lw.bqkv, nq, ropeq);
+        if (rest == "self_attn.k_proj.bias") return vec(lw.bqkv, nk, ropek);
+        if (rest == "self_attn.v_proj.bias") return vec(lw.bqkv, nk, vmap);
+    }
+    if (rest == "self_attn.o_proj.weight") return mat(lw.wo, H, nq, ident);
+    if (rest == "mlp.gate_proj.weight") return mat(lw.wgu, I, H, RowMap{0, 2, 0, 0});
+    if (rest == "mlp.up_proj.weight") return mat(lw.wgu, I, H, RowMap{0, 2, 0, 1});
+    if (rest == "mlp.down_proj.weight") return mat(lw.wdown, H, I, ident);
+    return false;
+}
+
+static std::vector<std::string> expected_tensors(const Weights& w) {
+    std::vector<std::string> v = {"model.embed_tokens.weight", "model.norm.weight"};
+    for (int l = 0; l < w.L; ++l) {
+        const std::string p = "model.layers." + std::to_string(l) + ".";
+        for (const char* s : {"input_layernorm.weight", "post_attention_layernorm.weight", "self_attn.q_proj.weight",
+                              "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight",
+                              "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight"})
+            v.push_back(p + s);
+        if (w.cfg.qkv_bias)
+            for (const char* s : {"self_attn.q_proj.bias", "self_attn.k_proj.bias", "self_attn.v_proj.bias"}) v.push_back(p + s);
+    }
+    return v;
+}
+
+static void put_tensor(Weights& w, const char* name, int dtype, const int64_t* shape, int rank, const void* host) {
+    FL_CHECK(!w.finalized, FL_ERR_STATE, "model already finalized");
+    TensorRoute r;
+    FL_CHECK(route_tensor(w, name, r), FL_ERR_INVALID, std::string("unknown tensor name: ") + name);
+    int64_t numel = 1;
+    for (int i = 0; i < rank; ++i) numel *= shape[i];
+    const bool shape_ok = (r.kind == TensorRoute::BF16_MAT) ? (rank == 2 && shape[0] == r.rows && shape[1] == r.cols)
+                                                            : (rank == 1 && shape[0] == r.rows);
+    FL_CHECK(shape_ok, FL_ERR_INVALID, std::string("shape mismatch for ") + name);
+    FL_CHECK(dtype == FL_DTYPE_F32 || dtype == FL_DTYPE_BF16 || dtype == FL_DTYPE_F16, FL_ERR_INVALID, "bad dtype");
+    // convert to bf16 bit patterns (round-to-nearest-even), the dtype the reference server loads into (main.rs:120)
+    std::vector<uint16_t> bits((size_t)numel);
+    if (dtype == FL_DTYPE_BF16) {
+        std::memcpy(bits.data(), host, (size_t)numel * 2);
+    } else if (dtype == FL_DTYPE_F32) {
+        const float* f = (const float*)host;
+        for (int64_t i = 0; i < numel; ++i) bits[i] = host_f32_to_bf16(f[i]);
+    } else {
+        const uint16_t* h = (const uint16_t*)host;
+        for (int64_t i = 0; i < numel; ++i) bits[i] = host_f32_to_bf16(host_f16_to_f32(h[i]));
+    }
+    if (r.kind == TensorRoute::BF16_MAT) {
+        uint16_t* dst = (uint16_t*)r.base;
+        const size_t rowb = (size_t)r.cols * 2;
+        if (r.map.mode == 0) {
+            FL_CUDA(cudaMemcpy(dst + r.map.dst_row0 * r.cols, bits.data(), (size_t)numel * 2, cudaMemcpyHostToDevice));
+        } else if (r.map.mode == 2) {
+            FL_CUDA(cudaMemcpy2D(dst + (size_t)r.map.lane * r.cols, 2 * rowb, bits.data(), rowb, rowb, (size_t)r.rows,
+                                 cudaMemcpyHostToDevice));
+        } else {
+            std::vector<uint16_t> perm((size_t)numel);
+            for (int64_t row = 0; row < r.rows; ++row)
+                std::memcpy(perm.data() + (size_t)(r.map.map(row) - r.map.dst_row0) * r.cols, bits.data() + (size_t)row * r.cols, rowb);
+            FL_CUDA(cudaMemcpy(dst + r.map.dst_row0 * r.cols, perm.data(), (size_t)numel * 2, cudaMemcpyHostToDevice));
+        }
+    } else {
+        std::vector<float> vals((size_t)r.rows);
+        for (int64_t row = 0; row < r.rows; ++row) {
+            const uint32_t b = (uint32_t)bits[row] << 16;
+            float f;
+            std::memcpy(&f, &b, 4);
+            vals[(size_t)(r.map.map(row) - r.map.dst_row0)] = f;
+        }
+        FL_CUDA(cudaMemcpy((float*)r.base + r.map.dst_row0, vals.data(), (size_t)r.rows * 4, cudaMemcpyHostToDevice));
+    }
+    w.have.insert(name);
+    if (std::string(name) == "lm_head.weight") w.lm_head_loaded = true;
+}
+
+static void random_init(Weights& w, uint64_t seed, float stdv) {
+    FL_CHECK(!w.finalized, FL_ERR_STATE, "model already finalized");
+    std::vector<std::string> names = expected_tensors(w);
+    names.push_back("lm_head.weight");
+    for (const std::string& n : names) {
+        TensorRoute r;
+        FL_CHECK(route_tensor(w, n, r), FL_ERR_INVALID, "internal: unroutable " + n);
+        const bool is_norm = n.size() >= 11 && n.compare(n.size() - 11, 11, "norm.weight") == 0;
+        const uint64_t ts = tensor_seed(seed, n.c_str());
+        if (r.kind == TensorRoute::BF16_MAT) {
+            synth_fill_bf16_kernel<<<kNumSMs * 8, 256>>>((uint16_t*)r.base, r.rows, r.cols, ts, stdv, r.map);
+        } else if (is_norm) {
+            fill_f32_kernel<<<8, 256>>>((float*)r.base, r.rows, 1.0f);
+        } else {
+            synth_fill_f32_kernel<<<8, 256>>>((float*)r.base, r.rows, ts, stdv, r.map);
+        }
+        g_launches.fetch_add(1);
+        w.have.insert(n);
+    }
+    w.lm_head_loaded = true;
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaDeviceSynchronize());
+}
+
+static void finalize(Weights& w) {
+    FL_CHECK(!w.finalized, FL_ERR_STATE, "model already finalized");
+    for (const std::string& n : expected_tensors(w))
+        FL_CHECK(w.have.count(n), FL_ERR_STATE, "missing tensor: " + n);
+    if (!w.lm_head_loaded) w.lm_head = w.embed;   // candle qwen2: tied embeddings when lm_head.weight is absent
+    // RoPE tables (see oracle/candle_ops.py rope_tables for the candle rule being followed)
+    const int half = w.d / 2;
+    std::vector<float> cs((size_t)w.max_pos * half), sn((size_t)w.max_pos * half);
+    std::vector<float> inv(half);
+    for (int i = 0; i < half; ++i) {
+        float p;
+        if (w.cfg.arch == FL_ARCH_LLAMA) {
+            const float e = (float)(2 * i) / (float)w.d;
+            p = (float)std::pow((double)(float)w.cfg.rope_theta, (double)e);
+        } else {
+            p = (float)std::pow(w.cfg.rope_theta, (double)(2 * i) / (double)w.d);
+        }
+        inv[i] = 1.0f / p;
+    }
+    for (int pos = 0; pos < w.max_pos; ++pos)
+        for (int i = 0; i < half; ++i) {
+            const float f = (float)pos * inv[i];
+            cs[(size_t)pos * half + i] = (float)std::cos((double)f);
+            sn[(size_t)pos * half + i] = (float)std::sin((double)f);
+        }
+    FL_CUDA(cudaMemcpy(w.rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    FL_CUDA(cudaMemcpy(w.rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+    w.finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cache + forward
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPassRows = 2;   // activation rows per CUDA-core GEMV pass
+
+static void cache_create(fl_cache& c, int max_batch, int max_seq) {
+    const Weights& w = *c.w;
+    FL_CHECK(w.finalized, FL_ERR_STATE, "model not finalized");
+    FL_CHECK(max_batch >= 1 && max_batch <= kMaxBatch && max_seq >= 1, FL_ERR_INVALID, "bad cache dimensions");
+    c.max_batch = max_batch;
+    c.max_seq = max_seq;
+    c.pages_per_seq = (max_seq + kKvPage - 1) / kKvPage;
+    FL_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.state.alloc(1, true);
+    std::vector<int> pt((size_t)max_batch * c.pages_per_seq);
+    for (size_t i = 0; i < pt.size(); ++i) pt[i] = (int)i;   // static page assignment; the layout stays paged
+    c.page_table.alloc(pt.size());
+    FL_CUDA(cudaMemcpy(c.page_table.p, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice));
+    c.layer_pool_elems = (size_t)max_batch * c.pages_per_seq * w.nkv * kKvPage * w.d;
+    c.kpool.alloc(c.layer_pool_elems * w.L, true);
+    c.vpool.alloc(c.layer_pool_elems * w.L, true);
+    int ns = (2 * kNumSMs + w.nkv * kPassRows - 1) / (w.nkv * kPassRows);
+    if (ns > c.pages_per_seq) ns = c.pages_per_seq;
+    if (ns < 1) ns = 1;
+    c.nsplit = ns;
+    const size_t nq = (size_t)w.nh * w.d;
+    c.ids.alloc((size_t)max_batch * max_seq);
+    c.next_ids.alloc(max_batch, true);
+    c.trace_pos.alloc(1, true);
+    c.resid.alloc(kPassRows * w.H);
+    c.q.alloc(kPassRows * nq);
+    c.attn_out.alloc(kPassRows * nq);
+    c.act.alloc((size_t)kPassRows * w.I);
+    c.logits.alloc((size_t)max_batch * w.V, true);
+    c.part_acc.alloc((size_t)kPassRows * w.nh * c.nsplit * w.d);
+    c.part_ml.alloc((size_t)kPassRows * w.nh * c.nsplit * 2);
+    c.counters.alloc((size_t)kPassRows * w.nkv, true);
+    c.amax_parts = kNumSMs * 4;
+    c.amax_val.alloc((size_t)kPassRows * c.amax_parts);
+    c.amax_idx.alloc((size_t)kPassRows * c.amax_parts);
+    c.h_ids.alloc((size_t)max_batch * max_seq);
+    c.h_logits.alloc((size_t)max_batch * w.V);
+    const size_t smem = attn_smem_bytes(w.d, w.nh / w.nkv);
+    switch (w.d) {
+        case 16: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+        case 32: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+        case 64: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+        default: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
+    }
+    FL_CUDA(cudaDeviceSynchronize());
+}
+
+static void cache_destroy_graphs(fl_cache& c) {
+    for (auto& kv : c.graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c.graphs.clear();
+}
+
+// Enqueue the whole forward for the flattened [b, t] call on lc.stream.  Rows are processed in passes of kPassRows,
+// pass-major / layer-minor: a token's layer-l attention only needs the layer-l K/V of EARLIER tokens, which earlier
+// passes already appended, so the order is causal-correct.
+static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode) {
+    const Weights& w = *c.w;
+    const int rows = b * t;
+    const size_t nq = (size_t)w.nh * w.d;
+    const GemvPlan p_qkv = plan_gemv(w.nqkv, w.H), p_o = plan_gemv(w.H, (int)nq), p_gu = plan_gemv(2 * w.I, w.H),
+                   p_down = plan_gemv(w.H, w.I), p_head = plan_gemv(w.V, w.H);
+    FL_CHECK(p_head.grid <= c.amax_parts, FL_ERR_STATE, "internal: arg-max partial buffer too small");
+    const size_t attn_smem = attn_smem_bytes(w.d, w.nh / w.nkv);
+    const float qscale = (float)(1.0 / std::sqrt((double)w.d));
+    const bool windowed = (w.cfg.arch != FL_ARCH_LLAMA) && w.cfg.sliding_window > 0 && t > 1;
+
+    for (int row_base = 0; row_base < rows; row_base += kPassRows) {
+        const int M = std::min(kPassRows, rows - row_base);
+        bool has_last = false;
+        for (int m = 0; m < M; ++m) has_last |= ((row_base + m) % t == t - 1);
+
+        launch(lc, "embed_gather", (uint64_t)M * w.H * 2, embed_gather_kernel, dim3((w.H / 8 + 255) / 256, M), dim3(256), 0,
+               (const uint16_t*)w.embed, (const uint32_t*)c.ids.p, row_base, w.H, w.V, c.resid.p);
+
+        for (int l = 0; l < w.L; ++l) {
+            const LayerW& lw = w.layers[l];
+            GemvArgs a{};
+            a.row_base = row_base; a.t = t; a.eps = w.cfg.norm_eps;
+            // K2+K3+K4+K5+K6: RMSNorm -> fused q|k|v GEMV (+bias) -> RoPE -> q store + in-place paged KV append
+            a.W = lw.wqkv; a.N = w.nqkv; a.K = w.H; a.x = c.resid.p; a.norm_w = lw.ln1; a.bias = lw.bqkv;
+            a.q_out = c.q.p; a.kpool = c.kpool.p + (size_t)l * c.layer_pool_elems; a.vpool = c.vpool.p + (size_t)l * c.layer_pool_elems;
+            a.page_table = c.page_table.p; a.pt_stride = c.pages_per_seq; a.state = c.state.p;
+            a.rope_cos = w.rope_cos; a.rope_sin = w.rope_sin; a.nh = w.nh; a.nkv = w.nkv; a.d = w.d; a.max_pos = w.max_pos;
+            launch_gemv<PRO_RMSNORM, EPI_QKV>(lc, "gemv_qkv_rope", M, p_qkv, a);
+
+            // K7-K11: split-K paged decode attention
+            AttnArgs at{};
+            at.q = c.q.p; at.kpool = a.kpool; at.vpool = a.vpool; at.page_table = c.page_table.p; at.pt_stride = c.pages_per_seq;
+            at.state = c.state.p; at.part_acc = c.part_acc.p; at.part_ml = c.part_ml.p; at.counters = c.counters.p; at.out = c.attn_out.p;
+            at.nh = w.nh; at.nkv = w.nkv; at.t = t; at.row_base = row_base;
+            at.sliding_window = windowed ? w.cfg.sliding_window : 0;
+            at.qscale = qscale;
+            const uint64_t kv_bytes = (uint64_t)M * (c.kv_len + t) * w.nkv * w.d * 2 * 2;
+            launch_attn(lc, w.d, c.nsplit, w.nkv, M, attn_smem, kv_bytes, at);
+
+            // K12+K13: o_proj + residual add
+            GemvArgs o{};
+            o.row_base = row_base; o.t = t;
+            o.W = lw.wo; o.N = w.H; o.K = (int)nq; o.x = c.attn_out.p; o.out = c.resid.p;
+            launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_o_resid", M, p_o, o);
+
+            // K14+K15: RMSNorm -> fused gate|up GEMV -> SiLU(gate) * up
+            GemvArgs g{};
+            g.row_base = row_base; g.t = t; g.eps = w.cfg.norm_eps;
+            g.W = lw.wgu; g.N = 2 * w.I; g.K = w.H; g.x = c.resid.p; g.norm_w = lw.ln2; g.out = c.act.p;
+            launch_gemv<PRO_RMSNORM, EPI_SILU>(lc, "gemv_gateup_silu", M, p_gu, g);
+
+            // K16: down_proj + residual add
+            GemvArgs dn{};
+            dn.row_base = row_base; dn.t = t;
+            dn.W = lw.wdown; dn.N = w.H; dn.K = w.I; dn.x = c.act.p; dn.out = c.resid.p;
+            launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_down_resid", M, p_down, dn);
+        }
+        if (has_last) {
+            // K17 (+K18): final RMSNorm -> lm_head -> f32 logits of the last position + arg-max partials
+            GemvArgs h{};
+            h.row_base = row_base; h.t = t; h.eps = w.cfg.norm_eps;
+            h.W = w.lm_head; h.N = w.V; h.K = w.H; h.x = c.resid.p; h.norm_w = w.final_norm;
+            h.out = c.logits.p; h.ldo = w.V; h.last_only = 1; h.amax_val = c.amax_val.p; h.amax_idx = c.amax_idx.p;
+            launch_gemv<PRO_RMSNORM, EPI_STORE>(lc, "gemv_lm_head", M, p_head, h);
+            launch(lc, "argmax_finalize", 0, argmax_finalize_kernel, dim3(1), dim3(256), 0, (const float*)c.amax_val.p,
+                   (const int*)c.amax_idx.p, p_head.grid, M, row_base, t, c.next_ids.p);
+        }
+    }
+    launch(lc, "advance_state", 0, advance_state_kernel, dim3(1), dim3(kMaxBatch), 0, c.state.p, b, t, loop_mode ? 1 : 0, c.ids.p,
+           (const uint32_t*)c.next_ids.p, loop_mode ? 1 : 0, loop_mode ? c.trace.p : (uint32_t*)nullptr,
+           loop_mode ? c.trace_pos.p : (int*)nullptr);
+}
+
+static GraphEntry& get_graph(fl_cache& c, int b, bool loop_mode) {
+    const GraphKey key{b, loop_mode ? 1 : 0};
+    auto it = c.graphs.find(key);
+    if (it != c.graphs.end()) return it->second;
+    LaunchCtx lc;
+    lc.stream = c.stream;
+    lc.pdl = !env_flag("FL_NO_PDL");
+    lc.capturing = true;
+    cudaGraph_t graph = nullptr;
+    FL_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        enqueue_forward(c, lc, b, 1, loop_mode);
+    } catch (...) {
+        cudaStreamEndCapture(c.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    FL_CUDA(cudaStreamEndCapture(c.stream, &graph));
+    GraphEntry e;
+    FL_CUDA(cudaGraphInstantiate(&e.exec, graph, 0));
+    FL_CUDA(cudaGraphDestroy(graph));
+    e.kernels = lc.captured;
+    return c.graphs[key] = e;
+}
+
+static void check_call(fl_cache& c, const uint32_t* ids, int b, int t, size_t rope_offset, int extra_steps) {
+    const Weights& w = *c.w;
+    FL_CHECK(!c.poisoned, FL_ERR_CUDA, "cache poisoned by an earlier CUDA error");
+    FL_CHECK(ids != nullptr, FL_ERR_INVALID, "ids is NULL");
+    FL_CHECK(b >= 1 && b <= c.max_batch && t >= 1, FL_ERR_INVALID, "bad batch / sequence length");
+    FL_CHECK(c.kv_len + t + extra_steps <= c.max_seq, FL_ERR_STATE, "KV cache full (kv_len + t > max_seq)");
+    FL_CHECK((int64_t)rope_offset + t + extra_steps <= w.max_pos, FL_ERR_INVALID, "RoPE position beyond max_position_embeddings");
+    // candle's Llama mask is t x t: a multi-token call on a non-empty cache is a shape error there
+    FL_CHECK(!(w.cfg.arch == FL_ARCH_LLAMA && t > 1 && c.kv_len != 0), FL_ERR_INVALID,
+             "Llama: multi-token forward needs an empty cache (candle builds a t x t mask)");
+    for (int i = 0; i < b * t; ++i) FL_CHECK(ids[i] < (uint32_t)w.V, FL_ERR_INVALID, "token id out of range");
+}
+
+static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t rope_offset) {
+    check_call(c, ids, b, t, rope_offset, 0);
+    std::memcpy(c.h_ids.p, ids, (size_t)b * t * 4);
+    FL_CUDA(cudaMemcpyAsync(c.ids.p, c.h_ids.p, (size_t)b * t * 4, cudaMemcpyHostToDevice, c.stream));
+    set_state_kernel<<<1, 1, 0, c.stream>>>(c.state.p, (int)rope_offset);
+    g_launches.fetch_add(1);
+    const bool use_graph = (t == 1) && !g_prof.on && !env_flag("FL_NO_GRAPH");
+    if (use_graph) {
+        GraphEntry& g = get_graph(c, b, false);
+        FL_CUDA(cudaGraphLaunch(g.exec, c.stream));
+        g_launches.fetch_add(g.kernels);
+    } else {
+        LaunchCtx lc;
+        lc.stream = c.stream;
+        lc.pdl = !env_flag("FL_NO_PDL");
+        enqueue_forward(c, lc, b, t, false);
+    }
+    c.kv_len += t;
+}
+
+}  // namespace fl
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------------
+using namespace fl;
+
+#define FL_API_BEGIN try {
+#define FL_API_END                                                 \
+    return FL_OK;                                                  \
+    }                                                              \
+    catch (const fl::Error& e) {                                   \
+        fl::g_last_error = e.what();                               \
+        return e.code;                                             \
+    }                                                              \
+    catch (const std::exception& e) {                              \
+        fl::g_last_error = std::string("internal: ") + e.what();   \
+        return FL_ERR_INVALID;                                     \
+    }
+
+static void use_device() {
+    const int dev = g_device.load();
+    FL_CHECK(dev >= 0, FL_ERR_STATE, "fl_init has not been called");
+    FL_CUDA(cudaSetDevice(dev));   // no thread-affine state: callers may hop OS threads between calls
+}
+
+extern "C" {
+
+FL_EXPORT const char* fl_last_error(void) { return g_last_error.c_str(); }
+FL_EXPORT int fl_version(void) { return 100; }
+
+FL_EXPORT int fl_init(int device) {
+    FL_API_BEGIN
+    int n = 0;
+    FL_CUDA(cudaGetDeviceCount(&n));
+    FL_CHECK(n > 0, FL_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    FL_CHECK(device >= 0 && device < n, FL_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    FL_CUDA(cudaGetDeviceProperties(&prop, device));
+    FL_CHECK(prop.major == 10, FL_ERR_UNSUPPORTED,
+             std::string("fastllm_b200 is built for sm_100a (B200) only; found ") + prop.name);
+    FL_CUDA(cudaSetDevice(device));
+    g_device.store(device);
+    FL_API_END
+}
+
+FL_EXPORT int fl_device_synchronize(void) {
+    FL_API_BEGIN
+    use_device();
+    FL_CUDA(cudaDeviceSynchronize());
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_create(const fl_config* cfg, fl_model** out) {
+    FL_API_BEGIN
+    FL_CHECK(cfg != nullptr && out != nullptr, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    validate_config(*cfg);
+    auto w = std::make_shared<Weights>();
+    w->cfg = *cfg;
+    w->device = g_device.load();
+    build_weights(*w);
+    *out = new fl_model{w};
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_put_tensor(fl_model* m, const char* name, int dtype, const int64_t* shape, int rank, const void* host_ptr) {
+    FL_API_BEGIN
+    FL_CHECK(m && name && shape && host_ptr, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    std::lock_guard<std::mutex> g(m->w->mu);
+    put_tensor(*m->w, name, dtype, shape, rank, host_ptr);
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_random_init(fl_model* m, uint64_t seed, float stdv) {
+    FL_API_BEGIN
+    FL_CHECK(m, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    std::lock_guard<std::mutex> g(m->w->mu);
+    random_init(*m->w, seed, stdv);
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_finalize(fl_model* m) {
+    FL_API_BEGIN
+    FL_CHECK(m, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    std::lock_guard<std::mutex> g(m->w->mu);
+    finalize(*m->w);
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_clone(fl_model* m, fl_model** out) {
+    FL_API_BEGIN
+    FL_CHECK(m && out, FL_ERR_INVALID, "NULL argument");
+    *out = new fl_model{m->w};
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_destroy(fl_model* m) {
+    FL_API_BEGIN
+    if (m) {
+        use_device();
+        delete m;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_model_weight_bytes(fl_model* m, uint64_t* streamed_bytes) {
+    FL_API_BEGIN
+    FL_CHECK(m && streamed_bytes, FL_ERR_INVALID, "NULL argument");
+    *streamed_bytes = m->w->streamed_bytes;
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_create(fl_model* m, int max_batch, int max_seq, fl_cache** out) {
+    FL_API_BEGIN
+    FL_CHECK(m && out, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    std::unique_ptr<fl_cache> c(new fl_cache);
+    c->w = m->w;
+    cache_create(*c, max_batch, max_seq);
+    *out = c.release();
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_reset(fl_cache* c) {
+    FL_API_BEGIN
+    FL_CHECK(c, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    reset_state_kernel<<<1, 256, 0, c->stream>>>(c->state.p, 0);
+    g_launches.fetch_add(1);
+    FL_CUDA(cudaStreamSynchronize(c->stream));
+    c->kv_len = 0;
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_kv_len(fl_cache* c, int* out) {
+    FL_API_BEGIN
+    FL_CHECK(c && out, FL_ERR_INVALID, "NULL argument");
+    *out = c->kv_len;
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_fill_synthetic(fl_cache* c, int batch, int kv_len, uint64_t seed) {
+    FL_API_BEGIN
+    FL_CHECK(c, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(batch >= 1 && batch <= c->max_batch && kv_len >= 0 && kv_len <= c->max_seq, FL_ERR_INVALID, "bad synthetic fill size");
+    use_device();
+    const RowMap ident{0, 0, 0, 0};
+    synth_fill_bf16_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->kpool.p, 1, (int64_t)c->kpool.n, tensor_seed(seed, "kv.k"), 0.5f, ident);
+    synth_fill_bf16_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->vpool.p, 1, (int64_t)c->vpool.n, tensor_seed(seed, "kv.v"), 0.5f, ident);
+    reset_state_kernel<<<1, 256, 0, c->stream>>>(c->state.p, kv_len);
+    g_launches.fetch_add(3);
+    FL_CUDA(cudaStreamSynchronize(c->stream));
+    c->kv_len = kv_len;
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_destroy(fl_cache* c) {
+    FL_API_BEGIN
+    if (c) {
+        use_device();
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        cache_destroy_graphs(*c);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_forward(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, float* logits_host) {
+    FL_API_BEGIN
+    FL_CHECK(m && c && logits_host, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    use_device();
+    try {
+        run_forward(*c, ids, b, t, rope_offset);
+        const size_t n = (size_t)b * c->w->V;
+        FL_CUDA(cudaMemcpyAsync(c->h_logits.p, c->logits.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        FL_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(logits_host, c->h_logits.p, n * 4);
+    } catch (const fl::Error& e) {
+        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        throw;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_forward_greedy(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, uint32_t* next_ids) {
+    FL_API_BEGIN
+    FL_CHECK(m && c && next_ids, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    use_device();
+    try {
+        run_forward(*c, ids, b, t, rope_offset);
+        FL_CUDA(cudaMemcpyAsync(c->h_ids.p, c->next_ids.p, (size_t)b * 4, cudaMemcpyDeviceToHost, c->stream));
+        FL_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(next_ids, c->h_ids.p, (size_t)b * 4);
+    } catch (const fl::Error& e) {
+        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        throw;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* first_ids, int b, size_t rope_offset, int steps,
+                          uint32_t* out_ids, float* elapsed_ms) {
+    FL_API_BEGIN
+    FL_CHECK(m && c, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    FL_CHECK(steps >= 1, FL_ERR_INVALID, "steps must be >= 1");
+    use_device();
+    try {
+        check_call(*c, first_ids, b, 1, rope_offset, steps - 1);
+        if (c->trace_cap < (size_t)steps * b) {
+            c->trace.alloc((size_t)steps * b);
+            c->trace_cap = (size_t)steps * b;
+            cache_destroy_graphs(*c);   // captured graphs hold the old trace pointer
+        }
+        std::memcpy(c->h_ids.p, first_ids, (size_t)b * 4);
+        FL_CUDA(cudaMemcpyAsync(c->ids.p, c->h_ids.p, (size_t)b * 4, cudaMemcpyHostToDevice, c->stream));
+        FL_CUDA(cudaMemsetAsync(c->trace_pos.p, 0, 4, c->stream));
+        set_state_kernel<<<1, 1, 0, c->stream>>>(c->state.p, (int)rope_offset);
+        g_launches.fetch_add(1);
+        const bool use_graph = !g_prof.on && !env_flag("FL_NO_GRAPH");
+        GraphEntry* g = use_graph ? &get_graph(*c, b, true) : nullptr;
+        cudaEvent_t e0, e1;
+        FL_CUDA(cudaEventCreate(&e0));
+        FL_CUDA(cudaEventCreate(&e1));
+        FL_CUDA(cudaEventRecord(e0, c->stream));
+        for (int s = 0; s < steps; ++s) {
+            if (g) {
+                FL_CUDA(cudaGraphLaunch(g->exec, c->stream));
+                g_launches.fetch_add(g->kernels);
+            } else {
+                LaunchCtx lc;
+                lc.stream = c->stream;
+                lc.pdl = !env_flag("FL_NO_PDL");
+                enqueue_forward(*c, lc, b, 1, true);
+            }
+            c->kv_len += 1;
+        }
+        FL_CUDA(cudaEventRecord(e1, c->stream));
+        FL_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        FL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (elapsed_ms) *elapsed_ms = ms;
+        if (out_ids) FL_CUDA(cudaMemcpy(out_ids, c->trace.p, (size_t)steps * b * 4, cudaMemcpyDeviceToHost));
+    } catch (const fl::Error& e) {
+        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        throw;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_embed(fl_model* m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out) {
+    FL_API_BEGIN
+    (void)m; (void)ids; (void)mask; (void)b; (void)t; (void)out;
+    throw fl::Error(FL_ERR_UNSUPPORTED, "fl_embed: BERT encoder not built yet");
+    FL_API_END
+}
+
+FL_EXPORT int fl_comm_unique_id(void* out) {
+    FL_API_BEGIN
+    (void)out;
+    throw fl::Error(FL_ERR_UNSUPPORTED, "tensor parallelism not built yet");
+    FL_API_END
+}
+FL_EXPORT int fl_comm_init(int rank, int world, const void* id) {
+    FL_API_BEGIN
+    (void)rank; (void)world; (void)id;
+    throw fl::Error(FL_ERR_UNSUPPORTED, "tensor parallelism not built yet");
+    FL_API_END
+}
+FL_EXPORT int fl_comm_destroy(void) { return FL_OK; }
+
+FL_EXPORT int fl_prof_begin(void) {
+    FL_API_BEGIN
+    use_device();
+    FL_CUDA(cudaDeviceSynchronize());
+    g_prof.entries.clear();
+    g_prof.on = true;
+    FL_API_END
+}
+
+FL_EXPORT int fl_prof_end(char* json_out, size_t cap) {
+    FL_API_BEGIN
+    use_device();
+    FL_CUDA(cudaDeviceSynchronize());
+    g_prof.on = false;
+    struct Agg { uint64_t n = 0, bytes = 0; double ms = 0; };
+    std::map<std::string, Agg> agg;
+    std::vector<std::string> order;
+    for (auto& e : g_prof.entries) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.e0, e.e1);
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+        if (!agg.count(e.tag)) order.push_back(e.tag);
+        Agg& a = agg[e.tag];
+        a.n++; a.bytes += e.bytes; a.ms += ms;
+    }
+    g_prof.entries.clear();
+    std::ostringstream os;
+    os << "[";
+    for (size_t i = 0; i < order.size(); ++i) {
+        const Agg& a = agg[order[i]];
+        os << (i ? "," : "") << "{\"kernel\":\"" << order[i] << "\",\"launches\":" << a.n << ",\"ms\":" << a.ms << ",\"bytes\":" << a.bytes << "}";
+    }
+    os << "]";
+    const std::string s = os.str();
+    FL_CHECK(json_out && cap > s.size(), FL_ERR_INVALID, "profile buffer too small");
+    std::memcpy(json_out, s.c_str(), s.size() + 1);
+    FL_API_END
+}
+
+FL_EXPORT int fl_launch_count(uint64_t* n) {
+    FL_API_BEGIN
+    FL_CHECK(n, FL_ERR_INVALID, "NULL argument");
+    *n = g_launches.load();
+    FL_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Model / cache objects behind the C ABI (declarations).
+#pragma once
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/fastllm_b200.h"
+#include "gemv.cuh"
+#include "runtime.cuh"
+
+namespace fl {
+
+struct LayerW {
+    uint16_t* wqkv = nullptr;   // [(nh + 2 nkv) d, H]  q | k | v rows; q/k rows pair-permuted per head for RoPE
+    float* bqkv = nullptr;      // [(nh + 2 nkv) d] or null (same permutation)
+    uint16_t* wo = nullptr;     // [H, nh d]
+    uint16_t* wgu = nullptr;    // [2 I, H]  row 2j = gate_j, row 2j+1 = up_j
+    uint16_t* wdown = nullptr;  // [H, I]
+    float* ln1 = nullptr;       // [H]
+    float* ln2 = nullptr;       // [H]
+};
+
+// Immutable after finalize; shared (ref-counted) between fl_model clones and their caches.
+struct Weights {
+    fl_config cfg{};
+    int H = 0, I = 0, V = 0, L = 0, nh = 0, nkv = 0, d = 0, max_pos = 0;
+    int nqkv = 0;               // (nh + 2 nkv) * d
+    int device = 0;
+    DevBuf<uint8_t> slab;       // every weight lives in this one allocation
+    uint16_t* embed = nullptr;  // [V, H]
+    uint16_t* lm_head = nullptr;
+    float* final_norm = nullptr;
+    std::vector<LayerW> layers;
+    float* rope_cos = nullptr;  // [max_pos, d/2]
+    float* rope_sin = nullptr;
+    std::set<std::string> have; // tensor names that arrived
+    bool lm_head_loaded = false;
+    bool finalized = false;
+    uint64_t streamed_bytes = 0;
+    std::mutex mu;
+};
+
+struct GraphKey {
+    int b;
+    int loop;
+    bool operator<(const GraphKey& o) const { return b != o.b ? b < o.b : loop < o.loop; }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernels = 0;
+};
+
+}  // namespace fl
+
+struct fl_model {
+    std::shared_ptr<fl::Weights> w;
+};
+
+struct fl_cache {
+    std::shared_ptr<fl::Weights> w;
+    cudaStream_t stream = nullptr;
+    int max_batch = 0, max_seq = 0, pages_per_seq = 0, nsplit = 1;
+    int kv_len = 0;                       // host mirror of StepState.kv_base (same for every sequence)
+    fl::DevBuf<fl::StepState> state;
+    fl::DevBuf<int> page_table;           // [max_batch, pages_per_seq]
+    fl::DevBuf<uint16_t> kpool, vpool;    // [L][pages][nkv][kKvPage][d]
+    size_t layer_pool_elems = 0;
+    fl::DevBuf<uint32_t> ids, next_ids, trace;
+    fl::DevBuf<int> trace_pos;
+    fl::DevBuf<float> resid, q, attn_out, act, logits, part_acc, part_ml, amax_val;
+    fl::DevBuf<int> amax_idx, counters;
+    fl::PinnedBuf<uint32_t> h_ids;
+    fl::PinnedBuf<float> h_logits;
+    size_t trace_cap = 0;
+    int amax_parts = 0;
+    std::map<fl::GraphKey, fl::GraphEntry> graphs;
+    bool poisoned = false;
+};

@@ -1,0 +1,388 @@
+"""Host-side mirror of the reference's trait-based model API over the C ABI.
+
+The reference is Rust and there is no Rust toolchain in this image, so the drop-in host side ships twice:
+  * `host/fastllm_host.hpp` -- the C++ mirror (compiled, what INTEGRATION.md's Rust shim is a transliteration of);
+  * this module -- the same interface in Python, used by tests/ and bench.py so the parity tests read like the
+    reference's own tests (same names, same argument meaning, same offset rules, same error behaviour).
+
+Reference interfaces mirrored (paths under /root/reference/src/models):
+  ModelInitializer {initialize_model, initialize_cache, forward}     model_initializer.rs:6-22
+  ModelCache {increment_offset, reset, get_offset}                   cache.rs:5-10
+  LlamaWithConfig / LlamaCache                                       llama.rs:52-149
+  MistralWithConfig / MistralCache                                   mistral.rs:16-236
+  QwenWithConfig / QwenCache                                         qwen.rs:12-151
+  Model::generate (greedy path)                                      mod.rs:363-463
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import FastllmError, FlConfig
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# thin RAII handles over the C ABI
+# --------------------------------------------------------------------------------------------------------------------
+class DeviceModel:
+    """fl_model*: device weights (shared between clones)."""
+
+    def __init__(self, cfg: FlConfig, device: int = 0, _handle=None):
+        _lib.init(device)
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = device
+        if _handle is None:
+            h = C.c_void_p()
+            _lib.check(self.lib.fl_model_create(C.byref(cfg), C.byref(h)))
+            self.h = h
+        else:
+            self.h = _handle
+
+    def put_tensor(self, name: str, arr: np.ndarray):
+        if arr.dtype == np.float32:
+            dt = _lib.FL_DTYPE_F32
+        elif arr.dtype == np.float16:
+            dt = _lib.FL_DTYPE_F16
+        elif arr.dtype == np.uint16:        # raw bf16 bit patterns
+            dt = _lib.FL_DTYPE_BF16
+        else:
+            raise FastllmError(-1, f"unsupported dtype {arr.dtype} for {name}")
+        arr = np.ascontiguousarray(arr)
+        shape = (C.c_int64 * arr.ndim)(*arr.shape)
+        _lib.check(self.lib.fl_model_put_tensor(self.h, name.encode(), dt, shape, arr.ndim, arr.ctypes.data_as(C.c_void_p)))
+
+    def random_init(self, seed: int = 0, std: float = 0.02):
+        _lib.check(self.lib.fl_model_random_init(self.h, seed, std))
+
+    def finalize(self):
+        _lib.check(self.lib.fl_model_finalize(self.h))
+
+    def clone(self) -> "DeviceModel":
+        h = C.c_void_p()
+        _lib.check(self.lib.fl_model_clone(self.h, C.byref(h)))
+        return DeviceModel(self.cfg, self.device, _handle=h)
+
+    def streamed_bytes(self) -> int:
+        n = C.c_uint64()
+        _lib.check(self.lib.fl_model_weight_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.fl_model_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class DeviceCache:
+    """fl_cache*: paged KV cache + per-cache stream/workspaces."""
+
+    def __init__(self, model: DeviceModel, max_batch: int, max_seq: int):
+        self.model, self.lib = model, model.lib
+        self.max_batch, self.max_seq = max_batch, max_seq
+        self.vocab = model.cfg.vocab_size
+        h = C.c_void_p()
+        _lib.check(self.lib.fl_cache_create(model.h, max_batch, max_seq, C.byref(h)))
+        self.h = h
+
+    def reset(self):
+        _lib.check(self.lib.fl_cache_reset(self.h))
+
+    def kv_len(self) -> int:
+        n = C.c_int()
+        _lib.check(self.lib.fl_cache_kv_len(self.h, C.byref(n)))
+        return n.value
+
+    def fill_synthetic(self, batch: int, kv_len: int, seed: int = 3):
+        _lib.check(self.lib.fl_cache_fill_synthetic(self.h, batch, kv_len, seed))
+
+    def forward(self, ids: np.ndarray, rope_offset: int) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if ids.ndim != 2:
+            raise FastllmError(-1, f"input must be [batch, seq], got shape {ids.shape}")   # input.dims2()? in the reference
+        b, t = ids.shape
+        out = np.empty((b, self.vocab), dtype=np.float32)
+        _lib.check(self.lib.fl_forward(self.model.h, self.h, ids.ctypes.data_as(C.c_void_p), b, t, rope_offset,
+                                       out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def forward_greedy(self, ids: np.ndarray, rope_offset: int) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        b, t = ids.shape
+        out = np.empty((b,), dtype=np.uint32)
+        _lib.check(self.lib.fl_forward_greedy(self.model.h, self.h, ids.ctypes.data_as(C.c_void_p), b, t, rope_offset,
+                                              out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def decode_greedy_loop(self, first_ids: np.ndarray, rope_offset: int, steps: int):
+        first = np.ascontiguousarray(first_ids, dtype=np.uint32).reshape(-1)
+        b = first.shape[0]
+        out = np.empty((steps, b), dtype=np.uint32)
+        ms = C.c_float()
+        _lib.check(self.lib.fl_decode_greedy_loop(self.model.h, self.h, first.ctypes.data_as(C.c_void_p), b, rope_offset,
+                                                  steps, out.ctypes.data_as(C.c_void_p), C.byref(ms)))
+        return out, ms.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.fl_cache_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def prof_begin():
+    _lib.check(_lib.load().fl_prof_begin())
+
+
+def prof_end() -> list:
+    buf = C.create_string_buffer(1 << 16)
+    _lib.check(_lib.load().fl_prof_end(buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
+def launch_count() -> int:
+    n = C.c_uint64()
+    _lib.check(_lib.load().fl_launch_count(C.byref(n)))
+    return n.value
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# configs (what the adapters deserialize from config.json)
+# --------------------------------------------------------------------------------------------------------------------
+@dataclass
+class ConfigFile:
+    """llama.rs:17-29 / mistral.rs:78-91 / models/config.rs:5-18 (BaseModelConfig)."""
+    hidden_size: int
+    intermediate_size: int
+    vocab_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int | None = None
+    rms_norm_eps: float = 1e-5
+    rope_theta: float | None = None
+    max_position_embeddings: int | None = None
+    sliding_window: int | None = None
+    torch_dtype: str | None = None     # never consulted by the reference (huggingface.rs:132)
+
+
+def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: int, qkv_bias: bool) -> FlConfig:
+    c = FlConfig()
+    c.arch = _lib.FL_ARCH[arch]
+    c.hidden_size, c.intermediate_size, c.vocab_size = cf.hidden_size, cf.intermediate_size, cf.vocab_size
+    c.num_hidden_layers, c.num_attention_heads = cf.num_hidden_layers, cf.num_attention_heads
+    c.num_key_value_heads = cf.num_key_value_heads or cf.num_attention_heads
+    c.max_position_embeddings = cf.max_position_embeddings or default_max_pos
+    c.sliding_window = sliding_window
+    c.qkv_bias = 1 if qkv_bias else 0
+    c.norm_eps = cf.rms_norm_eps
+    c.rope_theta = float(cf.rope_theta if cf.rope_theta is not None else 10000.0)
+    c.tp_rank, c.tp_size = 0, 1
+    return c
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ModelCache implementations
+# --------------------------------------------------------------------------------------------------------------------
+class _OffsetCache:
+    """ModelCache (cache.rs:5-10): increment_offset / reset / get_offset."""
+
+    def __init__(self):
+        self.seqlen_offset = 0
+
+    def increment_offset(self):
+        self.seqlen_offset += 1
+
+    def reset(self):
+        self.seqlen_offset = 0
+
+    def get_offset(self) -> int:
+        return self.seqlen_offset
+
+
+class LlamaCache(_OffsetCache):
+    """llama.rs:61-92.  In the reference this owns candle's KV `Cache`; here it owns the device KV cache, created lazily
+    on the first forward because initialize_cache(device, dtype) gets no model argument."""
+
+    def __init__(self):
+        super().__init__()
+        self.inner: DeviceCache | None = None
+
+
+class MistralCache(_OffsetCache):
+    """mistral.rs:16-47: only the offset; the KV lives inside the model object."""
+
+
+class QwenCache(_OffsetCache):
+    """qwen.rs:58-87."""
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ModelInitializer implementations
+# --------------------------------------------------------------------------------------------------------------------
+class _CausalBase:
+    arch = ""
+    family = ""
+    architectures: tuple = ()
+    KV_CAPACITY = 4096        # tokens of KV a cache can hold (the reference grows by `cat`; we preallocate pages)
+    MAX_BATCH = 1
+
+    def __init__(self, dev: DeviceModel, cfg: FlConfig):
+        self.dev, self.cfg = dev, cfg
+
+    @classmethod
+    def _to_fl_config(cls, config: ConfigFile) -> FlConfig:
+        raise NotImplementedError
+
+    @classmethod
+    def initialize_model(cls, config: ConfigFile, tensors: dict | None, dtype="bf16", device: int = 0, *, random_seed=None,
+                         std: float = 0.02):
+        """ModelInitializer::initialize_model(&Config, HashMap<String,Tensor>, DType, &Device) -> (Self, Cache).
+        `tensors` maps HF names to numpy arrays (f32 / f16 / uint16 bf16 bits); they are rounded to bf16 as
+        VarBuilder::from_tensors(.., BF16, ..) would (main.rs:120).  tensors=None + random_seed = synthetic weights."""
+        cfg = cls._to_fl_config(config)
+        dev = DeviceModel(cfg, device)
+        if tensors is None:
+            dev.random_init(0 if random_seed is None else random_seed, std)
+        else:
+            for name, arr in tensors.items():
+                dev.put_tensor(name, np.asarray(arr))
+        dev.finalize()
+        self = cls(dev, cfg)
+        return self, cls.initialize_cache(device, dtype)
+
+    @classmethod
+    def get_family(cls) -> str:
+        return cls.family
+
+    @classmethod
+    def supports_architecture(cls, architecture: str) -> bool:
+        return architecture in cls.architectures
+
+    def _capacity(self) -> int:
+        return min(self.KV_CAPACITY, self.cfg.max_position_embeddings)
+
+
+class LlamaWithConfig(_CausalBase):
+    """llama.rs:52-160."""
+    arch, family, architectures = "llama", "Llama", ("LlamaForCausalLM",)
+
+    @classmethod
+    def _to_fl_config(cls, cf: ConfigFile) -> FlConfig:
+        # llama.rs:31-50: rope_theta default 1e4, max_position_embeddings default 4096, no sliding window, no bias
+        return _fl_config("llama", cf, 4096, 0, False)
+
+    @staticmethod
+    def initialize_cache(device=0, dtype="bf16") -> LlamaCache:
+        return LlamaCache()
+
+    def forward(self, input: np.ndarray, pos: int, cache: LlamaCache) -> np.ndarray:
+        """llama.rs:147-149: model.forward(input, pos, &mut cache.inner) -> f32 [b, V]."""
+        ids = np.asarray(input)
+        if cache.inner is None:
+            cache.inner = DeviceCache(self.dev, max(self.MAX_BATCH, ids.shape[0] if ids.ndim == 2 else 1), self._capacity())
+        return cache.inner.forward(ids, pos)
+
+    def clone(self) -> "LlamaWithConfig":
+        return LlamaWithConfig(self.dev.clone(), self.cfg)
+
+
+class MistralWithConfig(_CausalBase):
+    """mistral.rs:49-248.  The KV cache lives in the model object (one per clone), as in candle's mistral::Model."""
+    arch, family, architectures = "mistral", "Mistral", ("MistralForCausalLM",)
+    cache_cls = MistralCache
+
+    def __init__(self, dev: DeviceModel, cfg: FlConfig):
+        super().__init__(dev, cfg)
+        self._kv: DeviceCache | None = None
+
+    @classmethod
+    def _to_fl_config(cls, cf: ConfigFile) -> FlConfig:
+        # mistral.rs:93-154: asserts on head dims / GQA (raised as FastllmError by fl_model_create),
+        # sliding_window = Some(cfg.unwrap_or(4096)), max_position_embeddings default 32768
+        return _fl_config("mistral", cf, 32768, cf.sliding_window if cf.sliding_window is not None else 4096, False)
+
+    @classmethod
+    def initialize_cache(cls, device=0, dtype="bf16"):
+        return cls.cache_cls()
+
+    def clear_kv_cache(self):
+        if self._kv is not None:
+            self._kv.reset()
+
+    def forward(self, input: np.ndarray, _pos: int, cache) -> np.ndarray:
+        """mistral.rs:206-236 / qwen.rs:129-145: `_pos` ignored; KV cleared when the offset is 0; RoPE offset = the
+        cache's seqlen_offset, which then grows by ONE per call (not by seq_len).  Returns [b, 1, V]."""
+        ids = np.asarray(input)
+        if ids.ndim != 2:
+            raise FastllmError(-1, f"input must be [batch, seq], got shape {ids.shape}")
+        if self._kv is None:
+            self._kv = DeviceCache(self.dev, max(self.MAX_BATCH, ids.shape[0]), self._capacity())
+        if cache.get_offset() == 0:
+            self.clear_kv_cache()
+        out = self._kv.forward(ids, cache.get_offset())
+        cache.increment_offset()
+        return out[:, None, :]
+
+    def clone(self):
+        return type(self)(self.dev.clone(), self.cfg)
+
+
+class QwenWithConfig(MistralWithConfig):
+    """qwen.rs:12-186 (ModelForward::forward_pass + clear_cache; q/k/v bias)."""
+    arch, family = "qwen2", "Qwen"
+    architectures = ("Qwen2ForCausalLM", "Qwen2_5_VLForConditionalGeneration")
+    cache_cls = QwenCache
+
+    @classmethod
+    def _to_fl_config(cls, cf: ConfigFile) -> FlConfig:
+        # qwen.rs:30-56: sliding_window.unwrap_or(4096), max_position_embeddings default 32768, rope default 1e4
+        return _fl_config("qwen2", cf, 32768, cf.sliding_window if cf.sliding_window is not None else 4096, True)
+
+    def forward_pass(self, input, cache):
+        return self.forward(input, 0, cache)
+
+    def clear_cache(self):
+        self.clear_kv_cache()
+
+
+def sample_argmax(logits: np.ndarray) -> int:
+    """LogitsProcessor::sample with temperature None/<1e-7: arg-max, LAST index among equal maxima (mod.rs:425-428)."""
+    v = np.asarray(logits, dtype=np.float32).reshape(-1)
+    return int(np.flatnonzero(v == v.max())[-1])
+
+
+class Model:
+    """Model<M> (mod.rs:342-464) without the tokenizer: prompts are already token ids."""
+
+    def __init__(self, model, cache, eos_token_id: int | None = 2):
+        self.model, self.cache, self.eos_token_id = model, cache, eos_token_id
+
+    def generate(self, prompt_ids, max_tokens: int, temperature: float = 0.0, return_logits: bool = False):
+        if temperature >= 1e-7:
+            raise FastllmError(-5, "temperature sampling (candle WeightedIndex/StdRng) is SURVEY.md section 8f item 1, not built")
+        self.cache = self.model.initialize_cache()                       # mod.rs:370
+        ids = np.asarray(prompt_ids, dtype=np.uint32).reshape(1, -1)    # mod.rs:386-394
+        pos = 0
+        logits = self.model.forward(ids, pos, self.cache)               # mod.rs:402-405
+        pos += ids.shape[1]
+        out, trace = [], []
+        for _ in range(max_tokens):                                      # mod.rs:411-453
+            last = np.asarray(logits)[0].reshape(-1)                     # logits.get(0)?.flatten_all()?
+            if return_logits:
+                trace.append(last.copy())
+            tok = sample_argmax(last)
+            if self.eos_token_id is not None and tok == self.eos_token_id:
+                break                                                    # EOS: break before emitting (mod.rs:431-436)
+            out.append(tok)
+            logits = self.model.forward(np.array([[tok]], dtype=np.uint32), pos, self.cache)
+            pos += 1
+        return (out, trace) if return_logits else out

@@ -80,13 +80,17 @@ def rope_tables(head_dim: int, max_pos: int, theta: float, theta_pow_f64: bool):
     Mistral/Qwen2 (RotaryEmbedding::new): theta is f64 and inv_freq = 1f32 / theta.powf(i as f64 / d as f64) as f32.
     Then freqs = positions(f32) outer inv_freq (f32 matmul), cos/sin in f32."""
     i = np.arange(0, head_dim, 2)
+    # libm powf / cosf / sinf are (almost always) correctly rounded; model them as f64 evaluation rounded to f32,
+    # which is also what fastllm_b200/csrc/model.cu does on the host, so both sides hold identical tables.
     if theta_pow_f64:
-        inv = (F32(1.0) / np.power(np.float64(theta), i.astype(np.float64) / np.float64(head_dim)).astype(F32)).astype(F32)
+        p = np.power(np.float64(theta), i.astype(np.float64) / np.float64(head_dim)).astype(F32)
     else:
-        inv = (F32(1.0) / np.power(F32(theta), (i.astype(F32) / F32(head_dim)).astype(F32)).astype(F32)).astype(F32)
+        e = (i.astype(F32) / F32(head_dim)).astype(F32)
+        p = np.power(np.float64(F32(theta)), e.astype(np.float64)).astype(F32)
+    inv = (F32(1.0) / p).astype(F32)
     pos = np.arange(max_pos, dtype=F32)[:, None]
     freqs = (pos * inv[None, :]).astype(F32)
-    return np.cos(freqs).astype(F32), np.sin(freqs).astype(F32)
+    return np.cos(freqs.astype(np.float64)).astype(F32), np.sin(freqs.astype(np.float64)).astype(F32)
 
 
 def rope_rotate_half(x: np.ndarray, cos: np.ndarray, sin: np.ndarray) -> np.ndarray:
