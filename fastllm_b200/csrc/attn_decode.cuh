@@ -218,21 +218,42 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < D) {
-        for (int h = 0; h < n_rep; ++h) {
-            const size_t base = ((size_t)row * a.nh + kvh * n_rep + h) * nsplit;
-            float mstar = -INFINITY;
-            for (int s = 0; s < nsplit; ++s) mstar = fmaxf(mstar, __ldcg(a.part_ml + (base + s) * 2));
-            float num = 0.f, den = 0.f;
-            for (int s = 0; s < nsplit; ++s) {
-                const float ms = __ldcg(a.part_ml + (base + s) * 2);
-                if (ms == -INFINITY) continue;
-                const float w = expf(ms - mstar);
-                den = fmaf(w, __ldcg(a.part_ml + (base + s) * 2 + 1), den);
-                num = fmaf(w, __ldcg(a.part_acc + (base + s) * D + tid), num);
-            }
-            a.out[(size_t)row * a.nh * D + (size_t)(kvh * n_rep + h) * D + tid] = num / den;
+    // The merge is latency-bound (one CTA, L2 reads): spread it over all threads and keep many loads in flight.
+    float* cm = reinterpret_cast<float*>(dsm);            // [n_rep][nsplit] split weights, reusing the staging buffer
+    float* cden = cm + kAttnMaxRep * nsplit;              // [n_rep]
+    __syncthreads();
+    for (int h = warp; h < n_rep; h += kAttnThreads / 32) {
+        const size_t base = ((size_t)row * a.nh + kvh * n_rep + h) * nsplit;
+        float mstar = -INFINITY;
+        for (int s = lane; s < nsplit; s += 32) mstar = fmaxf(mstar, __ldcg(a.part_ml + (base + s) * 2));
+        mstar = warp_max(mstar);
+        float den = 0.f;
+        for (int s = lane; s < nsplit; s += 32) {
+            const float ms = __ldcg(a.part_ml + (base + s) * 2);
+            const float w = (ms == -INFINITY) ? 0.f : expf(ms - mstar);
+            cm[h * nsplit + s] = w;
+            den = fmaf(w, __ldcg(a.part_ml + (base + s) * 2 + 1), den);
         }
+        den = warp_sum(den);
+        if (lane == 0) cden[h] = den;
+    }
+    __syncthreads();
+    constexpr int D4 = D / 4;
+    for (int i = tid; i < n_rep * D4; i += kAttnThreads) {
+        const int h = i / D4, c4 = i % D4;
+        const float4* src = reinterpret_cast<const float4*>(a.part_acc + ((size_t)row * a.nh + kvh * n_rep + h) * nsplit * D) + c4;
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int s = 0; s < nsplit; ++s) {
+            const float w = cm[h * nsplit + s];
+            if (w != 0.f) {                                // empty splits hold unwritten (possibly non-finite) partials
+                const float4 v = __ldcg(src + (size_t)s * D4);
+                num.x = fmaf(w, v.x, num.x); num.y = fmaf(w, v.y, num.y); num.z = fmaf(w, v.z, num.z); num.w = fmaf(w, v.w, num.w);
+            }
+        }
+        const float den = cden[h];
+        float4 o = make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
+        reinterpret_cast<float4*>(a.out + (size_t)row * a.nh * D + (size_t)(kvh * n_rep + h) * D)[c4] = o;
     }
     if (tid == 0) a.counters[row * a.nkv + kvh] = 0;
 }

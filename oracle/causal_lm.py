@@ -99,9 +99,13 @@ def synth_weights(cfg: CausalLMConfig, seed: int = 0, std: float = 0.02) -> dict
 class CausalLM:
     """One candle model instance: weights + (for Mistral/Qwen2) the model-internal KV cache."""
 
-    def __init__(self, cfg: CausalLMConfig, weights: dict, rope_len: int | None = None):
+    def __init__(self, cfg: CausalLMConfig, weights: dict, rope_len: int | None = None, kv_dtype: str = "f32"):
+        """kv_dtype="bf16" rounds K (after RoPE) and V to bf16 before they enter the cache -- what the reference's
+        server build does implicitly (KV in model dtype BF16, main.rs:120) and what the product's paged cache stores.
+        The default "f32" is the pure candle-CPU-F32 restatement."""
         cfg.validate()
         self.cfg = cfg
+        self.kv_dtype = kv_dtype
         self.w = {k: np.ascontiguousarray(v, dtype=F32) for k, v in weights.items()}
         n = rope_len or cfg.max_position_embeddings
         # Llama: f32 theta pow; Mistral/Qwen2/Mixtral: f64 theta pow then f32 (see candle_ops.rope_tables)
@@ -147,6 +151,8 @@ class CausalLM:
         cos, sin = self.cos[rope_offset:rope_offset + t], self.sin[rope_offset:rope_offset + t]
         q = ops.rope_rotate_half(q, cos, sin)
         k = ops.rope_rotate_half(k, cos, sin)
+        if self.kv_dtype == "bf16":
+            k, v = synth.round_bf16(k), synth.round_bf16(v)
         prev = self.kv[li]
         kv_before = 0 if prev is None else prev[0].shape[2]
         if prev is not None:                       # Tensor::cat(&[prev, new], 2)  (K6)
