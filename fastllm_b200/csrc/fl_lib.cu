@@ -4,6 +4,7 @@
 #include <sstream>
 
 #include "attn_decode.cuh"
+#include "decode_persistent.cuh"
 #include "elementwise.cuh"
 #include "gemv.cuh"
 #include "model.cuh"
@@ -332,6 +333,11 @@ static void finalize(Weights& w) {
         }
     FL_CUDA(cudaMemcpy(w.rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
     FL_CUDA(cudaMemcpy(w.rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<PkLayer> pk(w.L);
+    for (int l = 0; l < w.L; ++l)
+        pk[l] = PkLayer{w.layers[l].wqkv, w.layers[l].bqkv, w.layers[l].wo, w.layers[l].wgu, w.layers[l].wdown, w.layers[l].ln1, w.layers[l].ln2};
+    w.pk_layers.alloc(w.L);
+    FL_CUDA(cudaMemcpy(w.pk_layers.p, pk.data(), pk.size() * sizeof(PkLayer), cudaMemcpyHostToDevice));
     w.finalized = true;
 }
 
@@ -339,6 +345,97 @@ static void finalize(Weights& w) {
 // Cache + forward
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kPassRows = 2;   // activation rows per CUDA-core GEMV pass
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent batch-1 decode kernel: plan + launch
+// ------------------------------------------------------------------------------------------------------------------
+static void plan_persistent(fl_cache& c) {
+    const Weights& w = *c.w;
+    PkPlan& p = c.pk;
+    p.ok = false;
+    if (env_flag("FL_NO_PERSISTENT")) return;
+    const int nq = w.nh * w.d;
+    if (!(w.d == 64 || w.d == 128)) return;
+    if (w.H < 2048 || nq < 2048 || w.I < 2048) return;      // every row must span all 256 consumer threads
+    if (w.H % 8 || nq % 8 || w.I % 8 || w.nqkv % 2 || w.V % 2) return;
+    const int n_rep = w.nh / w.nkv;
+    int kmax = std::max(w.H, std::max(nq, w.I));
+    p.xs_floats = (int)align_up((size_t)std::max(kmax, 8 * w.d * (1 + n_rep) + 8 * kNumSMs + 8), 4);
+    int rows = 0;
+    for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) rows = std::max(rows, 2 * ((N / 2 + kNumSMs - 1) / kNumSMs + 1));
+    p.partial_rows = rows;
+    const size_t fixed = (size_t)p.xs_floats * 4 + (size_t)p.partial_rows * kPkConsumerWarps * 4 + (size_t)kAttnMaxRep * kKvPage * 4 + 64 * 4;
+    const size_t avail = 232448 - 2048;   // 227 KB opt-in limit minus static shared memory and slack
+    if (fixed + 2 * (size_t)kPkStageBytes > avail) return;
+    p.nstages = (int)std::min<size_t>(kPkMaxStages, (avail - fixed) / kPkStageBytes);
+    p.smem = (size_t)p.nstages * kPkStageBytes + fixed;
+    p.nsplit = std::max(1, std::min(c.pages_per_seq, kNumSMs / w.nkv));
+    if (p.nsplit > c.nsplit) p.nsplit = c.nsplit;            // partial buffers are sized for c.nsplit
+    int coop = 0;
+    FL_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, w.device));
+    if (!coop) return;
+    if (w.d == 64)
+        FL_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    else
+        FL_CUDA(cudaFuncSetAttribute(decode_persistent_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    c.gbar.alloc(1, true);
+    p.ok = true;
+}
+
+// Enqueue `nsteps` batch-1 decode steps as ONE cooperative launch on the cache's stream.
+static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
+    const Weights& w = *c.w;
+    PkArgs a{};
+    a.layers = w.pk_layers.p; a.L = w.L; a.embed = w.embed; a.lm_head = w.lm_head; a.final_norm = w.final_norm;
+    a.H = w.H; a.I = w.I; a.V = w.V; a.nh = w.nh; a.nkv = w.nkv; a.d = w.d; a.nqkv = w.nqkv; a.max_pos = w.max_pos;
+    a.eps = w.cfg.norm_eps; a.qscale = (float)(1.0 / std::sqrt((double)w.d));
+    a.rope_cos = w.rope_cos; a.rope_sin = w.rope_sin;
+    a.kpool = c.kpool.p; a.vpool = c.vpool.p; a.layer_pool_elems = c.layer_pool_elems; a.page_table = c.page_table.p;
+    a.state = c.state.p; a.resid = c.resid.p; a.q = c.q.p; a.attn_out = c.attn_out.p; a.act = c.act.p; a.logits = c.logits.p;
+    a.part_acc = c.part_acc.p; a.part_ml = c.part_ml.p; a.counters = c.counters.p; a.nsplit = c.pk.nsplit;
+    a.amax_val = c.amax_val.p; a.amax_idx = c.amax_idx.p; a.ids = c.ids.p; a.next_ids = c.next_ids.p;
+    a.trace = feedback ? c.trace.p : nullptr; a.trace_pos = c.trace_pos.p; a.gbar = c.gbar.p;
+    a.nsteps = nsteps; a.feedback = feedback ? 1 : 0; a.nstages = c.pk.nstages; a.xs_floats = c.pk.xs_floats;
+    a.partial_rows = c.pk.partial_rows;
+    {
+        const char* la = std::getenv("FL_PK_LOOKAHEAD_KB");
+        a.lookahead_bytes = (la ? std::atoi(la) : 128) * 1024;
+        const char* fl = std::getenv("FL_PK_FLAGS");
+        a.flags = fl ? std::atoi(fl) : 0;
+    }
+    static long long* dbg_buf = nullptr;
+    const bool dbg = env_flag("FL_PK_DEBUG");
+    if (dbg && !dbg_buf) FL_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));
+    a.dbg = dbg ? dbg_buf : nullptr;
+    FL_CUDA(cudaMemsetAsync(c.gbar.p, 0, sizeof(unsigned int), c.stream));
+    void* params[] = {&a};
+    const void* fn = (w.d == 64) ? (const void*)decode_persistent_kernel<64> : (const void*)decode_persistent_kernel<128>;
+    ProfEntry pe;
+    if (g_prof.on) {
+        pe.tag = "decode_persistent";
+        pe.bytes = (uint64_t)nsteps * (w.streamed_bytes + (uint64_t)c.kv_len * w.L * w.nkv * w.d * 2 * 2);
+        FL_CUDA(cudaEventCreate(&pe.e0));
+        FL_CUDA(cudaEventCreate(&pe.e1));
+        FL_CUDA(cudaEventRecord(pe.e0, c.stream));
+    }
+    FL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(kNumSMs), dim3(kPkThreads), params, c.pk.smem, c.stream));
+    if (g_prof.on) {
+        FL_CUDA(cudaEventRecord(pe.e1, c.stream));
+        g_prof.entries.push_back(pe);
+    }
+    g_launches.fetch_add(1);
+    if (dbg) {
+        static const char* names[] = {"P1 x(rmsnorm)", "P1 consume qkv", "P1 epilogue", "P1 grid barrier", "P2 attention", "P2 grid barrier",
+                                      "P3 x", "P3 consume o", "P3 epilogue", "P3 grid barrier", "P4 x(rmsnorm)", "P4 consume gate/up",
+                                      "P4 epilogue", "P4 grid barrier", "P5 x", "P5 consume down", "P5 epilogue", "P5 grid barrier"};
+        long long h[19];
+        FL_CUDA(cudaStreamSynchronize(c.stream));
+        FL_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[FL_PK_DEBUG] layer %d, CTA 0 phase times (us):", w.L / 2);
+        for (int i = 0; i < 18; ++i) fprintf(stderr, " %s=%.2f;", names[i], (h[i + 1] - h[i]) / 1000.0);
+        fprintf(stderr, " layer total=%.2f\n", (h[18] - h[0]) / 1000.0);
+    }
+}
 
 static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     const Weights& w = *c.w;
@@ -377,6 +474,7 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     c.amax_idx.alloc((size_t)kPassRows * c.amax_parts);
     c.h_ids.alloc((size_t)max_batch * max_seq);
     c.h_logits.alloc((size_t)max_batch * w.V);
+    plan_persistent(c);
     const size_t smem = attn_smem_bytes(w.d, w.nh / w.nkv);
     switch (w.d) {
         case 16: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
@@ -515,7 +613,9 @@ static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t r
     set_state_kernel<<<1, 1, 0, c.stream>>>(c.state.p, (int)rope_offset);
     g_launches.fetch_add(1);
     const bool use_graph = (t == 1) && !g_prof.on && !env_flag("FL_NO_GRAPH");
-    if (use_graph) {
+    if (b == 1 && t == 1 && c.pk.ok) {
+        launch_persistent(c, 1, false);
+    } else if (use_graph) {
         GraphEntry& g = get_graph(c, b, false);
         FL_CUDA(cudaGraphLaunch(g.exec, c.stream));
         g_launches.fetch_add(g.kernels);
@@ -754,13 +854,18 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
         FL_CUDA(cudaMemsetAsync(c->trace_pos.p, 0, 4, c->stream));
         set_state_kernel<<<1, 1, 0, c->stream>>>(c->state.p, (int)rope_offset);
         g_launches.fetch_add(1);
-        const bool use_graph = !g_prof.on && !env_flag("FL_NO_GRAPH");
+        const bool persistent = (b == 1) && c->pk.ok;
+        const bool use_graph = !persistent && !g_prof.on && !env_flag("FL_NO_GRAPH");
         GraphEntry* g = use_graph ? &get_graph(*c, b, true) : nullptr;
         cudaEvent_t e0, e1;
         FL_CUDA(cudaEventCreate(&e0));
         FL_CUDA(cudaEventCreate(&e1));
         FL_CUDA(cudaEventRecord(e0, c->stream));
-        for (int s = 0; s < steps; ++s) {
+        if (persistent) {
+            launch_persistent(*c, steps, true);   // all steps inside one cooperative launch
+            c->kv_len += steps;
+        }
+        for (int s = 0; s < (persistent ? 0 : steps); ++s) {
             if (g) {
                 FL_CUDA(cudaGraphLaunch(g->exec, c->stream));
                 g_launches.fetch_add(g->kernels);

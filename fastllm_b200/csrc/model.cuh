@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/fastllm_b200.h"
+#include "decode_persistent.cuh"
 #include "gemv.cuh"
 #include "runtime.cuh"
 
@@ -33,6 +34,7 @@ struct Weights {
     uint16_t* lm_head = nullptr;
     float* final_norm = nullptr;
     std::vector<LayerW> layers;
+    DevBuf<PkLayer> pk_layers;  // device copy of the per-layer pointers for the persistent decode kernel
     float* rope_cos = nullptr;  // [max_pos, d/2]
     float* rope_sin = nullptr;
     std::set<std::string> have; // tensor names that arrived
@@ -40,6 +42,13 @@ struct Weights {
     bool finalized = false;
     uint64_t streamed_bytes = 0;
     std::mutex mu;
+};
+
+// Shared-memory plan of the persistent decode kernel for one (model, cache) pair.
+struct PkPlan {
+    bool ok = false;
+    int nstages = 0, xs_floats = 0, partial_rows = 0, nsplit = 1;
+    size_t smem = 0;
 };
 
 struct GraphKey {
@@ -76,5 +85,7 @@ struct fl_cache {
     size_t trace_cap = 0;
     int amax_parts = 0;
     std::map<fl::GraphKey, fl::GraphEntry> graphs;
+    fl::PkPlan pk;
+    fl::DevBuf<unsigned int> gbar;
     bool poisoned = false;
 };

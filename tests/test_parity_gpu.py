@@ -163,3 +163,42 @@ def test_true_width_two_layers(arch):
     kerr = float(np.abs(np.stack(logits) - np.stack(k_logits)).max())
     print(f"{arch}: max-abs logits err vs f32 oracle {err:.3e}, vs oracle with bf16 KV {kerr:.3e}")
     assert ids == want_ids and err <= LOGIT_TOL and kerr <= KERNEL_TOL_WIDE
+
+
+def _tiny_true_width(arch):
+    from dataclasses import replace
+    base = {"tinyllama": ocl.TINYLLAMA, "mistral7b": ocl.MISTRAL_7B, "qwen25_7b": replace(ocl.QWEN25_7B, vocab_size=32064)}[arch]
+    return replace(base, num_hidden_layers=2, max_position_embeddings=256)
+
+
+@pytest.mark.parametrize("arch", ["tinyllama", "mistral7b", "qwen25_7b"])
+def test_persistent_kernel_matches_multikernel_path(arch, monkeypatch):
+    """Batch-1 decode runs in the persistent cooperative kernel; the 5-kernels-per-layer path must agree with it
+    (different summation order only), and the in-kernel multi-step greedy loop must reproduce step-by-step decoding."""
+    from fastllm_b200 import models
+    cfg = _tiny_true_width(arch)
+    w = ocl.synth_weights(cfg, 0, 0.02)
+    prompt = synth.token_ids(1, cfg.vocab_size, (1, 70))           # crosses a 64-token KV page boundary
+    model, _ = product_model(cfg, w)
+    ca = models.DeviceCache(model.dev, 1, 128)
+    first = ca.forward_greedy(prompt, 0)
+    ids_loop, _ = ca.decode_greedy_loop(first, 70, 6)                # persistent kernel, 6 steps in one launch
+    cb = models.DeviceCache(model.dev, 1, 128)
+    tok, step_ids, step_logits = cb.forward_greedy(prompt, 0), [], []
+    for s in range(6):                                               # persistent kernel, one launch per step
+        lg = cb.forward(tok.reshape(1, 1), 70 + s)
+        step_logits.append(lg[0])
+        tok = np.array([models.sample_argmax(lg[0])], dtype=np.uint32)
+        step_ids.append(int(tok[0]))
+    assert list(ids_loop[:, 0]) == step_ids
+    monkeypatch.setenv("FL_NO_PERSISTENT", "1")
+    cc = models.DeviceCache(model.dev, 1, 128)                       # multi-kernel path
+    tok, mk_logits = cc.forward_greedy(prompt, 0), []
+    for s in range(6):
+        lg = cc.forward(tok.reshape(1, 1), 70 + s)
+        mk_logits.append(lg[0])
+        tok = np.array([models.sample_argmax(lg[0])], dtype=np.uint32)
+        assert int(tok[0]) == step_ids[s]
+    err = float(np.abs(np.stack(mk_logits) - np.stack(step_logits)).max())
+    print(f"{arch}: persistent vs multi-kernel max-abs logits diff {err:.3e}")
+    assert err <= KERNEL_TOL_WIDE
