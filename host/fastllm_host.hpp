@@ -1,0 +1,201 @@
+// C++ mirror of fastllm's trait-based model API over the C ABI (include/fastllm_b200.h).
+//
+// The reference's host side is Rust (compiled code) and there is no Rust toolchain in this image, so the compiled
+// host-side mirror is C++: same type names, same argument meaning, same offset rules and the same failure points as
+//   ModelInitializer / ModelArchitecture   src/models/model_initializer.rs:6-27
+//   ModelCache / CommonCache               src/models/cache.rs:5-46
+//   LlamaWithConfig / LlamaCache           src/models/llama.rs:52-160
+//   MistralWithConfig / MistralCache       src/models/mistral.rs:16-248
+//   QwenWithConfig / QwenCache             src/models/qwen.rs:12-186
+//   Model<M>::generate (greedy)            src/models/mod.rs:342-464
+// INTEGRATION.md shows the Rust shim (a transliteration of this file) a maintainer would add.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/fastllm_b200.h"
+
+namespace fastllm {
+
+struct Error : std::runtime_error {   // anyhow::Error
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+    if (rc != FL_OK) throw Error(rc, fl_last_error());
+}
+
+// A host tensor as handed over by load_model (providers/huggingface/huggingface.rs:85-130): name -> (dtype, shape, data)
+struct HostTensor {
+    fl_dtype dtype;
+    std::vector<int64_t> shape;
+    const void* data;
+};
+using TensorMap = std::map<std::string, HostTensor>;
+
+// llama.rs:17-29 / mistral.rs:78-91 / models/config.rs:5-18
+struct ConfigFile {
+    int hidden_size = 0, intermediate_size = 0, vocab_size = 0, num_hidden_layers = 0, num_attention_heads = 0;
+    std::optional<int> num_key_value_heads;
+    double rms_norm_eps = 1e-5;
+    std::optional<double> rope_theta;
+    std::optional<int> max_position_embeddings;
+    std::optional<int> sliding_window;
+};
+
+// ---- ModelCache (cache.rs:5-10) -------------------------------------------------------------------------------------
+struct ModelCache {
+    virtual ~ModelCache() = default;
+    virtual void increment_offset() = 0;
+    virtual void reset() = 0;
+    virtual size_t get_offset() const = 0;
+};
+struct CommonCache : ModelCache {   // cache.rs:12-46
+    size_t seqlen_offset = 0;
+    void increment_offset() override { seqlen_offset += 1; }
+    void reset() override { seqlen_offset = 0; }
+    size_t get_offset() const override { return seqlen_offset; }
+};
+
+struct DeviceModel {   // shared device weights (fl_model*)
+    fl_model* h = nullptr;
+    fl_config cfg{};
+    explicit DeviceModel(const fl_config& c) : cfg(c) { check(fl_model_create(&c, &h)); }
+    DeviceModel(fl_model* handle, const fl_config& c) : h(handle), cfg(c) {}
+    ~DeviceModel() { if (h) fl_model_destroy(h); }
+    DeviceModel(const DeviceModel&) = delete;
+    DeviceModel& operator=(const DeviceModel&) = delete;
+};
+struct DeviceCache {   // paged KV cache + stream (fl_cache*)
+    fl_cache* h = nullptr;
+    DeviceCache(fl_model* m, int max_batch, int max_seq) { check(fl_cache_create(m, max_batch, max_seq, &h)); }
+    ~DeviceCache() { if (h) fl_cache_destroy(h); }
+    DeviceCache(const DeviceCache&) = delete;
+    DeviceCache& operator=(const DeviceCache&) = delete;
+};
+
+struct LlamaCache : CommonCache {     // llama.rs:61-92: owns the KV (candle `Cache`); bound lazily on first forward
+    std::unique_ptr<DeviceCache> inner;
+};
+struct MistralCache : CommonCache {}; // mistral.rs:16-47: offset only, KV lives in the model
+struct QwenCache : CommonCache {};    // qwen.rs:58-87
+
+inline fl_config to_fl_config(fl_arch arch, const ConfigFile& cf, int default_max_pos, int sliding_window, bool qkv_bias) {
+    fl_config c{};
+    c.arch = arch;
+    c.hidden_size = cf.hidden_size; c.intermediate_size = cf.intermediate_size; c.vocab_size = cf.vocab_size;
+    c.num_hidden_layers = cf.num_hidden_layers; c.num_attention_heads = cf.num_attention_heads;
+    c.num_key_value_heads = cf.num_key_value_heads.value_or(cf.num_attention_heads);
+    c.max_position_embeddings = cf.max_position_embeddings.value_or(default_max_pos);
+    c.sliding_window = sliding_window; c.qkv_bias = qkv_bias ? 1 : 0;
+    c.norm_eps = (float)cf.rms_norm_eps; c.rope_theta = cf.rope_theta.value_or(10000.0);
+    c.tp_rank = 0; c.tp_size = 1;
+    return c;
+}
+
+inline std::shared_ptr<DeviceModel> upload(const fl_config& c, const TensorMap& tensors) {
+    auto m = std::make_shared<DeviceModel>(c);
+    for (const auto& kv : tensors)
+        check(fl_model_put_tensor(m->h, kv.first.c_str(), kv.second.dtype, kv.second.shape.data(), (int)kv.second.shape.size(), kv.second.data));
+    check(fl_model_finalize(m->h));
+    return m;
+}
+
+// Logits of one forward: [b, V] (Llama) or [b, 1, V] (Mistral/Qwen2); the generate loop flattens row 0 either way.
+struct Logits {
+    std::vector<float> data;
+    int batch = 0, vocab = 0;
+    const float* row(int b) const { return data.data() + (size_t)b * vocab; }
+};
+
+constexpr int kKvCapacity = 4096;   // the reference grows KV by `cat`; pages are preallocated here
+
+// ---- LlamaWithConfig (llama.rs:52-160) --------------------------------------------------------------------------------
+struct LlamaWithConfig {
+    using Config = ConfigFile;
+    using Cache = LlamaCache;
+    std::shared_ptr<DeviceModel> dev;
+    static const char* get_family() { return "Llama"; }
+    static bool supports_architecture(const std::string& a) { return a == "LlamaForCausalLM"; }
+    // initialize_model(&Config, HashMap<String,Tensor>, DType, &Device) -> (Self, Cache)   llama.rs:98-123
+    static std::pair<LlamaWithConfig, Cache> initialize_model(const Config& cfg, const TensorMap& tensors, int device) {
+        check(fl_init(device));
+        LlamaWithConfig m{upload(to_fl_config(FL_ARCH_LLAMA, cfg, 4096, 0, false), tensors)};
+        return {std::move(m), Cache{}};
+    }
+    static Cache initialize_cache(int /*device*/) { return Cache{}; }   // llama.rs:125-145
+    // forward(&self, &Tensor, pos, &mut Cache): model.forward(input, pos, &mut cache.inner)   llama.rs:147-149
+    Logits forward(const uint32_t* ids, int b, int t, size_t pos, Cache& cache) const {
+        if (!cache.inner) cache.inner = std::make_unique<DeviceCache>(dev->h, b, std::min(kKvCapacity, dev->cfg.max_position_embeddings));
+        Logits out; out.batch = b; out.vocab = dev->cfg.vocab_size; out.data.resize((size_t)b * out.vocab);
+        check(fl_forward(dev->h, cache.inner->h, ids, b, t, pos, out.data.data()));
+        return out;
+    }
+};
+
+// ---- MistralWithConfig / QwenWithConfig (mistral.rs:49-248, qwen.rs:12-186) -------------------------------------------
+template <fl_arch ARCH, typename CacheT>
+struct OffsetAdapter {
+    using Config = ConfigFile;
+    using Cache = CacheT;
+    std::shared_ptr<DeviceModel> dev;
+    mutable std::unique_ptr<DeviceCache> kv;   // candle keeps the KV inside the model (RefCell<Model>)
+    static std::pair<OffsetAdapter, Cache> initialize_model(const Config& cfg, const TensorMap& tensors, int device) {
+        check(fl_init(device));
+        // mistral.rs:139 / qwen.rs:49: sliding_window.unwrap_or(4096); bad head dims make fl_model_create fail where the reference asserts
+        OffsetAdapter m{upload(to_fl_config(ARCH, cfg, 32768, cfg.sliding_window.value_or(4096), ARCH == FL_ARCH_QWEN2), tensors), nullptr};
+        return {std::move(m), Cache{}};
+    }
+    static Cache initialize_cache(int /*device*/) { return Cache{}; }
+    void clear_kv_cache() const { if (kv) check(fl_cache_reset(kv->h)); }
+    // forward(&self, input, _pos, cache): clear KV at offset 0; rope offset = cache offset; offset += 1 PER CALL
+    Logits forward(const uint32_t* ids, int b, int t, size_t /*_pos*/, Cache& cache) const {
+        if (!kv) kv = std::make_unique<DeviceCache>(dev->h, b, std::min(kKvCapacity, dev->cfg.max_position_embeddings));
+        if (cache.get_offset() == 0) clear_kv_cache();
+        Logits out; out.batch = b; out.vocab = dev->cfg.vocab_size; out.data.resize((size_t)b * out.vocab);
+        check(fl_forward(dev->h, kv->h, ids, b, t, cache.get_offset(), out.data.data()));
+        cache.increment_offset();
+        return out;
+    }
+    OffsetAdapter clone() const { return OffsetAdapter{dev, nullptr}; }   // shared weights, independent KV (mod.rs:155)
+};
+using MistralWithConfig = OffsetAdapter<FL_ARCH_MISTRAL, MistralCache>;
+using QwenWithConfig = OffsetAdapter<FL_ARCH_QWEN2, QwenCache>;
+
+// LogitsProcessor::sample_argmax: max_by(total_cmp) => LAST index among equal maxima
+inline uint32_t sample_argmax(const float* v, int n) {
+    int best = 0;
+    for (int i = 1; i < n; ++i)
+        if (v[i] >= v[best]) best = i;
+    return (uint32_t)best;
+}
+
+// ---- Model<M>::generate, temperature 0 (mod.rs:363-463), prompts already tokenised -------------------------------------
+template <typename M>
+struct Model {
+    M model;
+    typename M::Cache cache;
+    std::optional<uint32_t> eos_token_id = 2;   // tokenizer.token_to_id("</s>")
+    std::vector<uint32_t> generate(const std::vector<uint32_t>& prompt, int max_tokens) {
+        cache = M::initialize_cache(0);                                           // mod.rs:370
+        size_t pos = 0;
+        Logits logits = model.forward(prompt.data(), 1, (int)prompt.size(), pos, cache);   // mod.rs:402-405
+        pos += prompt.size();
+        std::vector<uint32_t> out;
+        for (int i = 0; i < max_tokens; ++i) {                                    // mod.rs:411-453
+            const uint32_t tok = sample_argmax(logits.row(0), logits.vocab);
+            if (eos_token_id && tok == *eos_token_id) break;                      // break BEFORE emitting
+            out.push_back(tok);
+            logits = model.forward(&tok, 1, 1, pos, cache);
+            pos += 1;
+        }
+        return out;
+    }
+};
+
+}  // namespace fastllm

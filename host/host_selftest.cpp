@@ -1,0 +1,55 @@
+// Self-test of the C++ host mirror: builds a tiny synthetic Llama through the reference-shaped interface, runs
+// Model::generate, prints the greedy ids as JSON.  tests/test_host_cpp_gpu.py compares them with the oracle.
+// Build: g++ -std=c++17 -O2 host/host_selftest.cpp -o host/_build/host_selftest -Lfastllm_b200 -lfastllm_b200 -Wl,-rpath,...
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "fastllm_host.hpp"
+
+int main(int argc, char** argv) {
+    // argv: weights.bin (concatenated f32 tensors in manifest order), manifest.txt (name ndim dims...), prompt ids...
+    if (argc < 4) { std::fprintf(stderr, "usage: host_selftest manifest.txt weights.bin max_tokens id...\n"); return 2; }
+    try {
+        FILE* mf = std::fopen(argv[1], "r");
+        FILE* wf = std::fopen(argv[2], "rb");
+        if (!mf || !wf) throw std::runtime_error("cannot open inputs");
+        fastllm::ConfigFile cfg;
+        int nkv = 0, maxpos = 0;
+        double theta = 0;
+        if (std::fscanf(mf, "%d %d %d %d %d %d %lf %lf %d", &cfg.hidden_size, &cfg.intermediate_size, &cfg.vocab_size, &cfg.num_hidden_layers,
+                        &cfg.num_attention_heads, &nkv, &cfg.rms_norm_eps, &theta, &maxpos) != 9) throw std::runtime_error("bad manifest header");
+        cfg.num_key_value_heads = nkv; cfg.rope_theta = theta; cfg.max_position_embeddings = maxpos;
+        std::vector<std::vector<float>> storage;
+        fastllm::TensorMap tensors;
+        char name[256];
+        int nd;
+        while (std::fscanf(mf, "%255s %d", name, &nd) == 2) {
+            std::vector<int64_t> shape(nd);
+            size_t n = 1;
+            for (int i = 0; i < nd; ++i) { long long d; if (std::fscanf(mf, "%lld", &d) != 1) throw std::runtime_error("bad shape"); shape[i] = d; n *= (size_t)d; }
+            storage.emplace_back(n);
+            if (std::fread(storage.back().data(), 4, n, wf) != n) throw std::runtime_error("short weights file");
+            tensors[name] = fastllm::HostTensor{FL_DTYPE_F32, shape, storage.back().data()};
+        }
+        const int max_tokens = std::atoi(argv[3]);
+        std::vector<uint32_t> prompt;
+        for (int i = 4; i < argc; ++i) prompt.push_back((uint32_t)std::strtoul(argv[i], nullptr, 10));
+        auto pair = fastllm::LlamaWithConfig::initialize_model(cfg, tensors, 0);
+        fastllm::Model<fastllm::LlamaWithConfig> model{std::move(pair.first), std::move(pair.second), std::nullopt};
+        const auto ids = model.generate(prompt, max_tokens);
+        std::printf("[");
+        for (size_t i = 0; i < ids.size(); ++i) std::printf("%s%u", i ? "," : "", ids[i]);
+        std::printf("]\n");
+        // failure point parity: multi-token forward on a non-empty Llama cache must be an error, not a crash
+        try {
+            model.model.forward(prompt.data(), 1, (int)prompt.size(), prompt.size(), model.cache);
+            std::printf("ERROR: expected failure\n");
+            return 1;
+        } catch (const fastllm::Error& e) { std::fprintf(stderr, "expected error: %s\n", e.what()); }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "host_selftest failed: %s\n", e.what());
+        return 1;
+    }
+}
