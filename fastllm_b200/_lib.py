@@ -53,6 +53,7 @@ SYMBOLS = {
     "fl_forward_greedy": (_I, [_VP, _VP, _VP, _I, _I, _SZ, _VP]),
     "fl_decode_greedy_loop": (_I, [_VP, _VP, _VP, _I, _SZ, _I, _VP, C.POINTER(C.c_float)]),
     "fl_embed": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
+    "fl_embed_timed": (_I, [_VP, _VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_float)]),
     "fl_comm_unique_id": (_I, [_VP]),
     "fl_comm_init": (_I, [_I, _I, _VP]),
     "fl_comm_destroy": (_I, []),

@@ -6,7 +6,7 @@
 namespace fl {
 
 // K1: Embedding::forward = index_select.  resid[m, :] = f32(embed[ids[row_base + m], :])   (bf16 table, f32 residual stream)
-__global__ void embed_gather_kernel(const uint16_t* __restrict__ table, const uint32_t* __restrict__ ids, int row_base, int H,
+static __global__ void embed_gather_kernel(const uint16_t* __restrict__ table, const uint32_t* __restrict__ ids, int row_base, int H,
                                     int vocab, float* __restrict__ resid) {
     pdl_launch_dependents();
     pdl_wait();
@@ -26,7 +26,7 @@ __global__ void embed_gather_kernel(const uint16_t* __restrict__ table, const ui
 
 // K18 on device: merge the per-CTA arg-max partials of the lm_head GEMV (last index wins ties, like candle's
 // LogitsProcessor::sample_argmax) and write next_ids[seq] for rows that are the last token of their sequence.
-__global__ void argmax_finalize_kernel(const float* __restrict__ val, const int* __restrict__ idx, int nparts, int M, int row_base,
+static __global__ void argmax_finalize_kernel(const float* __restrict__ val, const int* __restrict__ idx, int nparts, int M, int row_base,
                                        int t, uint32_t* __restrict__ next_ids) {
     pdl_launch_dependents();
     pdl_wait();
@@ -59,7 +59,7 @@ __global__ void argmax_finalize_kernel(const float* __restrict__ val, const int*
 }
 
 // End of a forward call: kv_base[seq] += t.  In the device-resident greedy loop also rope_pos += 1 and ids <- next_ids.
-__global__ void advance_state_kernel(StepState* st, int b, int t, int rope_inc, uint32_t* ids, const uint32_t* next_ids, int feedback,
+static __global__ void advance_state_kernel(StepState* st, int b, int t, int rope_inc, uint32_t* ids, const uint32_t* next_ids, int feedback,
                                      uint32_t* trace, int* trace_pos) {
     pdl_launch_dependents();
     pdl_wait();
@@ -76,8 +76,8 @@ __global__ void advance_state_kernel(StepState* st, int b, int t, int rope_inc, 
     }
 }
 
-__global__ void set_state_kernel(StepState* st, int rope_pos) { st->rope_pos = rope_pos; }
-__global__ void reset_state_kernel(StepState* st, int kv_len) {
+static __global__ void set_state_kernel(StepState* st, int rope_pos) { st->rope_pos = rope_pos; }
+static __global__ void reset_state_kernel(StepState* st, int kv_len) {
     for (int i = threadIdx.x; i < kMaxBatch; i += blockDim.x) st->kv_base[i] = kv_len;
     if (threadIdx.x == 0) st->rope_pos = 0;
 }

@@ -121,6 +121,7 @@ static void validate_config(const fl_config& c) {
     FL_CHECK(d * c.num_attention_heads == c.hidden_size, FL_ERR_INVALID, "hidden_size must be divisible by num_attention_heads");
     FL_CHECK(d % 2 == 0, FL_ERR_INVALID, "head_dim must be even for RoPE embeddings");
     const int nkv = c.num_key_value_heads > 0 ? c.num_key_value_heads : c.num_attention_heads;
+    if (c.arch == FL_ARCH_BERT) return;   // remaining checks are causal-LM specific; bert_build has its own
     FL_CHECK(c.num_attention_heads % nkv == 0, FL_ERR_INVALID, "num_attention_heads must be divisible by num_key_value_heads");
     FL_CHECK(c.num_attention_heads / nkv <= kAttnMaxRep, FL_ERR_UNSUPPORTED, "GQA group size > 8 not supported");
     FL_CHECK(c.hidden_size % 8 == 0 && c.intermediate_size % 8 == 0, FL_ERR_UNSUPPORTED, "hidden/intermediate size must be a multiple of 8");
@@ -686,11 +687,18 @@ FL_EXPORT int fl_model_create(const fl_config* cfg, fl_model** out) {
     FL_CHECK(cfg != nullptr && out != nullptr, FL_ERR_INVALID, "NULL argument");
     use_device();
     validate_config(*cfg);
+    if (cfg->arch == FL_ARCH_BERT) {
+        auto bm = std::make_shared<BertModel>();
+        bm->cfg = *cfg;
+        bert_build(*bm);
+        *out = new fl_model{nullptr, bm};
+        return FL_OK;
+    }
     auto w = std::make_shared<Weights>();
     w->cfg = *cfg;
     w->device = g_device.load();
     build_weights(*w);
-    *out = new fl_model{w};
+    *out = new fl_model{w, nullptr};
     FL_API_END
 }
 
@@ -698,6 +706,11 @@ FL_EXPORT int fl_model_put_tensor(fl_model* m, const char* name, int dtype, cons
     FL_API_BEGIN
     FL_CHECK(m && name && shape && host_ptr, FL_ERR_INVALID, "NULL argument");
     use_device();
+    if (m->bert) {
+        std::lock_guard<std::mutex> g(m->bert->mu);
+        bert_put_tensor(*m->bert, name, dtype, shape, rank, host_ptr);
+        return FL_OK;
+    }
     std::lock_guard<std::mutex> g(m->w->mu);
     put_tensor(*m->w, name, dtype, shape, rank, host_ptr);
     FL_API_END
@@ -707,6 +720,11 @@ FL_EXPORT int fl_model_random_init(fl_model* m, uint64_t seed, float stdv) {
     FL_API_BEGIN
     FL_CHECK(m, FL_ERR_INVALID, "NULL argument");
     use_device();
+    if (m->bert) {
+        std::lock_guard<std::mutex> g(m->bert->mu);
+        bert_random_init(*m->bert, seed, stdv);
+        return FL_OK;
+    }
     std::lock_guard<std::mutex> g(m->w->mu);
     random_init(*m->w, seed, stdv);
     FL_API_END
@@ -716,6 +734,11 @@ FL_EXPORT int fl_model_finalize(fl_model* m) {
     FL_API_BEGIN
     FL_CHECK(m, FL_ERR_INVALID, "NULL argument");
     use_device();
+    if (m->bert) {
+        std::lock_guard<std::mutex> g(m->bert->mu);
+        bert_finalize(*m->bert);
+        return FL_OK;
+    }
     std::lock_guard<std::mutex> g(m->w->mu);
     finalize(*m->w);
     FL_API_END
@@ -724,7 +747,7 @@ FL_EXPORT int fl_model_finalize(fl_model* m) {
 FL_EXPORT int fl_model_clone(fl_model* m, fl_model** out) {
     FL_API_BEGIN
     FL_CHECK(m && out, FL_ERR_INVALID, "NULL argument");
-    *out = new fl_model{m->w};
+    *out = new fl_model{m->w, m->bert};
     FL_API_END
 }
 
@@ -740,6 +763,7 @@ FL_EXPORT int fl_model_destroy(fl_model* m) {
 FL_EXPORT int fl_model_weight_bytes(fl_model* m, uint64_t* streamed_bytes) {
     FL_API_BEGIN
     FL_CHECK(m && streamed_bytes, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w != nullptr, FL_ERR_INVALID, "not a causal LM");
     *streamed_bytes = m->w->streamed_bytes;
     FL_API_END
 }
@@ -747,6 +771,7 @@ FL_EXPORT int fl_model_weight_bytes(fl_model* m, uint64_t* streamed_bytes) {
 FL_EXPORT int fl_cache_create(fl_model* m, int max_batch, int max_seq, fl_cache** out) {
     FL_API_BEGIN
     FL_CHECK(m && out, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w != nullptr, FL_ERR_INVALID, "BERT models have no KV cache");
     use_device();
     std::unique_ptr<fl_cache> c(new fl_cache);
     c->w = m->w;
@@ -803,7 +828,7 @@ FL_EXPORT int fl_cache_destroy(fl_cache* c) {
 FL_EXPORT int fl_forward(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, float* logits_host) {
     FL_API_BEGIN
     FL_CHECK(m && c && logits_host, FL_ERR_INVALID, "NULL argument");
-    FL_CHECK(m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    FL_CHECK(m->w != nullptr && m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
     use_device();
     try {
         run_forward(*c, ids, b, t, rope_offset);
@@ -821,7 +846,7 @@ FL_EXPORT int fl_forward(fl_model* m, fl_cache* c, const uint32_t* ids, int b, i
 FL_EXPORT int fl_forward_greedy(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, uint32_t* next_ids) {
     FL_API_BEGIN
     FL_CHECK(m && c && next_ids, FL_ERR_INVALID, "NULL argument");
-    FL_CHECK(m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    FL_CHECK(m->w != nullptr && m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
     use_device();
     try {
         run_forward(*c, ids, b, t, rope_offset);
@@ -839,7 +864,7 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
                           uint32_t* out_ids, float* elapsed_ms) {
     FL_API_BEGIN
     FL_CHECK(m && c, FL_ERR_INVALID, "NULL argument");
-    FL_CHECK(m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    FL_CHECK(m->w != nullptr && m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
     FL_CHECK(steps >= 1, FL_ERR_INVALID, "steps must be >= 1");
     use_device();
     try {
@@ -894,8 +919,20 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
 
 FL_EXPORT int fl_embed(fl_model* m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out) {
     FL_API_BEGIN
-    (void)m; (void)ids; (void)mask; (void)b; (void)t; (void)out;
-    throw fl::Error(FL_ERR_UNSUPPORTED, "fl_embed: BERT encoder not built yet");
+    FL_CHECK(m && ids && out, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->bert != nullptr, FL_ERR_INVALID, "fl_embed needs a BERT-family model (the reference panics on embedding_size() of chat models, models/mod.rs:97-106)");
+    use_device();
+    bert_embed(*m->bert, ids, mask, b, t, out, nullptr);
+    FL_API_END
+}
+
+FL_EXPORT int fl_embed_timed(fl_model* m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out, int repeats, float* device_ms) {
+    FL_API_BEGIN
+    FL_CHECK(m && ids && out && device_ms, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->bert != nullptr, FL_ERR_INVALID, "fl_embed_timed needs a BERT-family model");
+    use_device();
+    bert_embed(*m->bert, ids, mask, b, t, out, nullptr);
+    bert_repeat(*m->bert, b, t, repeats < 1 ? 1 : repeats, device_ms);
     FL_API_END
 }
 

@@ -1,0 +1,223 @@
+// Dense bf16 GEMM on the 5th-gen tensor cores: D[M,N] = A[M,K] . B[N,K]^T (+ fused epilogue), sm_100a only.
+//
+// Hand-written tcgen05 / TMEM / TMA (inline PTX, no CUTLASS):
+//   * operands are K-major bf16 in global memory ([rows, K] row-major: activations [tokens, K], weights [out, K] exactly as
+//     HF stores them), fetched by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 4-stage shared-memory ring;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) with shared-memory descriptors,
+//     accumulating f32 in TMEM; tcgen05.commit releases ring slots / signals the epilogue through mbarriers;
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (tcgen05.ld
+//     32x32b: thread == accumulator row), which applies bias / GELU-tanh / residual and stores bf16 or f32.
+// Replaces the reference's cuBLAS-through-candle matmuls + separate bias/activation kernels (SURVEY.md section 2.4 B2, B5,
+// B6, B7 and K3/K12/K15/K16 for prefill).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fl {
+
+enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3 };
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;          // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kGemmStages = 3;          // 3 x 32 KB (BN=128): two CTAs per SM overlap one CTA's epilogue with the other's MMAs
+constexpr int kGemmThreads = 192;
+
+struct GemmArgs {
+    int M, N, K;
+    const float* bias;          // [N] or null
+    const uint16_t* resid;      // bf16 [M, ldr] residual (GEPI_BIAS_RESID_F32) or null
+    int ldr;
+    void* out;                  // bf16 or f32 [M, ldo]
+    int ldo;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// thread i of the warp receives columns [col, col+32) of TMEM lane (32*quarter + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes with the 128-byte swizzle
+// (exactly what TMA SWIZZLE_128B writes): start address >> 4, LBO = 1 (ignored for swizzled K-major), SBO = 1024 B >> 4
+// (stride between 8-row groups), version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(const void* smem_ptr) {
+    const uint64_t addr = (uint64_t)((smem_u32(smem_ptr) & 0x3FFFF) >> 4);
+    return addr | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9 = 1, 10-12 = 1), both K-major, N>>3 at 17, M>>4 at 24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    // candle Tensor::gelu(): 0.5 x (1 + tanh(sqrt(2/pi) x (1 + 0.044715 x^2)))   (models/embeddings.rs:229-231)
+    const float k = 0.7978845608028654f;
+    return 0.5f * x * (1.f + tanhf(k * x * (1.f + 0.044715f * x * x)));
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
+    constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;   // 16 KB
+    constexpr uint32_t kBBytes = BN * kGemmBK * 2;
+    constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    constexpr uint32_t kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+
+    extern __shared__ uint8_t gsm_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; the launch adds 1024 bytes of slack for this round-up
+    uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full[kGemmStages], empty[kGemmStages], acc_ready;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
+    const int nk = (g.K + kGemmBK - 1) / kGemmBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&acc_ready, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % kGemmStages;
+                mbar_wait(&empty[st], ((kb / kGemmStages) & 1) ^ 1);
+                uint8_t* sa = gsm + (size_t)st * kStageBytes;
+                mbar_expect_tx(&full[st], kStageBytes);
+                tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
+                tma_load_2d(sa + kABytes, &tmB, kb * kGemmBK, n0, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int st = kb % kGemmStages;
+                mbar_wait(&full[st], (kb / kGemmStages) & 1);
+                tc_fence_after();
+                const uint8_t* sa = gsm + (size_t)st * kStageBytes;
+                const uint64_t adesc = umma_smem_desc_sw128(sa), bdesc = umma_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < kGemmBK / 16; ++k)   // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (>>4) address field
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty[st]);                 // slot reusable once these MMAs have read it
+            }
+            umma_commit(&acc_ready);                     // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4, thread == output row =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(&acc_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (row < g.M) {
+                const int col = n0 + c0;
+                if (EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16) {
+                    uint16_t* o = reinterpret_cast<uint16_t*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (col + j < g.N) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                float v0 = __uint_as_float(r[j + e]) + (g.bias ? g.bias[col + j + e] : 0.f);
+                                float v1 = __uint_as_float(r[j + e + 1]) + (g.bias ? g.bias[col + j + e + 1] : 0.f);
+                                if (EPI == GEPI_BIAS_GELU_BF16) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); }
+                                pk[e >> 1] = (uint32_t)f32_to_bf16_rne(v0) | ((uint32_t)f32_to_bf16_rne(v1) << 16);
+                            }
+                            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                } else {
+                    float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+                    const uint16_t* rs = (EPI == GEPI_BIAS_RESID_F32 && g.resid) ? g.resid + (size_t)row * g.ldr + col : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col + j < g.N) {
+                            float4 v;
+                            v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]); v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                            if (EPI == GEPI_BIAS_RESID_F32) {
+                                if (g.bias) { v.x += g.bias[col + j]; v.y += g.bias[col + j + 1]; v.z += g.bias[col + j + 2]; v.w += g.bias[col + j + 3]; }
+                                if (rs) {
+                                    const uint2 rr = *reinterpret_cast<const uint2*>(rs + j);
+                                    v.x += bf16lo(rr.x); v.y += bf16hi(rr.x); v.z += bf16lo(rr.y); v.w += bf16hi(rr.y);
+                                }
+                            }
+                            *reinterpret_cast<float4*>(o + j) = v;
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace fl

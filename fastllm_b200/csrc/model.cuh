@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/fastllm_b200.h"
+#include "bert_model.cuh"
 #include "decode_persistent.cuh"
 #include "gemv.cuh"
 #include "runtime.cuh"
@@ -64,7 +65,8 @@ struct GraphEntry {
 }  // namespace fl
 
 struct fl_model {
-    std::shared_ptr<fl::Weights> w;
+    std::shared_ptr<fl::Weights> w;       // causal LMs
+    std::shared_ptr<fl::BertModel> bert;  // BERT-family encoder (arch == FL_ARCH_BERT)
 };
 
 struct fl_cache {

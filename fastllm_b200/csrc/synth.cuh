@@ -47,7 +47,7 @@ struct RowMap {
     }
 };
 
-__global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols, uint64_t tseed, float stdv, RowMap map) {
+static __global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols, uint64_t tseed, float stdv, RowMap map) {
     int64_t n = rows * cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / cols, c = i - r * cols;
@@ -56,12 +56,12 @@ __global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols
 }
 
 // f32 destination holding bf16-rounded values (biases, norm weights)
-__global__ void synth_fill_f32_kernel(float* dst, int64_t rows, uint64_t tseed, float stdv, RowMap map) {
+static __global__ void synth_fill_f32_kernel(float* dst, int64_t rows, uint64_t tseed, float stdv, RowMap map) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
         dst[map.map(i)] = __uint_as_float((uint32_t)synth_bf16(tseed, (uint64_t)i, stdv) << 16);
 }
 
-__global__ void fill_f32_kernel(float* dst, int64_t n, float v) {
+static __global__ void fill_f32_kernel(float* dst, int64_t n, float v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
 }
 

@@ -386,3 +386,85 @@ class Model:
             logits = self.model.forward(np.array([[tok]], dtype=np.uint32), pos, self.cache)
             pos += 1
         return (out, trace) if return_logits else out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# EmbeddingModel (models/embeddings.rs:17-38) -- BERT / MiniLM sentence encoder
+# --------------------------------------------------------------------------------------------------------------------
+@dataclass
+class BertConfig:
+    """models/embeddings.rs:46-54 (+ the vocabulary size the reference takes from the tokenizer, :301-306)."""
+    hidden_size: int = 384
+    num_attention_heads: int = 12
+    num_hidden_layers: int = 6
+    intermediate_size: int = 1536
+    max_position_embeddings: int = 512
+    layer_norm_eps: float = 1e-12
+    vocab_size: int = 30522
+
+
+class MiniLMModel:
+    """MiniLMModel (models/embeddings.rs:245-447) after tokenisation: `embed_ids` takes the token ids (and the tokenizer's
+    attention mask) and returns what EmbeddingModel::embed returns: the mean-pooled, L2-normalised f32 vector(s)."""
+    family, architectures = "bert", ("BertModel", "RobertaModel", "DebertaModel")
+
+    def __init__(self, config: BertConfig, tensors: dict | None, device: int = 0, model_id: str = "sentence-transformers/all-MiniLM-L6-v2",
+                 random_seed=None, std: float = 0.02):
+        c = FlConfig()
+        c.arch = _lib.FL_ARCH["bert"]
+        c.hidden_size, c.intermediate_size, c.vocab_size = config.hidden_size, config.intermediate_size, config.vocab_size
+        c.num_hidden_layers, c.num_attention_heads = config.num_hidden_layers, config.num_attention_heads
+        c.num_key_value_heads = config.num_attention_heads
+        c.max_position_embeddings = config.max_position_embeddings
+        c.norm_eps = config.layer_norm_eps
+        c.rope_theta, c.tp_rank, c.tp_size = 0.0, 0, 1
+        self.config, self._model_id = config, model_id
+        self.dev = DeviceModel(c, device)
+        if tensors is None:
+            self.dev.random_init(0 if random_seed is None else random_seed, std)
+        else:
+            for name, arr in tensors.items():
+                self.dev.put_tensor(name, np.asarray(arr, dtype=np.float32))
+        self.dev.finalize()
+
+    @classmethod
+    def get_family(cls) -> str:
+        return cls.family
+
+    @classmethod
+    def supports_architecture(cls, architecture: str) -> bool:
+        return architecture in cls.architectures
+
+    def model_id(self) -> str:
+        return self._model_id
+
+    def embedding_size(self) -> int:
+        return self.config.hidden_size          # the reference hard-codes 384 (embeddings.rs:453-455)
+
+    def embed_ids(self, ids: np.ndarray, mask: np.ndarray | None = None) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if ids.ndim == 1:
+            ids = ids[None]
+        b, t = ids.shape
+        out = np.empty((b, self.config.hidden_size), dtype=np.float32)
+        mptr = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32).reshape(b, t)
+            mptr = mask.ctypes.data_as(C.c_void_p)
+        _lib.check(self.dev.lib.fl_embed(self.dev.h, ids.ctypes.data_as(C.c_void_p), mptr, b, t, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def embed_ids_timed(self, ids: np.ndarray, repeats: int):
+        """-> (embeddings, device ms for `repeats` device-resident encoder passes over the uploaded batch)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        b, t = ids.shape
+        out = np.empty((b, self.config.hidden_size), dtype=np.float32)
+        ms = C.c_float()
+        _lib.check(self.dev.lib.fl_embed_timed(self.dev.h, ids.ctypes.data_as(C.c_void_p), None, b, t, out.ctypes.data_as(C.c_void_p),
+                                               repeats, C.byref(ms)))
+        return out, ms.value
+
+    def compute_similarity(self, ids1, ids2) -> float:
+        """EmbeddingModel::compute_similarity default impl (embeddings.rs:22-37): cosine of the two embeddings."""
+        v1, v2 = self.embed_ids(ids1)[0], self.embed_ids(ids2)[0]
+        return float(np.dot(v1, v2) / (np.linalg.norm(v1) * np.linalg.norm(v2)))

@@ -127,6 +127,9 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
 /* ---- embeddings (BERT family) ------------------------------------------------------------------ */
 /* ids/mask: host u32 [b, t]; mask may be NULL (all ones).  out: host f32 [b, hidden], mean-pooled and L2-normalised. */
 FL_EXPORT int fl_embed(fl_model* m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out);
+/* Benchmark hook: one fl_embed, then `repeats` device-resident encoder passes over the same (already uploaded) batch;
+ * device_ms = CUDA-event time of those repeats on the model's stream. */
+FL_EXPORT int fl_embed_timed(fl_model* m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out, int repeats, float* device_ms);
 
 /* ---- tensor / expert parallelism (one process per GPU; the library owns the NCCL communicator) -- */
 FL_EXPORT int fl_comm_unique_id(void* out_128_bytes);            /* rank 0 creates, the host side broadcasts it */

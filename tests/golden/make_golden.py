@@ -129,7 +129,7 @@ def make_causal(name: str, cfg: ocl.CausalLMConfig, check_hf: bool = True):
 def make_bert():
     import torch
     import transformers as tf
-    cfg = obert.BertConfig(64, 4, 2, 128, 64, 1e-12, 200)
+    cfg = obert.BertConfig(128, 4, 2, 256, 64, 1e-12, 200)     # head_dim 32 like all-MiniLM-L6-v2
     seed = 5
     w = obert.synth_weights(cfg, seed, STD)
     rng = np.random.default_rng(3)
@@ -139,12 +139,12 @@ def make_bert():
     ids = synth.token_ids(2, cfg.vocab_size, (3, 16))
     emb = obert.MiniLM(cfg, w).embed_ids(ids)
     hidden = obert.MiniLM(cfg, w).forward(ids)
-    hc = tf.BertConfig(hidden_size=64, num_attention_heads=4, num_hidden_layers=2, intermediate_size=128,
+    hc = tf.BertConfig(hidden_size=128, num_attention_heads=4, num_hidden_layers=2, intermediate_size=256,
                        max_position_embeddings=64, layer_norm_eps=1e-12, vocab_size=200,
                        hidden_act="gelu_pytorch_tanh", attn_implementation="eager")
     hm = tf.BertModel(hc, add_pooling_layer=False).eval().float()
     sd = {k: torch.from_numpy(v.copy()) for k, v in w.items()}
-    sd["embeddings.token_type_embeddings.weight"] = torch.zeros(2, 64)
+    sd["embeddings.token_type_embeddings.weight"] = torch.zeros(2, 128)
     missing, unexpected = hm.load_state_dict(sd, strict=False)
     assert not unexpected and all("position_ids" in k or "token_type_ids" in k for k in missing), (missing, unexpected)
     with torch.no_grad():

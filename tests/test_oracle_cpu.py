@@ -25,7 +25,7 @@ def test_oracle_reproduces_golden(name):
 
 def test_oracle_bert_golden():
     g = np.load(f"{GOLDEN}/bert_tiny.npz")
-    cfg = obert.BertConfig(64, 4, 2, 128, 64, 1e-12, 200)
+    cfg = obert.BertConfig(128, 4, 2, 256, 64, 1e-12, 200)
     w = obert.synth_weights(cfg, int(g["seed"]), float(g["std"]))
     for k in g.files:
         if k.startswith("w:"):
