@@ -90,7 +90,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { return (uint32_t)f32_to_bf16_rne(lo) | ((uint32_t)f32_to_bf16_rne(hi) << 16); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { return pack_bf16x2(lo, hi); }
 
 constexpr int kBertS = 128;      // max tokens per sentence handled by the fused kernel
 constexpr int kBertD = 32;       // head dim
@@ -139,13 +139,15 @@ static __global__ void __launch_bounds__(128) bert_attn_kernel(const uint16_t* _
             }
         }
         // scores / sqrt(d) (after the matmul, embeddings.rs:155-159), softmax over keys < t; rows g and g+8
+        // (the reference divides by sqrt(d); sqrt(32) is not a power of two, so x * (1/sqrt(d)) differs by <= 1 ulp)
+        const float inv_scale = 1.f / scale;
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 16; ++nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int key = nt * 8 + tq * 2 + (e & 1);
-                s[nt][e] = key < t ? s[nt][e] / scale : -INFINITY;
+                s[nt][e] = key < t ? s[nt][e] * inv_scale : -INFINITY;
             }
             mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
             mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
@@ -155,8 +157,8 @@ static __global__ void __launch_bounds__(128) bert_attn_kernel(const uint16_t* _
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 16; ++nt) {
-            s[nt][0] = expf(s[nt][0] - mx0); s[nt][1] = expf(s[nt][1] - mx0);
-            s[nt][2] = expf(s[nt][2] - mx1); s[nt][3] = expf(s[nt][3] - mx1);
+            s[nt][0] = __expf(s[nt][0] - mx0); s[nt][1] = __expf(s[nt][1] - mx0);
+            s[nt][2] = __expf(s[nt][2] - mx1); s[nt][3] = __expf(s[nt][3] - mx1);
             sum0 += s[nt][0] + s[nt][1];
             sum1 += s[nt][2] + s[nt][3];
         }

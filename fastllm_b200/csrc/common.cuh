@@ -53,6 +53,13 @@ __device__ __forceinline__ uint16_t f32_to_bf16_rne(float f) {
     return (uint16_t)((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
 }
 
+// two f32 -> packed bf16x2 (lo in bits 0-15), round-to-nearest-even, ONE instruction (same rounding as f32_to_bf16_rne)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);

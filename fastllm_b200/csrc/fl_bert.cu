@@ -50,8 +50,8 @@ static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
         FL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN);
-    gemm_tc_kernel<BN, EPI><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, g);
+    const int tiles = ((g.M + kGemmBM - 1) / kGemmBM) * ((g.N + BN - 1) / BN);
+    gemm_tc_kernel<BN, EPI><<<std::min(tiles, kNumSMs), kGemmThreads, smem, st>>>(tmA, tmB, g);
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 

@@ -20,8 +20,9 @@ enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;          // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kGemmStages = 3;          // 3 x 32 KB (BN=128): two CTAs per SM overlap one CTA's epilogue with the other's MMAs
-constexpr int kGemmThreads = 192;
+constexpr int kGemmStages = 6;        // 6 x 32 KB (BN=128) shared-memory ring, one persistent CTA per SM
+constexpr int kGemmEpiWarps = 16;      // four per TMEM lane quarter; each takes BN/4 columns of the tile
+constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
 struct GemmArgs {
     int M, N, K;
@@ -93,36 +94,52 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-    // candle Tensor::gelu(): 0.5 x (1 + tanh(sqrt(2/pi) x (1 + 0.044715 x^2)))   (models/embeddings.rs:229-231)
-    const float k = 0.7978845608028654f;
-    return 0.5f * x * (1.f + tanhf(k * x * (1.f + 0.044715f * x * x)));
+    // candle Tensor::gelu(): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) x (1 + 0.044715 x^2)   (models/embeddings.rs:229-231)
+    // Identity: 0.5 (1 + tanh(u)) = sigmoid(2u) = 1 / (1 + 2^(-2 u log2(e)))  ->  7 instructions, 2 of them MUFU (ex2, rcp);
+    // absolute error ~1e-6 x, far inside the bf16 rounding of the output.
+    const float c1 = -2.f * 0.7978845608028654f * 1.4426950408889634f;
+    const float c2 = c1 * 0.044715f;
+    const float t = x * fmaf(c2, x * x, c1);          // -2 u log2(e)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return x * r;
 }
 
+// Persistent, warp-specialised: grid = min(#SMs, #tiles); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so
+// the CTAs running concurrently share activation rows through L2).  Three pipelines: shared-memory ring (TMA -> MMA),
+// two TMEM accumulator stages (MMA -> epilogue: the epilogue of tile i overlaps the MMAs of tile i+1), and the tile walk.
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
+    static_assert(BN % 128 == 0 && BN >= 128 && BN <= 256, "BN: UMMA N for M=128 (multiple of 16 <= 256), split in 32-column chunks over 4 epilogue warps per lane quarter");
     constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;   // 16 KB
     constexpr uint32_t kBBytes = BN * kGemmBK * 2;
     constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    constexpr uint32_t kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    constexpr uint32_t kAccCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    constexpr uint32_t kTmemCols = 2 * kAccCols;          // two accumulator stages
 
     extern __shared__ uint8_t gsm_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch adds 1024 bytes of slack for this round-up
     uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t full[kGemmStages], empty[kGemmStages], acc_ready;
+    __shared__ __align__(8) uint64_t full[kGemmStages], empty[kGemmStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
     const int nk = (g.K + kGemmBK - 1) / kGemmBK;
+    const int mt = (g.M + kGemmBM - 1) / kGemmBM, nt = (g.N + BN - 1) / BN;
+    const int ntiles = mt * nt;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(&acc_ready, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], kGemmEpiWarps);      // one arrive per epilogue warp
+        }
         mbar_fence_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -136,83 +153,110 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < nk; ++kb) {
-                const int st = kb % kGemmStages;
-                mbar_wait(&empty[st], ((kb / kGemmStages) & 1) ^ 1);
-                uint8_t* sa = gsm + (size_t)st * kStageBytes;
-                mbar_expect_tx(&full[st], kStageBytes);
-                tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
-                tma_load_2d(sa + kABytes, &tmB, kb * kGemmBK, n0, &full[st]);
+            uint32_t c = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / nt) * kGemmBM, n0 = (tile % nt) * BN;
+                for (int kb = 0; kb < nk; ++kb, ++c) {
+                    const int st = c % kGemmStages;
+                    mbar_wait(&empty[st], ((c / kGemmStages) & 1) ^ 1);
+                    uint8_t* sa = gsm + (size_t)st * kStageBytes;
+                    mbar_expect_tx(&full[st], kStageBytes);
+                    tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
+                    tma_load_2d(sa + kABytes, &tmB, kb * kGemmBK, n0, &full[st]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
-            for (int kb = 0; kb < nk; ++kb) {
-                const int st = kb % kGemmStages;
-                mbar_wait(&full[st], (kb / kGemmStages) & 1);
+            uint32_t c = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+                const uint32_t as = ti & 1;
+                mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator stage
                 tc_fence_after();
-                const uint8_t* sa = gsm + (size_t)st * kStageBytes;
-                const uint64_t adesc = umma_smem_desc_sw128(sa), bdesc = umma_smem_desc_sw128(sa + kABytes);
+                const uint32_t tacc = tmem_base + as * kAccCols;
+                for (int kb = 0; kb < nk; ++kb, ++c) {
+                    const int st = c % kGemmStages;
+                    mbar_wait(&full[st], (c / kGemmStages) & 1);
+                    tc_fence_after();
+                    const uint8_t* sa = gsm + (size_t)st * kStageBytes;
+                    const uint64_t adesc = umma_smem_desc_sw128(sa), bdesc = umma_smem_desc_sw128(sa + kABytes);
 #pragma unroll
-                for (int k = 0; k < kGemmBK / 16; ++k)   // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                umma_commit(&empty[st]);                 // slot reusable once these MMAs have read it
+                    for (int k = 0; k < kGemmBK / 16; ++k)   // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (>>4) address field
+                        umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[st]);                 // slot reusable once these MMAs have read it
+                }
+                umma_commit(&acc_full[as]);                  // accumulator of this tile complete
             }
-            umma_commit(&acc_ready);                     // accumulator complete
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4, thread == output row =====
+        // ===== epilogue: warps 2..17; TMEM lane quarter = warp % 4 (hardware rule), column slice = (warp - 2) / 4; thread == output row =====
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(&acc_ready, 0);
-        tc_fence_after();
+        const int cslice = (warp - 2) >> 2;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            const int m0 = (tile / nt) * kGemmBM, n0 = (tile % nt) * BN;
+            const uint32_t as = ti & 1;
+            const int row = m0 + q * 32 + lane;
+            mbar_wait(&acc_full[as], (ti >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (row < g.M) {
-                const int col = n0 + c0;
-                if (EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16) {
-                    uint16_t* o = reinterpret_cast<uint16_t*>(g.out) + (size_t)row * g.ldo + col;
+            for (int c0 = cslice * (BN / 4); c0 < (cslice + 1) * (BN / 4); c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (row < g.M) {
+                    const int col = n0 + c0;
+                    if (EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16) {
+                        uint16_t* o = reinterpret_cast<uint16_t*>(g.out) + (size_t)row * g.ldo + col;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (col + j < g.N) {
-                            uint32_t pk[4];
+                        for (int j = 0; j < 32; j += 8) {
+                            if (col + j < g.N) {
+                                uint32_t pk[4];
+                                const float4 b0 = g.bias ? *reinterpret_cast<const float4*>(g.bias + col + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 b1 = g.bias ? *reinterpret_cast<const float4*>(g.bias + col + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                            for (int e = 0; e < 8; e += 2) {
-                                float v0 = __uint_as_float(r[j + e]) + (g.bias ? g.bias[col + j + e] : 0.f);
-                                float v1 = __uint_as_float(r[j + e + 1]) + (g.bias ? g.bias[col + j + e + 1] : 0.f);
-                                if (EPI == GEPI_BIAS_GELU_BF16) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); }
-                                pk[e >> 1] = (uint32_t)f32_to_bf16_rne(v0) | ((uint32_t)f32_to_bf16_rne(v1) << 16);
-                            }
-                            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
-                    }
-                } else {
-                    float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
-                    const uint16_t* rs = (EPI == GEPI_BIAS_RESID_F32 && g.resid) ? g.resid + (size_t)row * g.ldr + col : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (col + j < g.N) {
-                            float4 v;
-                            v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]); v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-                            if (EPI == GEPI_BIAS_RESID_F32) {
-                                if (g.bias) { v.x += g.bias[col + j]; v.y += g.bias[col + j + 1]; v.z += g.bias[col + j + 2]; v.w += g.bias[col + j + 3]; }
-                                if (rs) {
-                                    const uint2 rr = *reinterpret_cast<const uint2*>(rs + j);
-                                    v.x += bf16lo(rr.x); v.y += bf16hi(rr.x); v.z += bf16lo(rr.y); v.w += bf16hi(rr.y);
+                                for (int e = 0; e < 8; e += 2) {
+                                    float v0 = __uint_as_float(r[j + e]) + bb[e];
+                                    float v1 = __uint_as_float(r[j + e + 1]) + bb[e + 1];
+                                    if (EPI == GEPI_BIAS_GELU_BF16) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); }
+                                    pk[e >> 1] = pack_bf16x2(v0, v1);
                                 }
+                                *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
-                            *reinterpret_cast<float4*>(o + j) = v;
+                        }
+                    } else {
+                        float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+                        const uint16_t* rs = (EPI == GEPI_BIAS_RESID_F32 && g.resid) ? g.resid + (size_t)row * g.ldr + col : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col + j < g.N) {
+                                float4 v;
+                                v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]); v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                                if (EPI == GEPI_BIAS_RESID_F32) {
+                                    if (g.bias) {
+                                        const float4 bv = *reinterpret_cast<const float4*>(g.bias + col + j);
+                                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                                    }
+                                    if (rs) {
+                                        const uint2 rr = *reinterpret_cast<const uint2*>(rs + j);
+                                        v.x += bf16lo(rr.x); v.y += bf16hi(rr.x); v.z += bf16lo(rr.y); v.w += bf16hi(rr.y);
+                                    }
+                                }
+                                *reinterpret_cast<float4*>(o + j) = v;
+                            }
                         }
                     }
                 }
             }
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): hand the stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
