@@ -1,0 +1,202 @@
+// Element-wise kernels of the dense (tensor-core) causal-LM path: prefill and batched decode (3+ activation rows), sm_100a.
+// The GEMMs run on tcgen05 (gemm_tc.cuh) with bf16 operands; to stay within parity tolerance of the f32 oracle every f32
+// activation x is split as x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) and BOTH halves are multiplied with the same
+// staged weight tile (DUAL mode), i.e. ~16 mantissa bits on the activation side at no extra weight traffic.
+// These kernels implement the same fused steps as the GEMV epilogues in gemv.cuh.
+#pragma once
+#include "common.cuh"
+#include "gemv.cuh"
+
+namespace fl {
+
+__device__ __forceinline__ void split_hi_lo(float x, uint16_t& hi, uint16_t& lo) {
+    hi = f32_to_bf16_rne(x);
+    lo = f32_to_bf16_rne(x - __uint_as_float((uint32_t)hi << 16));
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    __syncthreads();
+    return s;
+}
+
+struct PrepArgs {
+    const uint16_t* embed;      // non-null: resid[row] = f32(embed[ids[row]])  (K1)
+    const uint32_t* ids;
+    int vocab;
+    float* resid;               // [R, K] residual stream (read, optionally updated)
+    const float* delta;         // non-null: resid[row] += sum over slices of delta[row]  (K13 / K16 residual add), ldd floats per row
+    int ldd;
+    int nsl;                    // split-K slices of delta (>= 1), summed in order: deterministic
+    long long sl_stride;
+    const float* norm_w;        // non-null: x = rms_norm(resid) * norm_w, else x = src row
+    float eps;
+    const float* src;           // plain split source [R, K] (norm_w == null, embed == null)
+    int K;
+    int t;                      // last_only: output row j takes input row (j + 1) * t - 1
+    int last_only;
+    uint16_t* xhi;              // [R_out, K]
+    uint16_t* xlo;
+};
+
+// one CTA per output row, float4-vectorised (K % 4 == 0); up to 1024 threads so a 4096-wide row is one load per thread
+static __global__ void __launch_bounds__(1024) dense_prep_kernel(const PrepArgs a) {
+    __shared__ float red[32];
+    const int orow = blockIdx.x;
+    const int row = a.last_only ? (orow + 1) * a.t - 1 : orow;
+    const int K = a.K, K4 = K >> 2;
+    uint2* xh = reinterpret_cast<uint2*>(a.xhi + (size_t)orow * K);
+    uint2* xl = reinterpret_cast<uint2*>(a.xlo + (size_t)orow * K);
+    auto emit = [&](int i, const float4& x) {
+        uint16_t h0, l0, h1, l1, h2, l2, h3, l3;
+        split_hi_lo(x.x, h0, l0); split_hi_lo(x.y, h1, l1); split_hi_lo(x.z, h2, l2); split_hi_lo(x.w, h3, l3);
+        xh[i] = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+        xl[i] = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    };
+    if (a.norm_w == nullptr && a.embed == nullptr) {      // plain hi/lo split of an f32 row
+        const float4* s = reinterpret_cast<const float4*>(a.src + (size_t)row * K);
+        for (int i = threadIdx.x; i < K4; i += blockDim.x) emit(i, s[i]);
+        return;
+    }
+    float4* r = reinterpret_cast<float4*>(a.resid + (size_t)row * K);
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < K4; i += blockDim.x) {
+        float4 v;
+        if (a.embed) {
+            uint32_t id = a.ids[row];
+            if (id >= (uint32_t)a.vocab) id = a.vocab - 1;
+            const uint2 e = reinterpret_cast<const uint2*>(a.embed + (size_t)id * K)[i];
+            v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
+            r[i] = v;
+        } else {
+            v = r[i];
+            if (a.delta) {
+                float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < a.nsl; ++s) {         // fixed order: deterministic split-K reduction
+                    const float4 p = reinterpret_cast<const float4*>(a.delta + (size_t)s * a.sl_stride + (size_t)row * a.ldd)[i];
+                    ds.x += p.x; ds.y += p.y; ds.z += p.z; ds.w += p.w;
+                }
+                v.x += ds.x; v.y += ds.y; v.z += ds.z; v.w += ds.w;
+                r[i] = v;
+            }
+        }
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    __syncthreads();
+    const float tot = block_sum_256(ss, red);
+    const float m = sqrtf(tot / (float)K + a.eps);       // candle rms_norm: x / sqrt(mean(x^2) + eps) * w
+    for (int i = threadIdx.x; i < K4; i += blockDim.x) {
+        const float4 v = r[i];
+        const float4 wv = reinterpret_cast<const float4*>(a.norm_w)[i];
+        emit(i, make_float4(v.x / m * wv.x, v.y / m * wv.y, v.z / m * wv.z, v.w / m * wv.w));
+    }
+}
+
+struct QkvEpiArgs {
+    int nsl;                   // split-K slices of y
+    long long sl_stride;
+    const float* y;            // [nsl][R, nqkv] GEMM output in the permuted row order of wqkv
+    const float* bias;         // [nqkv] or null
+    float* q_out;              // [R, nh*d]
+    uint16_t* kpool;
+    uint16_t* vpool;
+    const int* page_table;
+    int pt_stride;
+    const StepState* state;
+    const float* rope_cos;
+    const float* rope_sin;
+    int nh, nkv, d, max_pos, t, nqkv;
+};
+
+// bias + RoPE (rotate-half) + q store + paged KV append; thread per column pair, grid.y = row
+static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
+    const int row = blockIdx.y;
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair * 2 >= a.nqkv) return;
+    const int ra = pair * 2;
+    const int d = a.d, half = d >> 1;
+    const int hh = ra / d, j = (ra % d) >> 1;
+    float va = 0.f, vb = 0.f;
+    for (int s = 0; s < a.nsl; ++s) {
+        const float2 p = *reinterpret_cast<const float2*>(a.y + (size_t)s * a.sl_stride + (size_t)row * a.nqkv + ra);
+        va += p.x;
+        vb += p.y;
+    }
+    if (a.bias) { va += a.bias[ra]; vb += a.bias[ra + 1]; }
+    const int seq = row / a.t, irel = row % a.t;
+    const int slot = a.state->kv_base[seq] + irel;
+    const int page = a.page_table[seq * a.pt_stride + slot / kKvPage];
+    if (hh < a.nh + a.nkv) {
+        int pos = a.state->rope_pos + irel;
+        pos = pos < a.max_pos ? pos : a.max_pos - 1;
+        const float cs = a.rope_cos[(size_t)pos * half + j], sn = a.rope_sin[(size_t)pos * half + j];
+        const float o1 = va * cs - vb * sn, o2 = va * sn + vb * cs;
+        if (hh < a.nh) {
+            float* q = a.q_out + ((size_t)row * a.nh + hh) * d;
+            q[j] = o1;
+            q[j + half] = o2;
+        } else {
+            uint16_t* kp = a.kpool + (((size_t)page * a.nkv + (hh - a.nh)) * kKvPage + slot % kKvPage) * d;
+            kp[j] = f32_to_bf16_rne(o1);
+            kp[j + half] = f32_to_bf16_rne(o2);
+        }
+    } else {
+        uint16_t* vp = a.vpool + (((size_t)page * a.nkv + (hh - a.nh - a.nkv)) * kKvPage + slot % kKvPage) * d;
+        *reinterpret_cast<uint32_t*>(vp + 2 * j) = (uint32_t)f32_to_bf16_rne(va) | ((uint32_t)f32_to_bf16_rne(vb) << 16);
+    }
+}
+
+// act = silu(gate) * up from the interleaved gate|up GEMM output, written directly as the hi/lo split the down GEMM reads
+static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int I, uint16_t* __restrict__ xhi,
+                                               uint16_t* __restrict__ xlo) {
+    const int row = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= I) return;
+    float2 gu = make_float2(0.f, 0.f);
+    for (int s = 0; s < nsl; ++s) {
+        const float2 p = *reinterpret_cast<const float2*>(y + (size_t)s * sl_stride + (size_t)row * 2 * I + 2 * j);
+        gu.x += p.x;
+        gu.y += p.y;
+    }
+    const float act = gu.x / (1.f + expf(-gu.x)) * gu.y;
+    uint16_t h, l;
+    split_hi_lo(act, h, l);
+    xhi[(size_t)row * I + j] = h;
+    xlo[(size_t)row * I + j] = l;
+}
+
+// arg-max over the vocabulary, one CTA per row, last index wins ties (candle LogitsProcessor::sample_argmax)
+// (also folds the split-K slices of the lm_head GEMM into the f32 logits buffer the caller reads)
+static __global__ void __launch_bounds__(256) dense_argmax_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int V,
+                                                                  float* __restrict__ logits, uint32_t* __restrict__ next_ids) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    float* l = logits + (size_t)blockIdx.x * V;
+    float v = -INFINITY;
+    int idx = -1;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        float x = 0.f;
+        for (int s = 0; s < nsl; ++s) x += y[(size_t)s * sl_stride + (size_t)blockIdx.x * V + i];
+        l[i] = x;
+        if (x >= v) { v = x; idx = i; }      // i ascends per thread: >= keeps the last
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
+        if (ov > v || (ov == v && oi > idx)) { v = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (sv[w] > v || (sv[w] == v && si[w] > idx)) { v = sv[w]; idx = si[w]; }
+        next_ids[blockIdx.x] = (uint32_t)idx;
+    }
+}
+
+}  // namespace fl

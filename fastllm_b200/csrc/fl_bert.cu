@@ -44,14 +44,14 @@ CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64
 template <int EPI>
 static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
     constexpr int BN = 128;
-    const size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
+    const size_t smem = gemm_smem_bytes(BN, DUAL_NONE);
     static bool attr_set = false;
     if (!attr_set) {
         FL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int tiles = ((g.M + kGemmBM - 1) / kGemmBM) * ((g.N + BN - 1) / BN);
-    gemm_tc_kernel<BN, EPI><<<std::min(tiles, kNumSMs), kGemmThreads, smem, st>>>(tmA, tmB, g);
+    gemm_tc_kernel<BN, EPI><<<std::min(tiles, kNumSMs), kGemmThreads, smem, st>>>(tmA, tmA, tmB, g);
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
@@ -231,18 +231,18 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
     for (int l = 0; l < m.L; ++l) {
         const BertLayerW& w = m.layers[l];
         // B2: fused q|k|v projection + bias -> bf16 [T, 3H]
-        launch_gemm<GEPI_BIAS_BF16>(st, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H});
+        launch_gemm<GEPI_BIAS_BF16>(st, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
         // B3+B4: per (sentence, head) softmax(QK^T / sqrt(d)) V, no mask
         bert_attn_kernel<<<dim3(m.nh, b), 128, 0, st>>>(m.qkv.p, t, H, scale, m.ctx.p);
         g_launches.fetch_add(1);
         // B5: attention output dense + bias + residual -> f32, then LayerNorm -> bf16
-        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H});
+        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
         layernorm_kernel<<<(T + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(m.pre.p, w.ln1w, w.ln1b, T, H, eps, m.x1.p);
         g_launches.fetch_add(1);
         // B6: intermediate dense + bias + GELU(tanh) -> bf16 [T, I]
-        launch_gemm<GEPI_BIAS_GELU_BF16>(st, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I});
+        launch_gemm<GEPI_BIAS_GELU_BF16>(st, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
         // B7: output dense + bias + residual -> f32, LayerNorm -> bf16
-        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H});
+        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H, 1, 0});
         layernorm_kernel<<<(T + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(m.pre.p, w.ln2w, w.ln2b, T, H, eps, m.x.p);
         g_launches.fetch_add(1);
     }

@@ -5,6 +5,8 @@
 
 #include "attn_decode.cuh"
 #include "decode_persistent.cuh"
+#include "dense_ops.cuh"
+#include "gemm_tc.cuh"
 #include "elementwise.cuh"
 #include "gemv.cuh"
 #include "model.cuh"
@@ -334,6 +336,17 @@ static void finalize(Weights& w) {
         }
     FL_CUDA(cudaMemcpy(w.rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
     FL_CUDA(cudaMemcpy(w.rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+    w.dense_ok = !env_flag("FL_NO_DENSE") && (w.nh * w.d) % 8 == 0 && w.H % 8 == 0 && w.I % 8 == 0 && w.nqkv % 4 == 0 && w.V % 4 == 0 && w.H % 4 == 0;
+    if (w.dense_ok) {
+        const uint64_t nq = (uint64_t)w.nh * w.d;
+        for (LayerW& lw : w.layers) {
+            lw.tm_wqkv = make_tmap_bf16(lw.wqkv, w.nqkv, w.H, w.H, 128);
+            lw.tm_wo = make_tmap_bf16(lw.wo, w.H, nq, nq, 128);
+            lw.tm_wgu = make_tmap_bf16(lw.wgu, 2 * (uint64_t)w.I, w.H, w.H, 128);
+            lw.tm_wdown = make_tmap_bf16(lw.wdown, w.H, w.I, w.I, 128);
+        }
+        w.tm_head = make_tmap_bf16(w.lm_head, w.V, w.H, w.H, 128);
+    }
     std::vector<PkLayer> pk(w.L);
     for (int l = 0; l < w.L; ++l)
         pk[l] = PkLayer{w.layers[l].wqkv, w.layers[l].bqkv, w.layers[l].wo, w.layers[l].wgu, w.layers[l].wdown, w.layers[l].ln1, w.layers[l].ln2};
@@ -495,9 +508,15 @@ static void cache_destroy_graphs(fl_cache& c) {
 // Enqueue the whole forward for the flattened [b, t] call on lc.stream.  Rows are processed in passes of kPassRows,
 // pass-major / layer-minor: a token's layer-l attention only needs the layer-l K/V of EARLIER tokens, which earlier
 // passes already appended, so the order is causal-correct.
+static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode);
+
 static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode) {
     const Weights& w = *c.w;
     const int rows = b * t;
+    if (rows >= 3 && w.dense_ok && c.dw.rows >= (size_t)rows) {   // workspace is reserved by the caller (never during capture)
+        enqueue_forward_dense(c, lc, b, t, loop_mode);
+        return;
+    }
     const size_t nq = (size_t)w.nh * w.d;
     const GemvPlan p_qkv = plan_gemv(w.nqkv, w.H), p_o = plan_gemv(w.H, (int)nq), p_gu = plan_gemv(2 * w.I, w.H),
                    p_down = plan_gemv(w.H, w.I), p_head = plan_gemv(w.V, w.H);
@@ -569,6 +588,162 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
            loop_mode ? c.trace_pos.p : (int*)nullptr);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Dense (tcgen05) path: prefill and batched decode with 3+ activation rows
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDenseAttnChunk = 64;
+constexpr int kDenseMaxSplit = 8;     // split-K slices (only when there are too few output tiles to fill the GPU)
+
+static void ensure_dense_ws(fl_cache& c, int rows) {
+    DenseWs& d = c.dw;
+    if ((size_t)rows <= d.rows) return;
+    const Weights& w = *c.w;
+    FL_CUDA(cudaStreamSynchronize(c.stream));
+    for (auto& kv : c.graphs)            // captured graphs hold the old workspace pointers
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c.graphs.clear();
+    const size_t R = rows, nq = (size_t)w.nh * w.d;
+    const size_t kmax = std::max<size_t>(std::max<size_t>(w.H, nq), w.I);
+    const size_t nmax = std::max<size_t>(std::max<size_t>(w.nqkv, 2 * (size_t)w.I), std::max<size_t>(w.H, w.V));
+    d.xhi.alloc(R * kmax); d.xlo.alloc(R * kmax);
+    d.y.alloc(R * nmax * (R <= 128 ? kDenseMaxSplit : 1));
+    d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
+    d.chunk = std::min(rows, kDenseAttnChunk);
+    d.part_acc.alloc((size_t)d.chunk * w.nh * c.nsplit * w.d);
+    d.part_ml.alloc((size_t)d.chunk * w.nh * c.nsplit * 2);
+    d.counters.alloc((size_t)d.chunk * w.nkv, true);
+    d.rows = R;
+}
+
+template <int BN, int EPI, int DUAL>
+static void launch_gemm_tc(cudaStream_t st, int items, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g) {
+    const size_t smem = gemm_smem_bytes(BN, DUAL);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    gemm_tc_kernel<BN, EPI, DUAL><<<std::min(items, kNumSMs), kGemmThreads, smem, st>>>(a, a2, b, g);
+}
+
+// out[ks][R, N] (f32, row stride N, slice stride R*N) = (xhi + xlo)[R, K] . W[N, K]^T; returns the number of split-K slices,
+// which the consumer kernel sums in a fixed order (deterministic, no atomics, no memset).
+//   R <= 128 (decode batches, short prefills): swap-AB -- the weights are the 128-row MMA operand, the activations a tiny
+//             N = R tile, the result is stored transposed; the only large shared-memory traffic is the weight stream.
+//   R  > 128 (prefill): tokens are the M dimension, 128 x 128 output tiles.
+static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N, int K, const CUtensorMap& tmW, float* out) {
+    const int nk = (K + kGemmBK - 1) / kGemmBK;
+    const bool swap = R <= 128;
+    const int tiles = swap ? (N + 127) / 128 : ((R + kGemmBM - 1) / kGemmBM) * ((N + 127) / 128);
+    int ks = 1;
+    if (swap && tiles < 2 * kNumSMs) ks = std::max(1, std::min(std::min(nk / 4, kDenseMaxSplit), (2 * kNumSMs + tiles - 1) / tiles));
+    ProfEntry pe;
+    const bool prof = g_prof.on && !lc.capturing;
+    if (prof) {
+        pe.tag = tag;
+        pe.bytes = (uint64_t)N * K * 2;
+        FL_CUDA(cudaEventCreate(&pe.e0));
+        FL_CUDA(cudaEventCreate(&pe.e1));
+        FL_CUDA(cudaEventRecord(pe.e0, lc.stream));
+    }
+    if (swap) {
+        const int bn = R <= 16 ? 16 : (R <= 32 ? 32 : (R <= 64 ? 64 : 128));
+        const CUtensorMap hi = make_tmap_bf16(c.dw.xhi.p, R, K, K, bn), lo = make_tmap_bf16(c.dw.xlo.p, R, K, K, bn);
+        GemmArgs g{N, R, K, nullptr, nullptr, 0, out, N, ks, (long long)R * N};     // M = weight rows, N = activation rows
+        switch (bn) {
+            case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
+            case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
+            case 64: launch_gemm_tc<64, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
+            default: launch_gemm_tc<128, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
+        }
+    } else {
+        const CUtensorMap hi = make_tmap_bf16(c.dw.xhi.p, R, K, K, kGemmBM), lo = make_tmap_bf16(c.dw.xlo.p, R, K, K, kGemmBM);
+        GemmArgs g{R, N, K, nullptr, nullptr, 0, out, N, 1, (long long)R * N};
+        launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, tiles, hi, lo, tmW, g);
+    }
+    if (prof) {
+        FL_CUDA(cudaEventRecord(pe.e1, lc.stream));
+        g_prof.entries.push_back(pe);
+    }
+    if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ks;
+}
+
+static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode) {
+    const Weights& w = *c.w;
+    DenseWs& d = c.dw;
+    const int R = b * t;
+    const int nq = w.nh * w.d;
+    const bool saved_pdl = lc.pdl;
+    lc.pdl = false;                       // the tcgen05 GEMMs do not take part in programmatic dependent launch
+    const float qscale = (float)(1.0 / std::sqrt((double)w.d));
+    const bool windowed = (w.cfg.arch != FL_ARCH_LLAMA) && w.cfg.sliding_window > 0 && t > 1;
+    const size_t attn_smem = attn_smem_bytes(w.d, w.nh / w.nkv);
+
+    auto prep = [&](const char* tag, PrepArgs pa, int rows_out) {
+        pa.xhi = d.xhi.p; pa.xlo = d.xlo.p; pa.eps = w.cfg.norm_eps; pa.t = t;
+        const int threads = std::min(1024, std::max(32, (pa.K / 4 + 31) / 32 * 32));
+        launch(lc, tag, 0, dense_prep_kernel, dim3(rows_out), dim3(threads), 0, pa);
+    };
+    {   // K1 + K2 of layer 0
+        PrepArgs pa{};
+        pa.embed = w.embed; pa.ids = c.ids.p; pa.vocab = w.V; pa.resid = d.resid.p; pa.norm_w = w.layers[0].ln1; pa.K = w.H;
+        prep("dense_embed_rmsnorm", pa, R);
+    }
+    for (int l = 0; l < w.L; ++l) {
+        const LayerW& lw = w.layers[l];
+        uint16_t* kpool = c.kpool.p + (size_t)l * c.layer_pool_elems;
+        uint16_t* vpool = c.vpool.p + (size_t)l * c.layer_pool_elems;
+        int ks = dense_gemm(c, lc, "gemm_tc_qkv", R, w.nqkv, w.H, lw.tm_wqkv, d.y.p);
+        QkvEpiArgs qa{ks, (long long)R * w.nqkv, d.y.p, lw.bqkv, d.q.p, kpool, vpool, c.page_table.p, c.pages_per_seq, c.state.p, w.rope_cos,
+                      w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t, w.nqkv};
+        launch(lc, "dense_qkv_rope_append", 0, dense_qkv_epi_kernel, dim3((w.nqkv / 2 + 255) / 256, R), dim3(256), 0, qa);
+        for (int r0 = 0; r0 < R; r0 += d.chunk) {
+            const int rows = std::min(d.chunk, R - r0);
+            AttnArgs at{};
+            at.q = d.q.p + (size_t)r0 * nq; at.kpool = kpool; at.vpool = vpool; at.page_table = c.page_table.p; at.pt_stride = c.pages_per_seq;
+            at.state = c.state.p; at.part_acc = d.part_acc.p; at.part_ml = d.part_ml.p; at.counters = d.counters.p;
+            at.out = d.attn.p + (size_t)r0 * nq; at.nh = w.nh; at.nkv = w.nkv; at.t = t; at.row_base = r0;
+            at.sliding_window = windowed ? w.cfg.sliding_window : 0; at.qscale = qscale;
+            // enough (row, kv head) pairs already fill the GPU: fewer, longer splits stream pages through the 2-stage ring
+            const int nsp = std::max(1, std::min(c.nsplit, (3 * kNumSMs + rows * w.nkv - 1) / (rows * w.nkv)));
+            launch_attn(lc, w.d, nsp, w.nkv, rows, attn_smem, (uint64_t)rows * (c.kv_len + t) * w.nkv * w.d * 4, at);
+        }
+        {   // attention output -> hi/lo
+            PrepArgs pa{};
+            pa.src = d.attn.p; pa.K = nq;
+            prep("dense_split", pa, R);
+        }
+        ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p);
+        {   // K13 + K14: resid += o_proj; x = rms_norm(resid) * ln2
+            PrepArgs pa{};
+            pa.resid = d.resid.p; pa.delta = d.y.p; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.norm_w = lw.ln2; pa.K = w.H;
+            prep("dense_resid_rmsnorm", pa, R);
+        }
+        ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
+        launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
+               (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
+        ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
+        PrepArgs pa{};
+        pa.resid = d.resid.p; pa.delta = d.y.p; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.K = w.H;
+        if (l + 1 < w.L) {   // K16 + next layer's K2
+            pa.norm_w = w.layers[l + 1].ln1;
+            prep("dense_resid_rmsnorm", pa, R);
+        } else {             // K16 + K17: only the last token of every sequence goes on to the lm_head
+            pa.norm_w = w.final_norm; pa.last_only = 1;
+            prep("dense_final_rmsnorm", pa, b);
+        }
+    }
+    const int ksh = dense_gemm(c, lc, "gemm_tc_lm_head", b, w.V, w.H, w.tm_head, d.y.p);
+    launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)d.y.p, ksh, (long long)b * w.V, w.V, c.logits.p,
+           c.next_ids.p);
+    launch(lc, "advance_state", 0, advance_state_kernel, dim3(1), dim3(kMaxBatch), 0, c.state.p, b, t, loop_mode ? 1 : 0, c.ids.p,
+           (const uint32_t*)c.next_ids.p, loop_mode ? 1 : 0, loop_mode ? c.trace.p : (uint32_t*)nullptr,
+           loop_mode ? c.trace_pos.p : (int*)nullptr);
+    lc.pdl = saved_pdl;
+}
+
 static GraphEntry& get_graph(fl_cache& c, int b, bool loop_mode) {
     const GraphKey key{b, loop_mode ? 1 : 0};
     auto it = c.graphs.find(key);
@@ -609,6 +784,7 @@ static void check_call(fl_cache& c, const uint32_t* ids, int b, int t, size_t ro
 
 static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t rope_offset) {
     check_call(c, ids, b, t, rope_offset, 0);
+    if (b * t >= 3 && c.w->dense_ok) ensure_dense_ws(c, b * t);
     std::memcpy(c.h_ids.p, ids, (size_t)b * t * 4);
     FL_CUDA(cudaMemcpyAsync(c.ids.p, c.h_ids.p, (size_t)b * t * 4, cudaMemcpyHostToDevice, c.stream));
     set_state_kernel<<<1, 1, 0, c.stream>>>(c.state.p, (int)rope_offset);
@@ -869,6 +1045,7 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
     use_device();
     try {
         check_call(*c, first_ids, b, 1, rope_offset, steps - 1);
+        if (b >= 3 && c->w->dense_ok) ensure_dense_ws(*c, b);
         if (c->trace_cap < (size_t)steps * b) {
             c->trace.alloc((size_t)steps * b);
             c->trace_cap = (size_t)steps * b;

@@ -12,15 +12,17 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fl {
 
-enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3 };
+enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5 };
+enum : int { DUAL_NONE = 0, DUAL_A = 1, DUAL_B = 2 };
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;          // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kGemmStages = 6;        // 6 x 32 KB (BN=128) shared-memory ring, one persistent CTA per SM
 constexpr int kGemmEpiWarps = 16;      // four per TMEM lane quarter; each takes BN/4 columns of the tile
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 
@@ -31,6 +33,8 @@ struct GemmArgs {
     int ldr;
     void* out;                  // bf16 or f32 [M, ldo]
     int ldo;
+    int ksplit;                 // >1: K is cut into ksplit ranges handled by different work items (GEPI_F32 / GEPI_ATOMIC_F32)
+    long long split_stride;     // GEPI_F32 with ksplit > 1: split s writes its partial sums to out + s * split_stride (deterministic)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -93,6 +97,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// dynamic shared memory of gemm_tc_kernel<BN, *, DUAL> (ring + 1 KB alignment slack); mirrors the constants in the kernel
+inline size_t gemm_smem_bytes(int BN, int dual) {
+    const size_t stage = (size_t)(dual == DUAL_A ? 2 : 1) * kGemmBM * kGemmBK * 2 + (size_t)(dual == DUAL_B ? 2 : 1) * BN * kGemmBK * 2;
+    const size_t stages = std::min<size_t>(196608 / stage, 8);
+    return stages * stage + 1024;
+}
+
 __device__ __forceinline__ float gelu_tanh_f(float x) {
     // candle Tensor::gelu(): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) x (1 + 0.044715 x^2)   (models/embeddings.rs:229-231)
     // Identity: 0.5 (1 + tanh(u)) = sigmoid(2u) = 1 / (1 + 2^(-2 u log2(e)))  ->  7 instructions, 2 of them MUFU (ex2, rcp);
@@ -110,29 +121,40 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 // Persistent, warp-specialised: grid = min(#SMs, #tiles); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so
 // the CTAs running concurrently share activation rows through L2).  Three pipelines: shared-memory ring (TMA -> MMA),
 // two TMEM accumulator stages (MMA -> epilogue: the epilogue of tile i overlaps the MMAs of tile i+1), and the tile walk.
-template <int BN, int EPI>
+// DUAL_A / DUAL_B: that operand is the sum of two bf16 tensors (hi + lo split of an f32 activation); both halves are
+// multiplied with the same staged tile of the other operand: ~16 mantissa bits on the activations at no extra weight traffic.
+//   DUAL_A: prefill orientation, A = activations [tokens, K] (hi, lo), B = weights [out, K].
+//   DUAL_B: swap-AB decode orientation (<= 128 activation rows): A = weights [out, K] (the 128-row MMA operand, the only
+//           large tile), B = activations [rows <= BN, K] (hi, lo); D[out, rows] is stored transposed (GEPI_F32_T) so that
+//           a warp writes 32 consecutive floats of one activation row.
+template <int BN, int EPI, int DUAL = DUAL_NONE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-    static_assert(BN % 128 == 0 && BN >= 128 && BN <= 256, "BN: UMMA N for M=128 (multiple of 16 <= 256), split in 32-column chunks over 4 epilogue warps per lane quarter");
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+               const GemmArgs g) {
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
     constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;   // 16 KB
     constexpr uint32_t kBBytes = BN * kGemmBK * 2;
-    constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    constexpr uint32_t kStageBytes = (DUAL == DUAL_A ? 2 : 1) * kABytes + (DUAL == DUAL_B ? 2 : 1) * kBBytes;
+    constexpr int kStages = (196608 / kStageBytes) < 8 ? (196608 / kStageBytes) : 8;   // <= 192 KB of ring, <= 8 stages
+    constexpr uint32_t kBOff = (DUAL == DUAL_A ? 2 : 1) * kABytes;
     constexpr uint32_t kAccCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     constexpr uint32_t kTmemCols = 2 * kAccCols;          // two accumulator stages
 
     extern __shared__ uint8_t gsm_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment; the launch adds 1024 bytes of slack for this round-up
     uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) uint64_t full[kGemmStages], empty[kGemmStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (g.K + kGemmBK - 1) / kGemmBK;
     const int mt = (g.M + kGemmBM - 1) / kGemmBM, nt = (g.N + BN - 1) / BN;
-    const int ntiles = mt * nt;
+    const int ksplit = g.ksplit > 1 ? g.ksplit : 1;
+    const int nkps = (nk + ksplit - 1) / ksplit;          // k-blocks per split
+    const int ntiles = mt * nt * ksplit;                  // work items: (m tile, n tile, k split), k split fastest
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -154,15 +176,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t c = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
+                const int tile = item / ksplit, ks = item % ksplit;
                 const int m0 = (tile / nt) * kGemmBM, n0 = (tile % nt) * BN;
-                for (int kb = 0; kb < nk; ++kb, ++c) {
-                    const int st = c % kGemmStages;
-                    mbar_wait(&empty[st], ((c / kGemmStages) & 1) ^ 1);
+                const int kb1 = min((ks + 1) * nkps, nk);
+                for (int kb = ks * nkps; kb < kb1; ++kb, ++c) {
+                    const int st = c % kStages;
+                    mbar_wait(&empty[st], ((c / kStages) & 1) ^ 1);
                     uint8_t* sa = gsm + (size_t)st * kStageBytes;
                     mbar_expect_tx(&full[st], kStageBytes);
-                    tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
-                    tma_load_2d(sa + kABytes, &tmB, kb * kGemmBK, n0, &full[st]);
+                    if (DUAL == DUAL_B) {       // tmA = weights, tmA2 / tmB = activation hi / lo
+                        tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
+                        tma_load_2d(sa + kBOff, &tmA2, kb * kGemmBK, n0, &full[st]);
+                        tma_load_2d(sa + kBOff + kBBytes, &tmB, kb * kGemmBK, n0, &full[st]);
+                    } else {
+                        tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
+                        if (DUAL == DUAL_A) tma_load_2d(sa + kABytes, &tmA2, kb * kGemmBK, m0, &full[st]);
+                        tma_load_2d(sa + kBOff, &tmB, kb * kGemmBK, n0, &full[st]);
+                    }
                 }
             }
         }
@@ -171,20 +202,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
             uint32_t c = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+            for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++ti) {
+                const int ks = item % ksplit;
+                const int kb0 = ks * nkps, kb1 = min((ks + 1) * nkps, nk);
                 const uint32_t as = ti & 1;
                 mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * kAccCols;
-                for (int kb = 0; kb < nk; ++kb, ++c) {
-                    const int st = c % kGemmStages;
-                    mbar_wait(&full[st], (c / kGemmStages) & 1);
+                for (int kb = kb0; kb < kb1; ++kb, ++c) {
+                    const int st = c % kStages;
+                    mbar_wait(&full[st], (c / kStages) & 1);
                     tc_fence_after();
                     const uint8_t* sa = gsm + (size_t)st * kStageBytes;
-                    const uint64_t adesc = umma_smem_desc_sw128(sa), bdesc = umma_smem_desc_sw128(sa + kABytes);
+                    const uint64_t adesc = umma_smem_desc_sw128(sa), bdesc = umma_smem_desc_sw128(sa + kBOff);
 #pragma unroll
                     for (int k = 0; k < kGemmBK / 16; ++k)   // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-                        umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) ? 1u : 0u);
+                    if (DUAL == DUAL_A) {
+                        const uint64_t a2desc = umma_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < kGemmBK / 16; ++k) umma_bf16(tacc, a2desc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                    } else if (DUAL == DUAL_B) {
+                        const uint64_t b2desc = umma_smem_desc_sw128(sa + kBOff + kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kGemmBK / 16; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), b2desc + (uint64_t)(2 * k), idesc, 1u);
+                    }
                     umma_commit(&empty[st]);                 // slot reusable once these MMAs have read it
                 }
                 umma_commit(&acc_full[as]);                  // accumulator of this tile complete
@@ -195,14 +237,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int cslice = (warp - 2) >> 2;
         uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++ti) {
+            const int tile = item / ksplit, ksi = item % ksplit;
             const int m0 = (tile / nt) * kGemmBM, n0 = (tile % nt) * BN;
             const uint32_t as = ti & 1;
             const int row = m0 + q * 32 + lane;
             mbar_wait(&acc_full[as], (ti >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = cslice * (BN / 4); c0 < (cslice + 1) * (BN / 4); c0 += 32) {
+            for (int c0 = cslice * 32; c0 < BN; c0 += 128) {      // 32-column chunks dealt round-robin to the 4 warps of a lane quarter
                 uint32_t r[32];
                 tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 if (row < g.M) {
@@ -226,8 +269,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         }
-                    } else {
+                    } else if (EPI == GEPI_F32_T) {
+                        // transposed store: D[row = weight row, col = activation row] -> out[slice][col, row]; for a fixed col the
+                        // 32 lanes of the warp write 32 consecutive floats
+                        float* o = reinterpret_cast<float*>(g.out) + (size_t)ksi * (size_t)g.split_stride + row;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col + j < g.N) o[(size_t)(col + j) * g.ldo] = __uint_as_float(r[j]);
+                    } else if (EPI == GEPI_ATOMIC_F32) {
+                        // split-K partial sums meet in a pre-zeroed f32 buffer (vector red.global.add, sm_90+)
                         float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (col + j < g.N)
+                                atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                    } else {
+                        float* o = reinterpret_cast<float*>(g.out) + (EPI == GEPI_F32 ? (size_t)ksi * (size_t)g.split_stride : 0) + (size_t)row * g.ldo + col;
                         const uint16_t* rs = (EPI == GEPI_BIAS_RESID_F32 && g.resid) ? g.resid + (size_t)row * g.ldr + col : nullptr;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {

@@ -22,6 +22,7 @@ struct LayerW {
     uint16_t* wdown = nullptr;  // [H, I]
     float* ln1 = nullptr;       // [H]
     float* ln2 = nullptr;       // [H]
+    CUtensorMap tm_wqkv, tm_wo, tm_wgu, tm_wdown;   // TMA descriptors of the weights (dense tcgen05 path)
 };
 
 // Immutable after finalize; shared (ref-counted) between fl_model clones and their caches.
@@ -42,6 +43,8 @@ struct Weights {
     bool lm_head_loaded = false;
     bool finalized = false;
     uint64_t streamed_bytes = 0;
+    CUtensorMap tm_head;
+    bool dense_ok = false;      // shapes admit the dense (tcgen05) path for 3+ rows
     std::mutex mu;
 };
 
@@ -50,6 +53,17 @@ struct PkPlan {
     bool ok = false;
     int nstages = 0, xs_floats = 0, partial_rows = 0, nsplit = 1;
     size_t smem = 0;
+};
+
+// Workspace of the dense (tensor-core) path, sized for the largest row count seen so far.
+struct DenseWs {
+    size_t rows = 0;
+    int chunk = 0;              // attention rows per launch
+    DevBuf<uint16_t> xhi, xlo;  // [rows, Kmax] hi/lo bf16 split of the activations fed to the next GEMM
+    DevBuf<float> y;            // [rows, Nmax] GEMM output
+    DevBuf<float> resid, q, attn;
+    DevBuf<float> part_acc, part_ml;
+    DevBuf<int> counters;
 };
 
 struct GraphKey {
@@ -88,6 +102,7 @@ struct fl_cache {
     int amax_parts = 0;
     std::map<fl::GraphKey, fl::GraphEntry> graphs;
     fl::PkPlan pk;
+    fl::DenseWs dw;
     fl::DevBuf<unsigned int> gbar;
     bool poisoned = false;
 };
