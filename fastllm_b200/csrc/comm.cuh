@@ -1,0 +1,49 @@
+// NCCL communicator owned by the library (one process per GPU; tensor parallelism over NVLink 5 / NVSwitch).
+// NCCL is resolved at run time with dlopen("libnccl.so.2"): when torch has already loaded its bundled copy the same
+// handle is returned, otherwise the system library is used; the library itself has no link-time NCCL dependency.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "common.cuh"
+
+namespace fl {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+
+    void load() {
+        if (lib) return;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        FL_CHECK(lib != nullptr, -4, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+        auto sym = [&](const char* n) {
+            void* p = dlsym(lib, n);
+            FL_CHECK(p != nullptr, -4, std::string("NCCL symbol missing: ") + n);
+            return p;
+        };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+    }
+    void check(ncclResult_t r, const char* what) {
+        if (r != ncclSuccess) throw Error(-4, std::string(what) + ": " + (GetErrorString ? GetErrorString(r) : "NCCL error"));
+    }
+};
+
+extern NcclApi g_nccl;
+
+}  // namespace fl

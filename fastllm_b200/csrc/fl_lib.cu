@@ -4,6 +4,7 @@
 #include <sstream>
 
 #include "attn_decode.cuh"
+#include "comm.cuh"
 #include "decode_persistent.cuh"
 #include "dense_ops.cuh"
 #include "gemm_tc.cuh"
@@ -17,6 +18,7 @@ namespace fl {
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 Profiler g_prof;
+NcclApi g_nccl;
 static std::atomic<int> g_device{-1};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -132,10 +134,21 @@ static void validate_config(const fl_config& c) {
 
 static void build_weights(Weights& w) {
     const fl_config& c = w.cfg;
-    w.H = c.hidden_size; w.I = c.intermediate_size; w.V = c.vocab_size; w.L = c.num_hidden_layers;
-    w.nh = c.num_attention_heads;
-    w.nkv = c.num_key_value_heads > 0 ? c.num_key_value_heads : c.num_attention_heads;
-    w.d = w.H / w.nh;
+    const int nh_f = c.num_attention_heads, nkv_f = c.num_key_value_heads > 0 ? c.num_key_value_heads : c.num_attention_heads;
+    w.tp = c.tp_size > 1 ? c.tp_size : 1;
+    w.rank = w.tp > 1 ? c.tp_rank : 0;
+    FL_CHECK(w.rank >= 0 && w.rank < w.tp, FL_ERR_INVALID, "tp_rank out of range");
+    if (w.tp > 1) {
+        // column-parallel q/k/v (by head) and gate/up, row-parallel o_proj and down_proj, vocab-parallel lm_head
+        FL_CHECK(nh_f % w.tp == 0 && nkv_f % w.tp == 0, FL_ERR_UNSUPPORTED, "tensor parallelism needs heads and kv heads divisible by tp_size");
+        FL_CHECK(c.intermediate_size % (8 * w.tp) == 0 && c.vocab_size % (2 * w.tp) == 0, FL_ERR_UNSUPPORTED,
+                 "tensor parallelism needs intermediate_size % (8 tp) == 0 and vocab_size % (2 tp) == 0");
+    }
+    w.H = c.hidden_size; w.L = c.num_hidden_layers;
+    w.I = c.intermediate_size / w.tp; w.Vfull = c.vocab_size; w.V = c.vocab_size / w.tp;
+    w.nh = nh_f / w.tp;
+    w.nkv = nkv_f / w.tp;
+    w.d = w.H / nh_f;
     w.max_pos = c.max_position_embeddings;
     w.nqkv = (w.nh + 2 * w.nkv) * w.d;
     FL_CHECK(w.d == 16 || w.d == 32 || w.d == 64 || w.d == 128, FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
@@ -145,7 +158,7 @@ static void build_weights(Weights& w) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, A); return o; };
     const size_t H = w.H, I = w.I, V = w.V, nq = (size_t)w.nh * w.d;
-    const size_t o_embed = take(V * H * 2), o_head = take(V * H * 2), o_fnorm = take(H * 4);
+    const size_t o_embed = take((size_t)w.Vfull * H * 2), o_head = take(V * H * 2), o_fnorm = take(H * 4);
     struct LO { size_t wqkv, bqkv, wo, wgu, wdown, ln1, ln2; };
     std::vector<LO> lo(w.L);
     for (int l = 0; l < w.L; ++l) {
@@ -183,18 +196,31 @@ static void build_weights(Weights& w) {
 struct TensorRoute {
     enum Kind { BF16_MAT, F32_VEC } kind;
     void* base;
-    int64_t rows, cols;   // logical shape expected ([rows, cols] or [rows])
+    int64_t rows, cols;             // LOCAL block held by this rank ([rows, cols] or [rows])
     RowMap map;
+    int64_t full_rows, full_cols;   // shape the caller hands over (the full HF tensor)
+    int64_t src_row0, src_col0;     // window of the full tensor this rank keeps
 };
 
 static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
-    const int64_t H = w.H, I = w.I, V = w.V, d = w.d, nq = (int64_t)w.nh * d, nk = (int64_t)w.nkv * d;
-    auto mat = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m) { r = {TensorRoute::BF16_MAT, base, rows, cols, m}; return true; };
-    auto vec = [&](float* base, int64_t rows, RowMap m) { r = {TensorRoute::F32_VEC, base, rows, 1, m}; return true; };
+    const int64_t H = w.H, I = w.I, d = w.d, nq = (int64_t)w.nh * d, nk = (int64_t)w.nkv * d, tp = w.tp, rk = w.rank;
+    // row-sharded matrix: local rows [rk*rows, (rk+1)*rows) of a [tp*rows, cols] tensor; col-sharded: the same along columns
+    auto mat_rows = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m, bool sharded) {
+        r = {TensorRoute::BF16_MAT, base, rows, cols, m, sharded ? rows * tp : rows, cols, sharded ? rk * rows : 0, 0};
+        return true;
+    };
+    auto mat_cols = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m) {
+        r = {TensorRoute::BF16_MAT, base, rows, cols, m, rows, cols * tp, 0, rk * cols};
+        return true;
+    };
+    auto vec = [&](float* base, int64_t rows, RowMap m, bool sharded) {
+        r = {TensorRoute::F32_VEC, base, rows, 1, m, sharded ? rows * tp : rows, 1, sharded ? rk * rows : 0, 0};
+        return true;
+    };
     const RowMap ident{0, 0, 0, 0};
-    if (name == "model.embed_tokens.weight") return mat(w.embed, V, H, ident);
-    if (name == "lm_head.weight") return mat(w.lm_head, V, H, ident);
-    if (name == "model.norm.weight") return vec(w.final_norm, H, ident);
+    if (name == "model.embed_tokens.weight") return mat_rows(w.embed, w.Vfull, H, ident, false);
+    if (name == "lm_head.weight") return mat_rows(w.lm_head, w.V, H, ident, true);
+    if (name == "model.norm.weight") return vec(w.final_norm, H, ident, false);
     const std::string pre = "model.layers.";
     if (name.compare(0, pre.size(), pre) != 0) return false;
     size_t dot = name.find('.', pre.size());
@@ -205,20 +231,20 @@ static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
     LayerW& lw = w.layers[li];
     const std::string rest = name.substr(dot + 1);
     const RowMap ropeq{0, 1, (int32_t)d, 0}, ropek{nq, 1, (int32_t)d, 0}, vmap{nq + nk, 0, 0, 0};
-    if (rest == "input_layernorm.weight") return vec(lw.ln1, H, ident);
-    if (rest == "post_attention_layernorm.weight") return vec(lw.ln2, H, ident);
-    if (rest == "self_attn.q_proj.weight") return mat(lw.wqkv, nq, H, ropeq);
-    if (rest == "self_attn.k_proj.weight") return mat(lw.wqkv, nk, H, ropek);
-    if (rest == "self_attn.v_proj.weight") return mat(lw.wqkv, nk, H, vmap);
+    if (rest == "input_layernorm.weight") return vec(lw.ln1, H, ident, false);
+    if (rest == "post_attention_layernorm.weight") return vec(lw.ln2, H, ident, false);
+    if (rest == "self_attn.q_proj.weight") return mat_rows(lw.wqkv, nq, H, ropeq, true);
+    if (rest == "self_attn.k_proj.weight") return mat_rows(lw.wqkv, nk, H, ropek, true);
+    if (rest == "self_attn.v_proj.weight") return mat_rows(lw.wqkv, nk, H, vmap, true);
     if (w.cfg.qkv_bias) {
-        if (rest == "self_attn.q_proj.bias") return vec(lw.bqkv, nq, ropeq);
-        if (rest == "self_attn.k_proj.bias") return vec(lw.bqkv, nk, ropek);
-        if (rest == "self_attn.v_proj.bias") return vec(lw.bqkv, nk, vmap);
+        if (rest == "self_attn.q_proj.bias") return vec(lw.bqkv, nq, ropeq, true);
+        if (rest == "self_attn.k_proj.bias") return vec(lw.bqkv, nk, ropek, true);
+        if (rest == "self_attn.v_proj.bias") return vec(lw.bqkv, nk, vmap, true);
     }
-    if (rest == "self_attn.o_proj.weight") return mat(lw.wo, H, nq, ident);
-    if (rest == "mlp.gate_proj.weight") return mat(lw.wgu, I, H, RowMap{0, 2, 0, 0});
-    if (rest == "mlp.up_proj.weight") return mat(lw.wgu, I, H, RowMap{0, 2, 0, 1});
-    if (rest == "mlp.down_proj.weight") return mat(lw.wdown, H, I, ident);
+    if (rest == "self_attn.o_proj.weight") return mat_cols(lw.wo, H, nq, ident);
+    if (rest == "mlp.gate_proj.weight") return mat_rows(lw.wgu, I, H, RowMap{0, 2, 0, 0}, true);
+    if (rest == "mlp.up_proj.weight") return mat_rows(lw.wgu, I, H, RowMap{0, 2, 0, 1}, true);
+    if (rest == "mlp.down_proj.weight") return mat_cols(lw.wdown, H, I, ident);
     return false;
 }
 
@@ -242,20 +268,26 @@ static void put_tensor(Weights& w, const char* name, int dtype, const int64_t* s
     FL_CHECK(route_tensor(w, name, r), FL_ERR_INVALID, std::string("unknown tensor name: ") + name);
     int64_t numel = 1;
     for (int i = 0; i < rank; ++i) numel *= shape[i];
-    const bool shape_ok = (r.kind == TensorRoute::BF16_MAT) ? (rank == 2 && shape[0] == r.rows && shape[1] == r.cols)
-                                                            : (rank == 1 && shape[0] == r.rows);
+    const bool shape_ok = (r.kind == TensorRoute::BF16_MAT) ? (rank == 2 && shape[0] == r.full_rows && shape[1] == r.full_cols)
+                                                            : (rank == 1 && shape[0] == r.full_rows);
     FL_CHECK(shape_ok, FL_ERR_INVALID, std::string("shape mismatch for ") + name);
     FL_CHECK(dtype == FL_DTYPE_F32 || dtype == FL_DTYPE_BF16 || dtype == FL_DTYPE_F16, FL_ERR_INVALID, "bad dtype");
-    // convert to bf16 bit patterns (round-to-nearest-even), the dtype the reference server loads into (main.rs:120)
+    // keep this rank's window of the full tensor, converted to bf16 bit patterns (round-to-nearest-even), the dtype the
+    // reference server loads into (main.rs:120)
+    numel = r.rows * r.cols;
     std::vector<uint16_t> bits((size_t)numel);
-    if (dtype == FL_DTYPE_BF16) {
-        std::memcpy(bits.data(), host, (size_t)numel * 2);
-    } else if (dtype == FL_DTYPE_F32) {
-        const float* f = (const float*)host;
-        for (int64_t i = 0; i < numel; ++i) bits[i] = host_f32_to_bf16(f[i]);
-    } else {
-        const uint16_t* h = (const uint16_t*)host;
-        for (int64_t i = 0; i < numel; ++i) bits[i] = host_f32_to_bf16(host_f16_to_f32(h[i]));
+    for (int64_t lr = 0; lr < r.rows; ++lr) {
+        const int64_t src = (lr + r.src_row0) * r.full_cols + r.src_col0;
+        uint16_t* dstp = bits.data() + (size_t)lr * r.cols;
+        if (dtype == FL_DTYPE_BF16) {
+            std::memcpy(dstp, (const uint16_t*)host + src, (size_t)r.cols * 2);
+        } else if (dtype == FL_DTYPE_F32) {
+            const float* f = (const float*)host + src;
+            for (int64_t i = 0; i < r.cols; ++i) dstp[i] = host_f32_to_bf16(f[i]);
+        } else {
+            const uint16_t* h = (const uint16_t*)host + src;
+            for (int64_t i = 0; i < r.cols; ++i) dstp[i] = host_f32_to_bf16(host_f16_to_f32(h[i]));
+        }
     }
     if (r.kind == TensorRoute::BF16_MAT) {
         uint16_t* dst = (uint16_t*)r.base;
@@ -295,11 +327,12 @@ static void random_init(Weights& w, uint64_t seed, float stdv) {
         const bool is_norm = n.size() >= 11 && n.compare(n.size() - 11, 11, "norm.weight") == 0;
         const uint64_t ts = tensor_seed(seed, n.c_str());
         if (r.kind == TensorRoute::BF16_MAT) {
-            synth_fill_bf16_kernel<<<kNumSMs * 8, 256>>>((uint16_t*)r.base, r.rows, r.cols, ts, stdv, r.map);
+            synth_fill_bf16_kernel<<<kNumSMs * 8, 256>>>((uint16_t*)r.base, r.rows, r.cols, ts, stdv, r.map,
+                                                         SrcWin{r.src_row0, r.src_col0, r.full_cols});
         } else if (is_norm) {
             fill_f32_kernel<<<8, 256>>>((float*)r.base, r.rows, 1.0f);
         } else {
-            synth_fill_f32_kernel<<<8, 256>>>((float*)r.base, r.rows, ts, stdv, r.map);
+            synth_fill_f32_kernel<<<8, 256>>>((float*)r.base, r.rows, ts, stdv, r.map, r.src_row0);
         }
         g_launches.fetch_add(1);
         w.have.insert(n);
@@ -356,6 +389,20 @@ static void finalize(Weights& w) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Tensor-parallel collectives (NCCL over NVLink 5 / NVSwitch; captured into the CUDA graph with the rest of the step)
+// ------------------------------------------------------------------------------------------------------------------
+static void tp_allreduce_sum(LaunchCtx& lc, float* buf, size_t count) {
+    FL_CHECK(g_nccl.comm != nullptr, FL_ERR_STATE, "tensor parallelism: fl_comm_init has not been called");
+    g_nccl.check(g_nccl.AllReduce(buf, buf, count, ncclFloat32, ncclSum, g_nccl.comm, lc.stream), "ncclAllReduce");
+    if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+static void tp_allgather(LaunchCtx& lc, const float* send, float* recv, size_t count) {
+    FL_CHECK(g_nccl.comm != nullptr, FL_ERR_STATE, "tensor parallelism: fl_comm_init has not been called");
+    g_nccl.check(g_nccl.AllGather(send, recv, count, ncclFloat32, g_nccl.comm, lc.stream), "ncclAllGather");
+    if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Cache + forward
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kPassRows = 2;   // activation rows per CUDA-core GEMV pass
@@ -368,6 +415,7 @@ static void plan_persistent(fl_cache& c) {
     PkPlan& p = c.pk;
     p.ok = false;
     if (env_flag("FL_NO_PERSISTENT")) return;
+    if (w.tp > 1) return;                  // the persistent kernel has no in-kernel collective yet: TP uses the multi-kernel path
     const int nq = w.nh * w.d;
     if (!(w.d == 64 || w.d == 128)) return;
     if (w.H < 2048 || nq < 2048 || w.I < 2048) return;      // every row must span all 256 consumer threads
@@ -479,7 +527,12 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     c.q.alloc(kPassRows * nq);
     c.attn_out.alloc(kPassRows * nq);
     c.act.alloc((size_t)kPassRows * w.I);
-    c.logits.alloc((size_t)max_batch * w.V, true);
+    c.logits.alloc((size_t)max_batch * w.Vfull, true);
+    if (w.tp > 1) {
+        c.tp_buf.alloc((size_t)kPassRows * w.H);
+        c.tp_local.alloc((size_t)max_batch * w.V, true);
+        c.tp_gather.alloc((size_t)w.tp * max_batch * w.V);
+    }
     c.part_acc.alloc((size_t)kPassRows * w.nh * c.nsplit * w.d);
     c.part_ml.alloc((size_t)kPassRows * w.nh * c.nsplit * 2);
     c.counters.alloc((size_t)kPassRows * w.nkv, true);
@@ -487,7 +540,7 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     c.amax_val.alloc((size_t)kPassRows * c.amax_parts);
     c.amax_idx.alloc((size_t)kPassRows * c.amax_parts);
     c.h_ids.alloc((size_t)max_batch * max_seq);
-    c.h_logits.alloc((size_t)max_batch * w.V);
+    c.h_logits.alloc((size_t)max_batch * w.Vfull);
     plan_persistent(c);
     const size_t smem = attn_smem_bytes(w.d, w.nh / w.nkv);
     switch (w.d) {
@@ -531,7 +584,7 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
         for (int m = 0; m < M; ++m) has_last |= ((row_base + m) % t == t - 1);
 
         launch(lc, "embed_gather", (uint64_t)M * w.H * 2, embed_gather_kernel, dim3((w.H / 8 + 255) / 256, M), dim3(256), 0,
-               (const uint16_t*)w.embed, (const uint32_t*)c.ids.p, row_base, w.H, w.V, c.resid.p);
+               (const uint16_t*)w.embed, (const uint32_t*)c.ids.p, row_base, w.H, w.Vfull, c.resid.p);
 
         for (int l = 0; l < w.L; ++l) {
             const LayerW& lw = w.layers[l];
@@ -558,7 +611,14 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
             GemvArgs o{};
             o.row_base = row_base; o.t = t;
             o.W = lw.wo; o.N = w.H; o.K = (int)nq; o.x = c.attn_out.p; o.out = c.resid.p;
-            launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_o_resid", M, p_o, o);
+            if (w.tp > 1) {   // row-parallel: partial sums -> all-reduce -> residual add
+                o.out = c.tp_buf.p; o.ldo = w.H;
+                launch_gemv<PRO_PLAIN, EPI_STORE>(lc, "gemv_o_partial", M, p_o, o);
+                tp_allreduce_sum(lc, c.tp_buf.p, (size_t)M * w.H);
+                launch(lc, "tp_resid_add", 0, add_rows_kernel, dim3(8), dim3(256), 0, c.resid.p, (const float*)c.tp_buf.p, M * w.H);
+            } else {
+                launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_o_resid", M, p_o, o);
+            }
 
             // K14+K15: RMSNorm -> fused gate|up GEMV -> SiLU(gate) * up
             GemvArgs g{};
@@ -570,7 +630,14 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
             GemvArgs dn{};
             dn.row_base = row_base; dn.t = t;
             dn.W = lw.wdown; dn.N = w.H; dn.K = w.I; dn.x = c.act.p; dn.out = c.resid.p;
-            launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_down_resid", M, p_down, dn);
+            if (w.tp > 1) {
+                dn.out = c.tp_buf.p; dn.ldo = w.H;
+                launch_gemv<PRO_PLAIN, EPI_STORE>(lc, "gemv_down_partial", M, p_down, dn);
+                tp_allreduce_sum(lc, c.tp_buf.p, (size_t)M * w.H);
+                launch(lc, "tp_resid_add", 0, add_rows_kernel, dim3(8), dim3(256), 0, c.resid.p, (const float*)c.tp_buf.p, M * w.H);
+            } else {
+                launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_down_resid", M, p_down, dn);
+            }
         }
         if (has_last) {
             // K17 (+K18): final RMSNorm -> lm_head -> f32 logits of the last position + arg-max partials
@@ -578,10 +645,21 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
             h.row_base = row_base; h.t = t; h.eps = w.cfg.norm_eps;
             h.W = w.lm_head; h.N = w.V; h.K = w.H; h.x = c.resid.p; h.norm_w = w.final_norm;
             h.out = c.logits.p; h.ldo = w.V; h.last_only = 1; h.amax_val = c.amax_val.p; h.amax_idx = c.amax_idx.p;
-            launch_gemv<PRO_RMSNORM, EPI_STORE>(lc, "gemv_lm_head", M, p_head, h);
-            launch(lc, "argmax_finalize", 0, argmax_finalize_kernel, dim3(1), dim3(256), 0, (const float*)c.amax_val.p,
-                   (const int*)c.amax_idx.p, p_head.grid, M, row_base, t, c.next_ids.p);
+            if (w.tp > 1) {   // vocab-parallel head: this rank's slice; gathered + arg-maxed after the pass loop
+                h.out = c.tp_local.p; h.amax_val = nullptr; h.amax_idx = nullptr;
+                launch_gemv<PRO_RMSNORM, EPI_STORE>(lc, "gemv_lm_head", M, p_head, h);
+            } else {
+                launch_gemv<PRO_RMSNORM, EPI_STORE>(lc, "gemv_lm_head", M, p_head, h);
+                launch(lc, "argmax_finalize", 0, argmax_finalize_kernel, dim3(1), dim3(256), 0, (const float*)c.amax_val.p,
+                       (const int*)c.amax_idx.p, p_head.grid, M, row_base, t, c.next_ids.p);
+            }
         }
+    }
+    if (w.tp > 1) {   // gather the vocab slices of every rank, lay them out as [b, Vfull], arg-max (last index wins ties)
+        tp_allgather(lc, c.tp_local.p, c.tp_gather.p, (size_t)b * w.V);
+        launch(lc, "tp_logits", 0, tp_logits_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)c.tp_gather.p, w.tp, b, w.V, c.logits.p);
+        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)c.logits.p, 1, (long long)0, w.Vfull,
+               c.logits.p, c.next_ids.p);
     }
     launch(lc, "advance_state", 0, advance_state_kernel, dim3(1), dim3(kMaxBatch), 0, c.state.p, b, t, loop_mode ? 1 : 0, c.ids.p,
            (const uint32_t*)c.next_ids.p, loop_mode ? 1 : 0, loop_mode ? c.trace.p : (uint32_t*)nullptr,
@@ -609,6 +687,7 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     d.xhi.alloc(R * kmax); d.xlo.alloc(R * kmax);
     d.y.alloc(R * nmax * (R <= 128 ? kDenseMaxSplit : 1));
     d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
+    if (w.tp > 1) d.tp_buf.alloc(R * w.H);
     d.chunk = std::min(rows, kDenseAttnChunk);
     d.part_acc.alloc((size_t)d.chunk * w.nh * c.nsplit * w.d);
     d.part_ml.alloc((size_t)d.chunk * w.nh * c.nsplit * 2);
@@ -688,7 +767,7 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
     };
     {   // K1 + K2 of layer 0
         PrepArgs pa{};
-        pa.embed = w.embed; pa.ids = c.ids.p; pa.vocab = w.V; pa.resid = d.resid.p; pa.norm_w = w.layers[0].ln1; pa.K = w.H;
+        pa.embed = w.embed; pa.ids = c.ids.p; pa.vocab = w.Vfull; pa.resid = d.resid.p; pa.norm_w = w.layers[0].ln1; pa.K = w.H;
         prep("dense_embed_rmsnorm", pa, R);
     }
     for (int l = 0; l < w.L; ++l) {
@@ -716,17 +795,29 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             prep("dense_split", pa, R);
         }
         ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p);
+        const float* delta = d.y.p;
+        auto tp_reduce = [&]() {   // row-parallel GEMM: fold the split-K slices, then all-reduce the partial sums across ranks
+            if (w.tp <= 1) return;
+            launch(lc, "tp_sum_slices", 0, sum_slices_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)d.y.p, ks, (long long)R * w.H, R * w.H,
+                   d.tp_buf.p);
+            tp_allreduce_sum(lc, d.tp_buf.p, (size_t)R * w.H);
+            delta = d.tp_buf.p;
+            ks = 1;
+        };
+        tp_reduce();
         {   // K13 + K14: resid += o_proj; x = rms_norm(resid) * ln2
             PrepArgs pa{};
-            pa.resid = d.resid.p; pa.delta = d.y.p; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.norm_w = lw.ln2; pa.K = w.H;
+            pa.resid = d.resid.p; pa.delta = delta; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.norm_w = lw.ln2; pa.K = w.H;
             prep("dense_resid_rmsnorm", pa, R);
         }
         ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
         launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
                (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
         ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
+        delta = d.y.p;
+        tp_reduce();
         PrepArgs pa{};
-        pa.resid = d.resid.p; pa.delta = d.y.p; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.K = w.H;
+        pa.resid = d.resid.p; pa.delta = delta; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.K = w.H;
         if (l + 1 < w.L) {   // K16 + next layer's K2
             pa.norm_w = w.layers[l + 1].ln1;
             prep("dense_resid_rmsnorm", pa, R);
@@ -736,8 +827,17 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
         }
     }
     const int ksh = dense_gemm(c, lc, "gemm_tc_lm_head", b, w.V, w.H, w.tm_head, d.y.p);
-    launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)d.y.p, ksh, (long long)b * w.V, w.V, c.logits.p,
-           c.next_ids.p);
+    if (w.tp > 1) {   // vocab-parallel head
+        launch(lc, "tp_sum_slices", 0, sum_slices_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)d.y.p, ksh, (long long)b * w.V, b * w.V,
+               c.tp_local.p);
+        tp_allgather(lc, c.tp_local.p, c.tp_gather.p, (size_t)b * w.V);
+        launch(lc, "tp_logits", 0, tp_logits_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)c.tp_gather.p, w.tp, b, w.V, c.logits.p);
+        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)c.logits.p, 1, (long long)0, w.Vfull, c.logits.p,
+               c.next_ids.p);
+    } else {
+        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)d.y.p, ksh, (long long)b * w.V, w.V, c.logits.p,
+               c.next_ids.p);
+    }
     launch(lc, "advance_state", 0, advance_state_kernel, dim3(1), dim3(kMaxBatch), 0, c.state.p, b, t, loop_mode ? 1 : 0, c.ids.p,
            (const uint32_t*)c.next_ids.p, loop_mode ? 1 : 0, loop_mode ? c.trace.p : (uint32_t*)nullptr,
            loop_mode ? c.trace_pos.p : (int*)nullptr);
@@ -779,7 +879,7 @@ static void check_call(fl_cache& c, const uint32_t* ids, int b, int t, size_t ro
     // candle's Llama mask is t x t: a multi-token call on a non-empty cache is a shape error there
     FL_CHECK(!(w.cfg.arch == FL_ARCH_LLAMA && t > 1 && c.kv_len != 0), FL_ERR_INVALID,
              "Llama: multi-token forward needs an empty cache (candle builds a t x t mask)");
-    for (int i = 0; i < b * t; ++i) FL_CHECK(ids[i] < (uint32_t)w.V, FL_ERR_INVALID, "token id out of range");
+    for (int i = 0; i < b * t; ++i) FL_CHECK(ids[i] < (uint32_t)w.Vfull, FL_ERR_INVALID, "token id out of range");
 }
 
 static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t rope_offset) {
@@ -870,6 +970,9 @@ FL_EXPORT int fl_model_create(const fl_config* cfg, fl_model** out) {
         *out = new fl_model{nullptr, bm};
         return FL_OK;
     }
+    if (cfg->tp_size > 1)
+        FL_CHECK(g_nccl.comm != nullptr && g_nccl.world == cfg->tp_size && g_nccl.rank == cfg->tp_rank, FL_ERR_STATE,
+                 "tensor-parallel model: call fl_comm_init(rank, world, id) with world == tp_size first");
     auto w = std::make_shared<Weights>();
     w->cfg = *cfg;
     w->device = g_device.load();
@@ -1008,7 +1111,7 @@ FL_EXPORT int fl_forward(fl_model* m, fl_cache* c, const uint32_t* ids, int b, i
     use_device();
     try {
         run_forward(*c, ids, b, t, rope_offset);
-        const size_t n = (size_t)b * c->w->V;
+        const size_t n = (size_t)b * c->w->Vfull;
         FL_CUDA(cudaMemcpyAsync(c->h_logits.p, c->logits.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
         FL_CUDA(cudaStreamSynchronize(c->stream));
         std::memcpy(logits_host, c->h_logits.p, n * 4);
@@ -1115,17 +1218,37 @@ FL_EXPORT int fl_embed_timed(fl_model* m, const uint32_t* ids, const uint32_t* m
 
 FL_EXPORT int fl_comm_unique_id(void* out) {
     FL_API_BEGIN
-    (void)out;
-    throw fl::Error(FL_ERR_UNSUPPORTED, "tensor parallelism not built yet");
+    FL_CHECK(out != nullptr, FL_ERR_INVALID, "NULL argument");
+    g_nccl.load();
+    ncclUniqueId id;
+    g_nccl.check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out, &id, sizeof(id));
     FL_API_END
 }
-FL_EXPORT int fl_comm_init(int rank, int world, const void* id) {
+FL_EXPORT int fl_comm_init(int rank, int world, const void* id_bytes) {
     FL_API_BEGIN
-    (void)rank; (void)world; (void)id;
-    throw fl::Error(FL_ERR_UNSUPPORTED, "tensor parallelism not built yet");
+    FL_CHECK(id_bytes != nullptr && world >= 1 && rank >= 0 && rank < world, FL_ERR_INVALID, "bad communicator arguments");
+    use_device();
+    g_nccl.load();
+    FL_CHECK(g_nccl.comm == nullptr, FL_ERR_STATE, "communicator already initialised");
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof(id));
+    g_nccl.check(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank), "ncclCommInitRank");
+    g_nccl.rank = rank;
+    g_nccl.world = world;
     FL_API_END
 }
-FL_EXPORT int fl_comm_destroy(void) { return FL_OK; }
+FL_EXPORT int fl_comm_destroy(void) {
+    FL_API_BEGIN
+    if (g_nccl.comm) {
+        use_device();
+        FL_CUDA(cudaDeviceSynchronize());
+        g_nccl.CommDestroy(g_nccl.comm);
+        g_nccl.comm = nullptr;
+    }
+    FL_API_END
+}
 
 FL_EXPORT int fl_prof_begin(void) {
     FL_API_BEGIN

@@ -29,7 +29,9 @@ struct LayerW {
 struct Weights {
     fl_config cfg{};
     int H = 0, I = 0, V = 0, L = 0, nh = 0, nkv = 0, d = 0, max_pos = 0;
-    int nqkv = 0;               // (nh + 2 nkv) * d
+    int nqkv = 0;               // (nh + 2 nkv) * d   (nh, nkv, I, V, nqkv are LOCAL to this tensor-parallel rank)
+    int tp = 1, rank = 0;       // tensor-parallel size / rank of this process
+    int Vfull = 0;              // full vocabulary (embedding table rows, logits length); V = Vfull / tp rows of lm_head live here
     int device = 0;
     DevBuf<uint8_t> slab;       // every weight lives in this one allocation
     uint16_t* embed = nullptr;  // [V, H]
@@ -62,6 +64,7 @@ struct DenseWs {
     DevBuf<uint16_t> xhi, xlo;  // [rows, Kmax] hi/lo bf16 split of the activations fed to the next GEMM
     DevBuf<float> y;            // [rows, Nmax] GEMM output
     DevBuf<float> resid, q, attn;
+    DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<float> part_acc, part_ml;
     DevBuf<int> counters;
 };
@@ -104,5 +107,8 @@ struct fl_cache {
     fl::PkPlan pk;
     fl::DenseWs dw;
     fl::DevBuf<unsigned int> gbar;
+    fl::DevBuf<float> tp_buf;        // [rows, H] partial o_proj / down_proj outputs awaiting the all-reduce (tp > 1)
+    fl::DevBuf<float> tp_gather;     // [tp, max_batch, V] vocab-parallel logits gathered from all ranks
+    fl::DevBuf<float> tp_local;      // [max_batch, V] this rank's logits slice
     bool poisoned = false;
 };

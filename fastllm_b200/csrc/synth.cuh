@@ -47,18 +47,25 @@ struct RowMap {
     }
 };
 
-static __global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols, uint64_t tseed, float stdv, RowMap map) {
+// The local [rows, cols] block is the window (src_row0.., src_col0..) of a full tensor with src_cols_full columns (tensor-
+// parallel shards); element values depend only on the FULL-tensor index, so every shard layout sees the same weights.
+struct SrcWin {
+    int64_t row0, col0, cols_full;   // cols_full == 0: the block is the whole tensor
+};
+static __global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols, uint64_t tseed, float stdv, RowMap map,
+                                              SrcWin win = SrcWin{0, 0, 0}) {
     int64_t n = rows * cols;
+    const int64_t cf = win.cols_full ? win.cols_full : cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / cols, c = i - r * cols;
-        dst[map.map(r) * cols + c] = synth_bf16(tseed, (uint64_t)i, stdv);
+        dst[map.map(r) * cols + c] = synth_bf16(tseed, (uint64_t)((r + win.row0) * cf + c + win.col0), stdv);
     }
 }
 
 // f32 destination holding bf16-rounded values (biases, norm weights)
-static __global__ void synth_fill_f32_kernel(float* dst, int64_t rows, uint64_t tseed, float stdv, RowMap map) {
+static __global__ void synth_fill_f32_kernel(float* dst, int64_t rows, uint64_t tseed, float stdv, RowMap map, int64_t src_row0 = 0) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x)
-        dst[map.map(i)] = __uint_as_float((uint32_t)synth_bf16(tseed, (uint64_t)i, stdv) << 16);
+        dst[map.map(i)] = __uint_as_float((uint32_t)synth_bf16(tseed, (uint64_t)(i + src_row0), stdv) << 16);
 }
 
 static __global__ void fill_f32_kernel(float* dst, int64_t n, float v) {

@@ -172,6 +172,8 @@ class ConfigFile:
     max_position_embeddings: int | None = None
     sliding_window: int | None = None
     torch_dtype: str | None = None     # never consulted by the reference (huggingface.rs:132)
+    tp_rank: int = 0                   # tensor parallelism (no reference counterpart): rank / size of this process
+    tp_size: int = 1
 
 
 def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: int, qkv_bias: bool) -> FlConfig:
@@ -185,7 +187,7 @@ def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: 
     c.qkv_bias = 1 if qkv_bias else 0
     c.norm_eps = cf.rms_norm_eps
     c.rope_theta = float(cf.rope_theta if cf.rope_theta is not None else 10000.0)
-    c.tp_rank, c.tp_size = 0, 1
+    c.tp_rank, c.tp_size = cf.tp_rank, cf.tp_size
     return c
 
 

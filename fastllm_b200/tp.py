@@ -1,0 +1,52 @@
+"""Tensor-parallel plumbing on the host side: one process per GPU, torch.distributed for the rendezvous, the library
+owns the NCCL communicator (fl_comm_*).  Also the Python statement of the sharding scheme the library applies when a model
+is created with tp_size > 1 (csrc/fl_lib.cu route_tensor): column-parallel q/k/v (by head) and gate/up, row-parallel
+o_proj / down_proj (+ all-reduce), vocab-parallel lm_head (+ all-gather); embeddings and norms replicated.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def init_tensor_parallel(rank: int, world: int, device: int):
+    """Rank 0 creates the NCCL unique id, torch.distributed broadcasts it, every rank joins the communicator."""
+    import torch
+    import torch.distributed as dist
+    _lib.init(device)
+    lib = _lib.load()
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(lib.fl_comm_unique_id(buf))
+    on_gpu = dist.get_backend() == "nccl"
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=f"cuda:{device}" if on_gpu else "cpu")
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    _lib.check(lib.fl_comm_init(rank, world, (C.c_uint8 * 128).from_buffer_copy(raw)))
+    return raw
+
+
+def shard_window(name: str, shape, nh: int, nkv: int, rank: int, tp: int):
+    """(row slice, col slice) of the FULL HF tensor `name` kept by `rank` of `tp` (None = whole axis)."""
+    rows = shape[0]
+    if tp == 1 or name in ("model.embed_tokens.weight", "model.norm.weight") or name.endswith("layernorm.weight"):
+        return slice(None), slice(None)
+    if name == "lm_head.weight" or ".q_proj." in name or ".k_proj." in name or ".v_proj." in name or \
+            ".gate_proj." in name or ".up_proj." in name:
+        n = rows // tp                      # q/k/v rows are head-major, so an equal row split is a split by head
+        return slice(rank * n, (rank + 1) * n), slice(None)
+    if ".o_proj." in name or ".down_proj." in name:
+        n = shape[1] // tp
+        return slice(None), slice(rank * n, (rank + 1) * n)
+    raise KeyError(name)
+
+
+def shard_weights(weights: dict, nh: int, nkv: int, rank: int, tp: int) -> dict:
+    out = {}
+    for k, v in weights.items():
+        rs, cs = shard_window(k, v.shape, nh, nkv, rank, tp)
+        out[k] = np.ascontiguousarray(v[rs] if v.ndim == 1 else v[rs, cs])
+    return out

@@ -1,0 +1,44 @@
+"""Tensor parallelism: world_size-2 gloo test of the sharding scheme on CPU, and (when 2+ GPUs are visible) TP-2 through
+the library with real NCCL against the TP-1 result."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(mode, nproc, out, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "tp_worker.py"), mode, out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return json.load(open(out))
+
+
+def test_tp_sharding_scheme_gloo_world2(tmp_path):
+    """Column-parallel gate/up + row-parallel down with an all-reduce, vocab-parallel head with an all-gather, q/k/v split by
+    head: same numbers as the unsharded oracle (numpy over gloo, 2 processes)."""
+    assert _run("cpu", 2, str(tmp_path / "cpu.json"), 29631)["ok"]
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_tp2_matches_tp1(tmp_path):
+    one = _run("gpu", 1, str(tmp_path / "tp1.json"), 29641)["mistral"]
+    two = _run("gpu", 2, str(tmp_path / "tp2.json"), 29642)["mistral"]
+    assert one["ids"] == two["ids"]
+    assert np.abs(np.array(one["logits"]) - np.array(two["logits"])).max() < 3e-3
+    assert np.abs(np.array(one["synth_logits"]) - np.array(two["synth_logits"])).max() < 3e-3
+    assert np.abs(np.array(one["batch3"]) - np.array(two["batch3"])).max() < 3e-3
