@@ -26,6 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner to stdout otherwise; stdout carries ONE JSON line
 
 WORKLOADS = {
     # name: (arch key, batch, context, description)
@@ -33,7 +34,10 @@ WORKLOADS = {
     "mistral7b_b8": ("mistral7b", 8, 2048, "Mistral-7B-v0.1 bf16 decode, batch 8, 2k context"),
     "tinyllama_b1": ("tinyllama", 1, 128, "TinyLlama-1.1B bf16 decode, batch 1, 128-token prompt"),
     "qwen25_7b_b1": ("qwen25_7b", 1, 2048, "Qwen2.5-7B bf16 decode, batch 1, 2k context"),
+    "mistral7b_b64": ("mistral7b", 64, 2048, "Mistral-7B-v0.1 bf16 decode, batch 64, 2k context"),
+    "minilm_256x128": ("minilm", 256, 128, "all-MiniLM-L6-v2 (BertModel) embeddings, batch 256 x seq 128"),
 }
+MINILM_FLOP_PER_TOKEN = 22.41e6      # 2 x 10.617 M linear + 4 T H 6 attention at T = 128
 
 
 def oracle_config(key):
@@ -42,16 +46,98 @@ def oracle_config(key):
     return {"mistral7b": ocl.MISTRAL_7B, "tinyllama": ocl.TINYLLAMA, "qwen25_7b": ocl.QWEN25_7B}[key]
 
 
-def peaks():
+def peaks(kind="hbm"):
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        d = json.load(open(p))
+        return float(d["hbm_gbs"] if kind == "hbm" else d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
+    return (6650.0 if kind == "hbm" else 1400.0), "fallback (B200_PROFILING.md)"
+
+
+def minilm_measure(local_rank, b, t, repeats, e2e_iters, warm=3):
+    """-> dict(device ms/batch, e2e s/batch) for b x t synthetic sentences on this rank's GPU."""
+    from fastllm_b200 import models
+    m = models.MiniLMModel(models.BertConfig(), None, local_rank, random_seed=0)
+    ids = (np.arange(b * t, dtype=np.uint64).reshape(b, t) * 7919 % 30000 + 3).astype(np.uint32)
+    for _ in range(warm):
+        m.embed_ids(ids)
+    _, ms = m.embed_ids_timed(ids, repeats)
+    t0 = time.perf_counter()
+    for _ in range(e2e_iters):
+        m.embed_ids(ids)                                   # host ids in (H2D), f32 [b, 384] out (D2H)
+    e2e_s = (time.perf_counter() - t0) / e2e_iters
+    return {"ms": ms / repeats, "e2e_s": e2e_s}
+
+
+def cpu_minilm_sample(b=16, t=128, iters=2):
+    from oracle import bert as obert
+    from oracle import synth
+    cfg = obert.MINILM_L6
+    m = obert.MiniLM(cfg, obert.synth_weights(cfg, 0, 0.02))
+    ids = synth.token_ids(2, cfg.vocab_size, (b, t))
+    m.embed_ids(ids)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        m.embed_ids(ids)
+    dt = (time.perf_counter() - t0) / iters
+    return b / dt, f"{iters} batches of {b} x {t} tokens, f32 numpy/BLAS port of the reference's CPU encoder (embeddings.rs), all host threads"
+
+
+def run_minilm(args, rank, world, local_rank):
+    import torch
+    from fastllm_b200 import models
+    _, B, T, desc = WORKLOADS["minilm_256x128"]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    b = B // world                                        # batch-data-parallel: 256 / N sentences per GPU, no collective
+    K, W = args.steps, args.warmup
+    l0 = models.launch_count()
+    with ClockSampler(local_rank) as clk:
+        minilm_measure(local_rank, b, T, W, 1, warm=1)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0w = time.time()
+        r = minilm_measure(local_rank, b, T, K, max(3, min(K, 20)), warm=0)
+        torch.cuda.synchronize()
+        t1w = time.time()
+        time.sleep(0.12)
+    launches = models.launch_count() - l0
+    tt = torch.tensor([r["ms"], r["e2e_s"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return
+    value = B / (ms / 1e3)
+    peak, src = peaks("tensor")
+    tflops = MINILM_FLOP_PER_TOKEN * b * T / (ms / 1e3) / 1e12           # per GPU
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, sample = cpu_minilm_sample()
+        cpu = {"value": v, "unit": "emb/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+    line = {"metric": "embeddings_per_s", "value": value, "unit": "emb/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "batch": B, "seq_len": T, "per_gpu_batch": b, "l2": "L2 not flushed: activations of one batch (25-100 MB per tensor) cycle through L2 as in production",
+                       "parallelism": "single GPU" if world == 1 else f"dp{world}: {b} sentences per GPU, no collective",
+                       "weights": "synthetic N(0,0.02^2)-like bf16, seed 0"},
+            "clocks": clk.summary(t0w, t1w),
+            "e2e": {"value": B / e2e_s, "unit": "emb/s", "h2d_bytes_per_step": int(b * T * 4), "d2h_bytes_per_step": int(b * 384 * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
+                         "kernel": "gemm_tc_kernel<128,EPI> (tcgen05/TMEM/TMA) x 24 + bert_attn_kernel x 6 per batch: whole-encoder algorithmic FLOPs / device time",
+                         "peak_source": src},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons.  Started before the warm-up (nvidia-smi takes ~1 s to produce its first line);
+    `summary(t0, t1)` keeps the samples whose timestamp falls inside the timed region [t0, t1] (host clock)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, dev):
@@ -59,7 +145,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -68,8 +154,16 @@ class ClockSampler:
         return self
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = time.time()
+            self.rows.append([ts] + f[1:])
 
     def __exit__(self, *a):
         if self.proc:
@@ -79,13 +173,17 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+    def summary(self, t0=None, t1=None):
+        rows = [r for r in self.rows if t0 is None or (t0 - 0.05 <= r[0] <= t1 + 0.05)]
+        where = "timed region"
+        if not rows:                       # very short timed region: fall back to everything sampled under load
+            rows, where = self.rows, "warm-up + timed region"
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": where}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -171,14 +269,22 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
-    from fastllm_b200 import models, presets
+    from dataclasses import replace
+    from fastllm_b200 import models, presets, tp as fltp
     arch, batch, ctx, desc = WORKLOADS[args.workload]
     cls, cf = presets.PRESETS[arch]
     dist = None
+    # Mistral / Qwen2 shard with tensor parallelism (NCCL all-reduce over NVLink, strong scaling); TinyLlama runs as
+    # independent batch-data-parallel replicas (no collective, weak scaling) -- BASELINE.json configs / SURVEY.md section 8e.
+    use_tp = world > 1 and arch in ("mistral7b", "qwen25_7b")
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if use_tp:
+            fltp.init_tensor_parallel(rank, world, local_rank)
+            cf = replace(cf, tp_rank=rank, tp_size=world)
+    jobs = 1 if (use_tp or world == 1) else world       # independent model instances in the job
 
     def barrier():
         if dist is not None:
@@ -193,20 +299,23 @@ def run_ours(args, rank, world, local_rank):
     launches0 = models.launch_count()
 
     # ---- device-resident decode: W warm-up steps, then exactly K timed steps -------------------------------------------
-    cache.fill_synthetic(batch, ctx)
-    cache.decode_greedy_loop(first, ctx, W)
-    cache.fill_synthetic(batch, ctx)                      # back to KV length = ctx for the timed region
-    barrier()
-    l0 = models.launch_count()
     with ClockSampler(local_rank) as clk:
+        cache.fill_synthetic(batch, ctx)
+        cache.decode_greedy_loop(first, ctx, W)
+        cache.fill_synthetic(batch, ctx)                      # back to KV length = ctx for the timed region
+        barrier()
+        l0 = models.launch_count()
+        t_wall0 = time.time()
         _, ms = cache.decode_greedy_loop(first, ctx, K)
         barrier()
+        t_wall1 = time.time()
+        time.sleep(0.12)                                      # let the sampler flush its last lines
     gpu_launches = models.launch_count() - l0
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
-    value = world * batch * K / (ms / 1e3)
+    value = jobs * batch * K / (ms / 1e3)
 
     # ---- end to end through the reference-facing call: host ids -> fl_forward -> host logits -> host arg-max ------------
     cache.fill_synthetic(batch, ctx)
@@ -224,17 +333,21 @@ def run_ours(args, rank, world, local_rank):
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e = world * batch * K / float(t_e.item())
+    e2e = jobs * batch * K / float(t_e.item())
 
-    if rank != 0:
+    if rank != 0 and not use_tp:
         barrier()
         return
 
     # ---- roofline of the dominant kernel family (GEMV weight streaming), measured live with CUDA events ----------------
+    # (under tensor parallelism every rank runs this pass: the forward contains collectives)
     cache.fill_synthetic(batch, ctx)
     models.prof_begin()
     cache.decode_greedy_loop(first, ctx, 4)
     prof = models.prof_end()
+    if rank != 0:
+        barrier()
+        return
     pk = [p for p in prof if p["kernel"] == "decode_persistent"]
     if pk:      # batch-1: the whole step is ONE persistent kernel; its algorithmic bytes = streamed weights + KV read
         dom, dom_name = pk, "decode_persistent_kernel<D> (whole decode step: weight stream + attention + arg-max, 4 steps per launch here)"
@@ -246,9 +359,9 @@ def run_ours(args, rank, world, local_rank):
     all_ms = sum(p["ms"] for p in prof)
     peak, peak_src = peaks()
     achieved = gemv_bytes / (gemv_ms / 1e3) / 1e9 if gemv_ms > 0 else 0.0
-    streamed = model.dev.streamed_bytes()
+    streamed = model.dev.streamed_bytes()                  # this rank's shard under TP
     head_dim = cf.hidden_size // cf.num_attention_heads
-    kv_bytes = batch * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 2 * 2
+    kv_bytes = batch * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 2 * 2 // (world if use_tp else 1)
     step_bytes = streamed + kv_bytes
     step_gbs = step_bytes / (ms / K / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -263,15 +376,25 @@ def run_ours(args, rank, world, local_rank):
         v, sample, threads, _ = cpu_decode_sample(oracle_config(arch), batch, ctx, 4, 1, 40.0)
         cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
 
+    secondary = None
+    if world == 1:     # the metric's second half (BASELINE.json: "MiniLM embeddings/s"), measured in the same run
+        try:
+            r = minilm_measure(local_rank, 256, 128, 20, 5)
+            secondary = {"metric": "embeddings_per_s", "workload": WORKLOADS["minilm_256x128"][3], "value": 256 / (r["ms"] / 1e3),
+                         "e2e": 256 / r["e2e_s"], "unit": "emb/s", "ms_per_batch": r["ms"],
+                         "tensor_tflops": MINILM_FLOP_PER_TOKEN * 256 * 128 / (r["ms"] / 1e3) / 1e12}
+        except Exception as ex:   # never lose the headline line over the secondary one
+            secondary = {"error": str(ex)}
     line = {"metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if use_tp else "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": desc, "batch": batch, "context": ctx, "l2": "inputs larger than L2 (weights streamed once per step)",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (batch-data-parallel)",
+                       "parallelism": "single GPU" if world == 1 else (f"tp{world}: column/row tensor parallel, NCCL all-reduce x2 per layer + vocab-parallel all-gather"
+                                                                       if use_tp else f"{world} independent replicas (batch-data-parallel)"),
                        "kv_cache": "bf16 paged, synthetic prefill", "weights": "synthetic N(0,0.02^2)-like bf16, seed 0"},
-            "clocks": clk.summary(),
+            "clocks": clk.summary(t_wall0, t_wall1),
             "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": int(batch * 4), "d2h_bytes_per_step": int(batch * cf.vocab_size * 4)},
-            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}
     print(json.dumps(line), flush=True)
     barrier()
 
@@ -290,12 +413,25 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.workload == "minilm_256x128":
+            if rank == 0:
+                v, sample = cpu_minilm_sample(16, 128, max(1, min(args.steps, 4)))
+                print(json.dumps({"impl": "reference", "metric": "embeddings_per_s", "value": v, "unit": "emb/s", "n_gpus": args.gpus,
+                                  "steps": args.steps, "warmup": args.warmup, "ms_per_step": 256e3 / v, "higher_is_better": True,
+                                  "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                                  "config": {"workload": WORKLOADS[args.workload][3], "parallelism": "host cores"},
+                                  "cpu_baseline": {"value": v, "unit": "emb/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                                  "e2e": {"value": v, "unit": "emb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+            return
         run_reference(args, rank)
         return
     import __graft_entry__ as g
     if rank == 0 or not os.path.exists(os.path.join(ROOT, "fastllm_b200", "libfastllm_b200.so")):
         g.build()
-    run_ours(args, rank, world, local_rank)
+    if args.workload == "minilm_256x128":
+        run_minilm(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
