@@ -169,6 +169,60 @@ static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int 
     xlo[(size_t)row * I + j] = l;
 }
 
+// ---- Mixtral sparse-MoE (candle-transformers models::mixtral::SparseMoeBlock) ----------------
+// router: logits = x . W_gate^T, softmax over ALL experts (f32), stable descending sort (ties keep the LOWER expert index),
+// take top_k, renormalise by their sum; route_w[row][e] = weight or 0.  One CTA per row.
+static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* __restrict__ xhi, const uint16_t* __restrict__ xlo, int H,
+                                                                const float* __restrict__ wgate, int E, int top_k, float* __restrict__ route_w) {
+    __shared__ float red[8];
+    __shared__ float logit[64];
+    const int row = blockIdx.x;
+    for (int e = 0; e < E; ++e) {
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            const float x = __uint_as_float((uint32_t)xhi[(size_t)row * H + i] << 16) + __uint_as_float((uint32_t)xlo[(size_t)row * H + i] << 16);
+            acc = fmaf(x, wgate[(size_t)e * H + i], acc);
+        }
+        const float tot = block_sum_256(acc, red);
+        if (threadIdx.x == 0) logit[e] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mx = -INFINITY;
+        for (int e = 0; e < E; ++e) mx = fmaxf(mx, logit[e]);
+        float sum = 0.f;
+        for (int e = 0; e < E; ++e) { logit[e] = expf(logit[e] - mx); sum += logit[e]; }
+        for (int e = 0; e < E; ++e) logit[e] /= sum;                 // softmax_last_dim
+        float* rw = route_w + (size_t)row * E;
+        for (int e = 0; e < E; ++e) rw[e] = 0.f;
+        float picked_sum = 0.f;
+        unsigned long long taken = 0ull;
+        int picked[8];
+        for (int k = 0; k < top_k; ++k) {                            // k-th largest, lowest index among equals
+            int best = -1;
+            for (int e = 0; e < E; ++e)
+                if (!((taken >> e) & 1ull) && (best < 0 || logit[e] > logit[best])) best = e;
+            taken |= 1ull << best;
+            picked[k] = best;
+            picked_sum += logit[best];                               // sum::<f32>() in rank order
+        }
+        for (int k = 0; k < top_k; ++k) rw[picked[k]] = logit[picked[k]] / picked_sum;
+    }
+}
+
+// moe_out[row] (=|+=) route_w[row][e] * sum over split-K slices of y[row]   (index_add of the weighted expert output)
+static __global__ void moe_accum_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int H, const float* __restrict__ route_w,
+                                        int E, int e, int first, float* __restrict__ moe_out) {
+    const int row = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H) return;
+    float s = 0.f;
+    for (int k = 0; k < nsl; ++k) s += y[(size_t)k * sl_stride + (size_t)row * H + i];
+    const float v = route_w[(size_t)row * E + e] * s;
+    float* o = moe_out + (size_t)row * H + i;
+    *o = first ? v : (*o + v);
+}
+
 // arg-max over the vocabulary, one CTA per row, last index wins ties (candle LogitsProcessor::sample_argmax)
 // (also folds the split-K slices of the lm_head GEMM into the f32 logits buffer the caller reads)
 static __global__ void __launch_bounds__(256) dense_argmax_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int V,

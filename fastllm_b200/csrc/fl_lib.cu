@@ -135,9 +135,18 @@ static void validate_config(const fl_config& c) {
 static void build_weights(Weights& w) {
     const fl_config& c = w.cfg;
     const int nh_f = c.num_attention_heads, nkv_f = c.num_key_value_heads > 0 ? c.num_key_value_heads : c.num_attention_heads;
-    w.tp = c.tp_size > 1 ? c.tp_size : 1;
-    w.rank = w.tp > 1 ? c.tp_rank : 0;
-    FL_CHECK(w.rank >= 0 && w.rank < w.tp, FL_ERR_INVALID, "tp_rank out of range");
+    const bool moe = c.arch == FL_ARCH_MIXTRAL;
+    // Mixtral shards by EXPERT (attention, router and head replicated); the dense models shard by tensor
+    w.ep = (moe && c.tp_size > 1) ? c.tp_size : 1;
+    w.tp = (!moe && c.tp_size > 1) ? c.tp_size : 1;
+    w.rank = c.tp_size > 1 ? c.tp_rank : 0;
+    if (moe) {
+        w.E = c.num_local_experts; w.top_k = c.num_experts_per_tok > 0 ? c.num_experts_per_tok : 2;
+        FL_CHECK(w.E >= 1 && w.E <= 64 && w.top_k >= 1 && w.top_k <= 8 && w.top_k <= w.E, FL_ERR_INVALID, "bad Mixtral expert counts");
+        FL_CHECK(w.E % w.ep == 0, FL_ERR_UNSUPPORTED, "expert parallelism needs num_local_experts divisible by the world size");
+        w.E_local = w.E / w.ep;
+    }
+    FL_CHECK(w.rank >= 0 && w.rank < std::max(w.tp, w.ep), FL_ERR_INVALID, "tp_rank out of range");
     if (w.tp > 1) {
         // column-parallel q/k/v (by head) and gate/up, row-parallel o_proj and down_proj, vocab-parallel lm_head
         FL_CHECK(nh_f % w.tp == 0 && nkv_f % w.tp == 0, FL_ERR_UNSUPPORTED, "tensor parallelism needs heads and kv heads divisible by tp_size");
@@ -152,21 +161,30 @@ static void build_weights(Weights& w) {
     w.max_pos = c.max_position_embeddings;
     w.nqkv = (w.nh + 2 * w.nkv) * w.d;
     FL_CHECK(w.d == 16 || w.d == 32 || w.d == 64 || w.d == 128, FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
-    FL_CHECK(c.arch != FL_ARCH_BERT && c.arch != FL_ARCH_MIXTRAL, FL_ERR_UNSUPPORTED, "arch not built yet in this round");
+    FL_CHECK(c.arch != FL_ARCH_BERT, FL_ERR_INVALID, "internal: BERT goes through bert_build");
 
     const size_t A = 256;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, A); return o; };
     const size_t H = w.H, I = w.I, V = w.V, nq = (size_t)w.nh * w.d;
     const size_t o_embed = take((size_t)w.Vfull * H * 2), o_head = take(V * H * 2), o_fnorm = take(H * 4);
-    struct LO { size_t wqkv, bqkv, wo, wgu, wdown, ln1, ln2; };
+    struct LO { size_t wqkv, bqkv, wo, wgu, wdown, ln1, ln2, wgate; std::vector<size_t> ewgu, ewdown; };
     std::vector<LO> lo(w.L);
     for (int l = 0; l < w.L; ++l) {
         lo[l].wqkv = take((size_t)w.nqkv * H * 2);
         lo[l].bqkv = c.qkv_bias ? take((size_t)w.nqkv * 4) : (size_t)-1;
         lo[l].wo = take(H * nq * 2);
-        lo[l].wgu = take(2 * I * H * 2);
-        lo[l].wdown = take(H * I * 2);
+        if (moe) {
+            lo[l].wgate = take((size_t)w.E * H * 4);
+            for (int e = 0; e < w.E_local; ++e) {
+                lo[l].ewgu.push_back(take(2 * I * H * 2));
+                lo[l].ewdown.push_back(take(H * I * 2));
+            }
+            lo[l].wgu = lo[l].wdown = 0;
+        } else {
+            lo[l].wgu = take(2 * I * H * 2);
+            lo[l].wdown = take(H * I * 2);
+        }
         lo[l].ln1 = take(H * 4);
         lo[l].ln2 = take(H * 4);
     }
@@ -181,16 +199,25 @@ static void build_weights(Weights& w) {
         w.layers[l].wqkv = (uint16_t*)(base + lo[l].wqkv);
         w.layers[l].bqkv = c.qkv_bias ? (float*)(base + lo[l].bqkv) : nullptr;
         w.layers[l].wo = (uint16_t*)(base + lo[l].wo);
-        w.layers[l].wgu = (uint16_t*)(base + lo[l].wgu);
-        w.layers[l].wdown = (uint16_t*)(base + lo[l].wdown);
+        if (moe) {
+            w.layers[l].wgate = (float*)(base + lo[l].wgate);
+            for (int e = 0; e < w.E_local; ++e) {
+                w.layers[l].ewgu.push_back((uint16_t*)(base + lo[l].ewgu[e]));
+                w.layers[l].ewdown.push_back((uint16_t*)(base + lo[l].ewdown[e]));
+            }
+        } else {
+            w.layers[l].wgu = (uint16_t*)(base + lo[l].wgu);
+            w.layers[l].wdown = (uint16_t*)(base + lo[l].wdown);
+        }
         w.layers[l].ln1 = (float*)(base + lo[l].ln1);
         w.layers[l].ln2 = (float*)(base + lo[l].ln2);
     }
     w.rope_cos = (float*)(base + o_cos);
     w.rope_sin = (float*)(base + o_sin);
     // bytes one decode step must stream: every parameter except the embedding table
-    w.streamed_bytes = 2 * ((uint64_t)w.L * ((uint64_t)w.nqkv * H + H * nq + 3 * I * H) + V * H) +
-                       4 * ((uint64_t)w.L * (2 * H + (c.qkv_bias ? w.nqkv : 0)) + H);
+    const uint64_t mlp = moe ? (uint64_t)w.E_local * 3 * I * H : 3 * I * H;     // every local expert is streamed each step
+    w.streamed_bytes = 2 * ((uint64_t)w.L * ((uint64_t)w.nqkv * H + H * nq + mlp) + V * H) +
+                       4 * ((uint64_t)w.L * (2 * H + (c.qkv_bias ? w.nqkv : 0) + (moe ? (uint64_t)w.E * H : 0)) + H);
 }
 
 struct TensorRoute {
@@ -242,6 +269,26 @@ static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
         if (rest == "self_attn.v_proj.bias") return vec(lw.bqkv, nk, vmap, true);
     }
     if (rest == "self_attn.o_proj.weight") return mat_cols(lw.wo, H, nq, ident);
+    if (w.cfg.arch == FL_ARCH_MIXTRAL) {
+        if (rest == "block_sparse_moe.gate.weight") return vec(lw.wgate, (int64_t)w.E * H, ident, false);   // [E, H] kept in f32
+        const std::string ep = "block_sparse_moe.experts.";
+        if (rest.compare(0, ep.size(), ep) != 0) return false;
+        const size_t d2 = rest.find('.', ep.size());
+        if (d2 == std::string::npos) return false;
+        int e = -1;
+        try { e = std::stoi(rest.substr(ep.size(), d2 - ep.size())); } catch (...) { return false; }
+        if (e < 0 || e >= w.E) return false;
+        const std::string tail = rest.substr(d2 + 1);
+        const int el = e - w.rank * w.E_local;                  // local slot, or outside this rank's range
+        const bool mine = el >= 0 && el < w.E_local;
+        uint16_t* gu = mine ? lw.ewgu[el] : nullptr;
+        uint16_t* dn = mine ? lw.ewdown[el] : nullptr;
+        bool ok = false;
+        if (tail == "w1.weight") ok = mat_rows(gu, I, H, RowMap{0, 2, 0, 0}, false);
+        else if (tail == "w3.weight") ok = mat_rows(gu, I, H, RowMap{0, 2, 0, 1}, false);
+        else if (tail == "w2.weight") ok = mat_rows(dn, H, I, ident, false);
+        return ok;      // r.base == nullptr: a valid tensor that belongs to another expert-parallel rank
+    }
     if (rest == "mlp.gate_proj.weight") return mat_rows(lw.wgu, I, H, RowMap{0, 2, 0, 0}, true);
     if (rest == "mlp.up_proj.weight") return mat_rows(lw.wgu, I, H, RowMap{0, 2, 0, 1}, true);
     if (rest == "mlp.down_proj.weight") return mat_cols(lw.wdown, H, I, ident);
@@ -253,9 +300,16 @@ static std::vector<std::string> expected_tensors(const Weights& w) {
     for (int l = 0; l < w.L; ++l) {
         const std::string p = "model.layers." + std::to_string(l) + ".";
         for (const char* s : {"input_layernorm.weight", "post_attention_layernorm.weight", "self_attn.q_proj.weight",
-                              "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight",
-                              "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight"})
+                              "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight"})
             v.push_back(p + s);
+        if (w.cfg.arch == FL_ARCH_MIXTRAL) {
+            v.push_back(p + "block_sparse_moe.gate.weight");
+            for (int e = w.rank * w.E_local; e < (w.rank + 1) * w.E_local; ++e)
+                for (const char* s : {"w1.weight", "w2.weight", "w3.weight"})
+                    v.push_back(p + "block_sparse_moe.experts." + std::to_string(e) + "." + s);
+        } else {
+            for (const char* s : {"mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight"}) v.push_back(p + s);
+        }
         if (w.cfg.qkv_bias)
             for (const char* s : {"self_attn.q_proj.bias", "self_attn.k_proj.bias", "self_attn.v_proj.bias"}) v.push_back(p + s);
     }
@@ -266,10 +320,11 @@ static void put_tensor(Weights& w, const char* name, int dtype, const int64_t* s
     FL_CHECK(!w.finalized, FL_ERR_STATE, "model already finalized");
     TensorRoute r;
     FL_CHECK(route_tensor(w, name, r), FL_ERR_INVALID, std::string("unknown tensor name: ") + name);
+    if (r.base == nullptr) return;       // an expert that lives on another expert-parallel rank
     int64_t numel = 1;
     for (int i = 0; i < rank; ++i) numel *= shape[i];
     const bool shape_ok = (r.kind == TensorRoute::BF16_MAT) ? (rank == 2 && shape[0] == r.full_rows && shape[1] == r.full_cols)
-                                                            : (rank == 1 && shape[0] == r.full_rows);
+                                                            : ((rank == 1 && shape[0] == r.full_rows) || (rank == 2 && shape[0] * shape[1] == r.full_rows));
     FL_CHECK(shape_ok, FL_ERR_INVALID, std::string("shape mismatch for ") + name);
     FL_CHECK(dtype == FL_DTYPE_F32 || dtype == FL_DTYPE_BF16 || dtype == FL_DTYPE_F16, FL_ERR_INVALID, "bad dtype");
     // keep this rank's window of the full tensor, converted to bf16 bit patterns (round-to-nearest-even), the dtype the
@@ -370,13 +425,21 @@ static void finalize(Weights& w) {
     FL_CUDA(cudaMemcpy(w.rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
     FL_CUDA(cudaMemcpy(w.rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
     w.dense_ok = !env_flag("FL_NO_DENSE") && (w.nh * w.d) % 8 == 0 && w.H % 8 == 0 && w.I % 8 == 0 && w.nqkv % 4 == 0 && w.V % 4 == 0 && w.H % 4 == 0;
+    FL_CHECK(w.dense_ok || w.cfg.arch != FL_ARCH_MIXTRAL, FL_ERR_UNSUPPORTED, "Mixtral runs on the dense path only: shapes must be multiples of 8");
     if (w.dense_ok) {
         const uint64_t nq = (uint64_t)w.nh * w.d;
         for (LayerW& lw : w.layers) {
             lw.tm_wqkv = make_tmap_bf16(lw.wqkv, w.nqkv, w.H, w.H, 128);
             lw.tm_wo = make_tmap_bf16(lw.wo, w.H, nq, nq, 128);
-            lw.tm_wgu = make_tmap_bf16(lw.wgu, 2 * (uint64_t)w.I, w.H, w.H, 128);
-            lw.tm_wdown = make_tmap_bf16(lw.wdown, w.H, w.I, w.I, 128);
+            if (w.cfg.arch == FL_ARCH_MIXTRAL) {
+                for (int e = 0; e < w.E_local; ++e) {
+                    lw.tm_ewgu.push_back(make_tmap_bf16(lw.ewgu[e], 2 * (uint64_t)w.I, w.H, w.H, 128));
+                    lw.tm_ewdown.push_back(make_tmap_bf16(lw.ewdown[e], w.H, w.I, w.I, 128));
+                }
+            } else {
+                lw.tm_wgu = make_tmap_bf16(lw.wgu, 2 * (uint64_t)w.I, w.H, w.H, 128);
+                lw.tm_wdown = make_tmap_bf16(lw.wdown, w.H, w.I, w.I, 128);
+            }
         }
         w.tm_head = make_tmap_bf16(w.lm_head, w.V, w.H, w.H, 128);
     }
@@ -416,6 +479,7 @@ static void plan_persistent(fl_cache& c) {
     p.ok = false;
     if (env_flag("FL_NO_PERSISTENT")) return;
     if (w.tp > 1) return;                  // the persistent kernel has no in-kernel collective yet: TP uses the multi-kernel path
+    if (w.cfg.arch == FL_ARCH_MIXTRAL) return;   // MoE runs on the dense path
     const int nq = w.nh * w.d;
     if (!(w.d == 64 || w.d == 128)) return;
     if (w.H < 2048 || nq < 2048 || w.I < 2048) return;      // every row must span all 256 consumer threads
@@ -566,7 +630,9 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
 static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode) {
     const Weights& w = *c.w;
     const int rows = b * t;
-    if (rows >= 3 && w.dense_ok && c.dw.rows >= (size_t)rows) {   // workspace is reserved by the caller (never during capture)
+    const bool moe = w.cfg.arch == FL_ARCH_MIXTRAL;
+    FL_CHECK(!moe || c.dw.rows >= (size_t)rows, FL_ERR_STATE, "internal: Mixtral needs the dense workspace");
+    if ((rows >= 3 || moe) && w.dense_ok && c.dw.rows >= (size_t)rows) {   // workspace is reserved by the caller (never during capture)
         enqueue_forward_dense(c, lc, b, t, loop_mode);
         return;
     }
@@ -688,6 +754,10 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     d.y.alloc(R * nmax * (R <= 128 ? kDenseMaxSplit : 1));
     d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
+    if (w.cfg.arch == FL_ARCH_MIXTRAL) {
+        d.xhi2.alloc(R * kmax); d.xlo2.alloc(R * kmax);
+        d.moe_out.alloc(R * w.H); d.route_w.alloc(R * w.E);
+    }
     d.chunk = std::min(rows, kDenseAttnChunk);
     d.part_acc.alloc((size_t)d.chunk * w.nh * c.nsplit * w.d);
     d.part_ml.alloc((size_t)d.chunk * w.nh * c.nsplit * 2);
@@ -711,7 +781,9 @@ static void launch_gemm_tc(cudaStream_t st, int items, const CUtensorMap& a, con
 //   R <= 128 (decode batches, short prefills): swap-AB -- the weights are the 128-row MMA operand, the activations a tiny
 //             N = R tile, the result is stored transposed; the only large shared-memory traffic is the weight stream.
 //   R  > 128 (prefill): tokens are the M dimension, 128 x 128 output tiles.
-static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N, int K, const CUtensorMap& tmW, float* out) {
+static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N, int K, const CUtensorMap& tmW, float* out,
+                      const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr) {
+    if (!xhi) { xhi = c.dw.xhi.p; xlo = c.dw.xlo.p; }
     const int nk = (K + kGemmBK - 1) / kGemmBK;
     const bool swap = R <= 128;
     const int tiles = swap ? (N + 127) / 128 : ((R + kGemmBM - 1) / kGemmBM) * ((N + 127) / 128);
@@ -728,7 +800,7 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
     }
     if (swap) {
         const int bn = R <= 16 ? 16 : (R <= 32 ? 32 : (R <= 64 ? 64 : 128));
-        const CUtensorMap hi = make_tmap_bf16(c.dw.xhi.p, R, K, K, bn), lo = make_tmap_bf16(c.dw.xlo.p, R, K, K, bn);
+        const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, bn), lo = make_tmap_bf16(xlo, R, K, K, bn);
         GemmArgs g{N, R, K, nullptr, nullptr, 0, out, N, ks, (long long)R * N};     // M = weight rows, N = activation rows
         switch (bn) {
             case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
@@ -737,7 +809,7 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
             default: launch_gemm_tc<128, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
         }
     } else {
-        const CUtensorMap hi = make_tmap_bf16(c.dw.xhi.p, R, K, K, kGemmBM), lo = make_tmap_bf16(c.dw.xlo.p, R, K, K, kGemmBM);
+        const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, kGemmBM), lo = make_tmap_bf16(xlo, R, K, K, kGemmBM);
         GemmArgs g{R, N, K, nullptr, nullptr, 0, out, N, 1, (long long)R * N};
         launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, tiles, hi, lo, tmW, g);
     }
@@ -810,12 +882,32 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             pa.resid = d.resid.p; pa.delta = delta; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.norm_w = lw.ln2; pa.K = w.H;
             prep("dense_resid_rmsnorm", pa, R);
         }
-        ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
-        launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
-               (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
-        ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
-        delta = d.y.p;
-        tp_reduce();
+        if (w.cfg.arch == FL_ARCH_MIXTRAL) {
+            // sparse MoE: route, then stream EVERY local expert once over all rows (weights of unselected experts are zero in
+            // route_w, so no host sync, no gather/scatter and a fixed summation order); at decode batch sizes the block is
+            // HBM-bound on the expert weights either way.
+            launch(lc, "moe_router", 0, moe_router_kernel, dim3(R), dim3(256), 0, (const uint16_t*)d.xhi.p, (const uint16_t*)d.xlo.p, w.H,
+                   (const float*)lw.wgate, w.E, w.top_k, d.route_w.p);
+            for (int j = 0; j < w.E_local; ++j) {
+                const int e = w.rank * w.E_local + j;
+                int ke = dense_gemm(c, lc, "gemm_tc_moe_w13", R, 2 * w.I, w.H, lw.tm_ewgu[j], d.y.p);
+                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)R * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p);
+                ke = dense_gemm(c, lc, "gemm_tc_moe_w2", R, w.H, w.I, lw.tm_ewdown[j], d.y.p, d.xhi2.p, d.xlo2.p);
+                launch(lc, "moe_accum", 0, moe_accum_kernel, dim3((w.H + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)R * w.H, w.H, (const float*)d.route_w.p, w.E, e, j == 0 ? 1 : 0, d.moe_out.p);
+            }
+            if (w.ep > 1) tp_allreduce_sum(lc, d.moe_out.p, (size_t)R * w.H);    // expert parallelism: combine = sum over ranks
+            delta = d.moe_out.p;
+            ks = 1;
+        } else {
+            ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
+            launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
+                   (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
+            ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
+            delta = d.y.p;
+            tp_reduce();
+        }
         PrepArgs pa{};
         pa.resid = d.resid.p; pa.delta = delta; pa.ldd = w.H; pa.nsl = ks; pa.sl_stride = (long long)R * w.H; pa.K = w.H;
         if (l + 1 < w.L) {   // K16 + next layer's K2
@@ -884,7 +976,7 @@ static void check_call(fl_cache& c, const uint32_t* ids, int b, int t, size_t ro
 
 static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t rope_offset) {
     check_call(c, ids, b, t, rope_offset, 0);
-    if (b * t >= 3 && c.w->dense_ok) ensure_dense_ws(c, b * t);
+    if ((b * t >= 3 || c.w->cfg.arch == FL_ARCH_MIXTRAL) && c.w->dense_ok) ensure_dense_ws(c, b * t);
     std::memcpy(c.h_ids.p, ids, (size_t)b * t * 4);
     FL_CUDA(cudaMemcpyAsync(c.ids.p, c.h_ids.p, (size_t)b * t * 4, cudaMemcpyHostToDevice, c.stream));
     set_state_kernel<<<1, 1, 0, c.stream>>>(c.state.p, (int)rope_offset);
@@ -970,7 +1062,7 @@ FL_EXPORT int fl_model_create(const fl_config* cfg, fl_model** out) {
         *out = new fl_model{nullptr, bm};
         return FL_OK;
     }
-    if (cfg->tp_size > 1)
+    if (cfg->tp_size > 1)   // tensor parallel (dense models) or expert parallel (Mixtral)
         FL_CHECK(g_nccl.comm != nullptr && g_nccl.world == cfg->tp_size && g_nccl.rank == cfg->tp_rank, FL_ERR_STATE,
                  "tensor-parallel model: call fl_comm_init(rank, world, id) with world == tp_size first");
     auto w = std::make_shared<Weights>();
@@ -1148,7 +1240,7 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
     use_device();
     try {
         check_call(*c, first_ids, b, 1, rope_offset, steps - 1);
-        if (b >= 3 && c->w->dense_ok) ensure_dense_ws(*c, b);
+        if ((b >= 3 || c->w->cfg.arch == FL_ARCH_MIXTRAL) && c->w->dense_ok) ensure_dense_ws(*c, b);
         if (c->trace_cap < (size_t)steps * b) {
             c->trace.alloc((size_t)steps * b);
             c->trace_cap = (size_t)steps * b;

@@ -23,6 +23,10 @@ struct LayerW {
     float* ln1 = nullptr;       // [H]
     float* ln2 = nullptr;       // [H]
     CUtensorMap tm_wqkv, tm_wo, tm_wgu, tm_wdown;   // TMA descriptors of the weights (dense tcgen05 path)
+    // Mixtral sparse-MoE: router + this rank's experts (w1|w3 interleaved like wgu, w2 like wdown)
+    float* wgate = nullptr;                         // [E, H] f32 (bf16-rounded values)
+    std::vector<uint16_t*> ewgu, ewdown;
+    std::vector<CUtensorMap> tm_ewgu, tm_ewdown;
 };
 
 // Immutable after finalize; shared (ref-counted) between fl_model clones and their caches.
@@ -31,6 +35,8 @@ struct Weights {
     int H = 0, I = 0, V = 0, L = 0, nh = 0, nkv = 0, d = 0, max_pos = 0;
     int nqkv = 0;               // (nh + 2 nkv) * d   (nh, nkv, I, V, nqkv are LOCAL to this tensor-parallel rank)
     int tp = 1, rank = 0;       // tensor-parallel size / rank of this process
+    int E = 0, top_k = 0;       // Mixtral: experts / experts per token
+    int ep = 1, E_local = 0;    // expert parallelism: this rank holds experts [rank * E_local, (rank + 1) * E_local)
     int Vfull = 0;              // full vocabulary (embedding table rows, logits length); V = Vfull / tp rows of lm_head live here
     int device = 0;
     DevBuf<uint8_t> slab;       // every weight lives in this one allocation
@@ -65,6 +71,8 @@ struct DenseWs {
     DevBuf<float> y;            // [rows, Nmax] GEMM output
     DevBuf<float> resid, q, attn;
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
+    DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
+    DevBuf<float> moe_out, route_w;
     DevBuf<float> part_acc, part_ml;
     DevBuf<int> counters;
 };

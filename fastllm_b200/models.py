@@ -173,7 +173,9 @@ class ConfigFile:
     sliding_window: int | None = None
     torch_dtype: str | None = None     # never consulted by the reference (huggingface.rs:132)
     tp_rank: int = 0                   # tensor parallelism (no reference counterpart): rank / size of this process
-    tp_size: int = 1
+    tp_size: int = 1                   # (for Mixtral the same two fields mean expert-parallel rank / size)
+    num_local_experts: int = 0         # Mixtral
+    num_experts_per_tok: int = 2
 
 
 def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: int, qkv_bias: bool) -> FlConfig:
@@ -188,6 +190,7 @@ def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: 
     c.norm_eps = cf.rms_norm_eps
     c.rope_theta = float(cf.rope_theta if cf.rope_theta is not None else 10000.0)
     c.tp_rank, c.tp_size = cf.tp_rank, cf.tp_size
+    c.num_local_experts, c.num_experts_per_tok = cf.num_local_experts, cf.num_experts_per_tok
     return c
 
 
@@ -354,6 +357,17 @@ class QwenWithConfig(MistralWithConfig):
 
     def clear_cache(self):
         self.clear_kv_cache()
+
+
+class MixtralWithConfig(MistralWithConfig):
+    """MixtralForCausalLM.  The reference does NOT wire this architecture (model_registry.rs:169-182 has no matching key,
+    mistral.rs:244-246 accepts only MistralForCausalLM); the adapter follows the Mistral one (same offset rule) over
+    candle-transformers' mixtral model: attention as Mistral, MLP replaced by the top-k sparse-MoE block."""
+    arch, family, architectures = "mixtral", "Mixtral", ("MixtralForCausalLM",)
+
+    @classmethod
+    def _to_fl_config(cls, cf: ConfigFile) -> FlConfig:
+        return _fl_config("mixtral", cf, 32768, cf.sliding_window if cf.sliding_window is not None else 4096, False)
 
 
 def sample_argmax(logits: np.ndarray) -> int:

@@ -41,6 +41,8 @@ def product_model(cfg: ocl.CausalLMConfig, weights):
     from fastllm_b200 import models
     cf = models.ConfigFile(cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers,
                            cfg.num_attention_heads, cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta,
-                           cfg.max_position_embeddings, cfg.sliding_window if cfg.arch != "llama" else None)
-    cls = {"llama": models.LlamaWithConfig, "mistral": models.MistralWithConfig, "qwen2": models.QwenWithConfig}[cfg.arch]
+                           cfg.max_position_embeddings, cfg.sliding_window if cfg.arch != "llama" else None,
+                           num_local_experts=cfg.num_local_experts, num_experts_per_tok=cfg.num_experts_per_tok)
+    cls = {"llama": models.LlamaWithConfig, "mistral": models.MistralWithConfig, "qwen2": models.QwenWithConfig,
+           "mixtral": models.MixtralWithConfig}[cfg.arch]
     return cls.initialize_model(cf, weights, "bf16", 0)

@@ -33,7 +33,7 @@ def _generate(model, cache, prompt, n):
     return models.Model(model, cache, eos_token_id=None).generate(prompt, n, return_logits=True)
 
 
-@pytest.mark.parametrize("name", ["llama", "llama_gqa8", "mistral", "mistral_sw", "qwen2"])
+@pytest.mark.parametrize("name", ["llama", "llama_gqa8", "mistral", "mistral_sw", "qwen2", "mixtral"])
 def test_golden_greedy_and_logits(name):
     """Reference-faithful mode (Mistral/Qwen2: +1-per-call RoPE offset) against tests/golden/causal_*.npz."""
     cfg, w, g = golden_weights(name)
@@ -207,3 +207,32 @@ def test_persistent_kernel_matches_multikernel_path(arch, monkeypatch):
     err = float(np.abs(np.stack(mk_logits) - np.stack(step_logits)).max())
     print(f"{arch}: persistent vs multi-kernel max-abs logits diff {err:.3e}")
     assert err <= KERNEL_TOL_WIDE
+
+
+def test_mixtral_router_known_answers_and_batch():
+    """Mixtral MoE block: batch rows route independently (batch-3 prefill == 3 single prefills), device synthetic init equals
+    host-generated weights, and a true-width single layer (H=4096, I=14336, 8 experts, top-2) matches the oracle."""
+    from dataclasses import replace
+    from fastllm_b200 import models
+    cfg, w, g = golden_weights("mixtral")
+    model, _ = product_model(cfg, w)
+    prompts = synth.token_ids(5, cfg.vocab_size, (3, 10))
+    cb = models.DeviceCache(model.dev, 3, 64)
+    lb = cb.forward(prompts, 0)
+    want = ocl.CausalLM(cfg, w, kv_dtype="bf16").forward(prompts, 0)
+    assert np.abs(lb - want).max() <= KERNEL_TOL
+    for s in range(3):
+        c1 = models.DeviceCache(model.dev, 1, 64)
+        assert np.array_equal(c1.forward(prompts[s:s + 1], 0)[0], lb[s])
+    wide = replace(ocl.MIXTRAL_8X7B, num_hidden_layers=1, vocab_size=4096, max_position_embeddings=128)
+    ww = ocl.synth_weights(wide, 0, 0.02)
+    p = synth.token_ids(1, wide.vocab_size, (1, 9))
+    o_ids, o_logits = ocl.generate(ocl.make_adapter(ocl.CausalLM(wide, ww, kv_dtype="bf16")), p[0], 3, eos_id=None, return_logits=True)
+    cf = models.ConfigFile(wide.hidden_size, wide.intermediate_size, wide.vocab_size, 1, wide.num_attention_heads, wide.num_key_value_heads,
+                           wide.rms_norm_eps, wide.rope_theta, wide.max_position_embeddings, wide.sliding_window, num_local_experts=8,
+                           num_experts_per_tok=2)
+    m2, c2 = models.MixtralWithConfig.initialize_model(cf, None, "bf16", 0, random_seed=0, std=0.02)
+    ids, logits = models.Model(m2, c2, eos_token_id=None).generate(p[0], 3, return_logits=True)
+    err = float(np.abs(np.stack(logits) - np.stack(o_logits)).max())
+    print(f"mixtral true-width layer: max-abs logits err vs oracle (bf16 KV) {err:.3e}")
+    assert ids == o_ids and err <= KERNEL_TOL_WIDE
