@@ -230,7 +230,8 @@ struct TensorRoute {
 };
 
 static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
-    const int64_t H = w.H, I = w.I, d = w.d, nq = (int64_t)w.nh * d, nk = (int64_t)w.nkv * d, tp = w.tp, rk = w.rank;
+    const int64_t H = w.H, I = w.I, d = w.d, nq = (int64_t)w.nh * d, nk = (int64_t)w.nkv * d, tp = w.tp,
+                  rk = w.tp > 1 ? w.rank : 0;   // under expert parallelism (tp == 1) every dense tensor is replicated
     // row-sharded matrix: local rows [rk*rows, (rk+1)*rows) of a [tp*rows, cols] tensor; col-sharded: the same along columns
     auto mat_rows = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m, bool sharded) {
         r = {TensorRoute::BF16_MAT, base, rows, cols, m, sharded ? rows * tp : rows, cols, sharded ? rk * rows : 0, 0};

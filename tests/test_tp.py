@@ -36,8 +36,12 @@ def _ngpu():
 @pytest.mark.gpu
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_tp2_matches_tp1(tmp_path):
-    one = _run("gpu", 1, str(tmp_path / "tp1.json"), 29641)["mistral"]
-    two = _run("gpu", 2, str(tmp_path / "tp2.json"), 29642)["mistral"]
+    r1 = _run("gpu", 1, str(tmp_path / "tp1.json"), 29641)
+    r2 = _run("gpu", 2, str(tmp_path / "tp2.json"), 29642)
+    # expert parallelism (Mixtral): EP-2 == EP-1 == golden greedy ids
+    assert r1["mixtral"]["ids"] == r2["mixtral"]["ids"] == r1["mixtral"]["golden_ids"]
+    assert np.abs(np.array(r1["mixtral"]["logits"]) - np.array(r2["mixtral"]["logits"])).max() < 3e-3
+    one, two = r1["mistral"], r2["mistral"]
     assert one["ids"] == two["ids"]
     assert np.abs(np.array(one["logits"]) - np.array(two["logits"])).max() < 3e-3
     assert np.abs(np.array(one["synth_logits"]) - np.array(two["synth_logits"])).max() < 3e-3

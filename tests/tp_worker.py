@@ -38,6 +38,14 @@ def gpu_main(out_path):
         p3 = np.stack([g["prompt"], g["prompt"][::-1], np.roll(g["prompt"], 3)]).astype(np.uint32)
         l3 = c3.forward(p3, 0)
         res[name] = {"ids": [int(i) for i in ids], "logits": np.stack(logits).tolist(), "synth_logits": l2[0, 0].tolist(), "batch3": l3.tolist()}
+    # Mixtral: expert parallelism (experts sharded across ranks, attention replicated, one all-reduce per MoE block)
+    cfg, w, g = golden_weights("mixtral")
+    cf = models.ConfigFile(cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers, cfg.num_attention_heads,
+                           cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, cfg.max_position_embeddings, cfg.sliding_window,
+                           tp_rank=rank, tp_size=world, num_local_experts=cfg.num_local_experts, num_experts_per_tok=cfg.num_experts_per_tok)
+    model, cache = models.MixtralWithConfig.initialize_model(cf, w, "bf16", local)
+    ids, logits = models.Model(model, cache, eos_token_id=None).generate(g["prompt"], len(g["faithful_ids"]), return_logits=True)
+    res["mixtral"] = {"ids": [int(i) for i in ids], "logits": np.stack(logits).tolist(), "golden_ids": [int(i) for i in g["faithful_ids"]]}
     if rank == 0:
         json.dump(res, open(out_path, "w"))
     dist.barrier()
