@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         ++dbg_i;
     };
     const int n_rep = a.nh / a.nkv;
-    constexpr int LPT = D / 8, TPW = 32 / LPT, G = kPkConsumerWarps * TPW, NIT = kKvPage / G;
+    constexpr int LPT = D / 8, TPW = 32 / LPT;
     const int grp = lane / LPT, gl = lane % LPT;
 
     for (int step = 0; step < a.nsteps; ++step) {
@@ -492,123 +492,116 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             stamp(l);
 
             // ---------------- P2: split-K attention over (kv head, split) items + last-arriver merge ----------------
+            // Latency-optimised: every 16-lane group (two per warp, 16 per CTA) runs its OWN online softmax over a strided
+            // subset of the item's tokens with all of its K/V loads in flight at once and q held in registers (loaded from L2
+            // concurrently with K/V); the 16 partial states meet in shared memory after ONE block sync.
             {
+                constexpr int HG = 4;                       // query heads per pass (register budget)
+                constexpr int NG = kPkConsumerWarps * TPW;  // lane groups per CTA
+                constexpr int BATCH = 4;                    // tokens in flight per lane group
                 const int npages = (len + kKvPage - 1) / kKvPage;
                 const int per = (npages + a.nsplit - 1) / a.nsplit;
+                float* gacc = xs;                            // [NG][HG][D]
+                float* gml = xs + NG * HG * D;               // [NG][HG][2]
                 for (int item = cta; item < a.nkv * a.nsplit; item += ncta) {
                     const int kvh = item / a.nsplit, split = item % a.nsplit;
-                    const int p0 = split * per, p1 = min(p0 + per, npages);
-                    float* qs = xs;   // [n_rep][D] in the [half][chunk][4] layout of attn_decode.cuh
-                    for (int i = tid; i < n_rep * D; i += kPkConsumers) {
-                        const int h = i / D, dd = i % D;
-                        qs[h * D + ((dd >> 2) & 1) * (D / 2) + (dd >> 3) * 4 + (dd & 3)] =
-                            __ldcg(a.q + (size_t)(kvh * n_rep + h) * D + dd) * a.qscale;
-                    }
-                    if (tid < kAttnMaxRep) { mrun[tid] = -INFINITY; lrun[tid] = 0.f; }
-                    float acc[kAttnMaxRep][8];
+                    const int tok0 = split * per * kKvPage, tok1 = min(min((split + 1) * per, npages) * kKvPage, len);
+                    const int gidx = warp * TPW + grp;
+                    for (int h0 = 0; h0 < n_rep; h0 += HG) {
+                        float qv[HG][8], acc[HG][8], mr[HG], lr[HG];
 #pragma unroll
-                    for (int h = 0; h < kAttnMaxRep; ++h)
+                        for (int h = 0; h < HG; ++h) {
+                            mr[h] = -INFINITY;
+                            lr[h] = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[h][i] = 0.f;
-                    pk_named_sync();
-                    for (int p = p0; p < p1; ++p) {
-                        const size_t base = ((size_t)__ldg(a.page_table + p) * a.nkv + kvh) * (size_t)(kKvPage * D);
-                        uint4 kw[NIT], vw[NIT];
+                            for (int i = 0; i < 8; ++i) acc[h][i] = 0.f;
+                            if (h0 + h < n_rep) {
+                                const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)(kvh * n_rep + h0 + h) * D + gl * 8);
+                                const float4 q0 = __ldcg(qp), q1 = __ldcg(qp + 1);
+                                qv[h][0] = q0.x * a.qscale; qv[h][1] = q0.y * a.qscale; qv[h][2] = q0.z * a.qscale; qv[h][3] = q0.w * a.qscale;
+                                qv[h][4] = q1.x * a.qscale; qv[h][5] = q1.y * a.qscale; qv[h][6] = q1.z * a.qscale; qv[h][7] = q1.w * a.qscale;
+                            } else {
 #pragma unroll
-                        for (int it = 0; it < NIT; ++it) {
-                            const int tok = it * G + warp * TPW + grp;
-                            kw[it] = ldcg_u4(kpool + base + (size_t)tok * D + gl * 8);
-                            vw[it] = ldcg_u4(vpool + base + (size_t)tok * D + gl * 8);
+                                for (int i = 0; i < 8; ++i) qv[h][i] = 0.f;
+                            }
                         }
+                        // trip count is uniform across the CTA (the shuffles below use the full mask); validity is per lane group
+                        for (int tb0 = tok0; tb0 < tok1; tb0 += NG * BATCH) {
+                            const int tb = tb0 + gidx;
+                            uint4 kw[BATCH], vw[BATCH];
 #pragma unroll
-                        for (int it = 0; it < NIT; ++it) {
-                            const int tok = it * G + warp * TPW + grp;
-                            const float kf[8] = {bf16lo(kw[it].x), bf16hi(kw[it].x), bf16lo(kw[it].y), bf16hi(kw[it].y),
-                                                 bf16lo(kw[it].z), bf16hi(kw[it].z), bf16lo(kw[it].w), bf16hi(kw[it].w)};
-                            const bool valid = p * kKvPage + tok < len;
-#pragma unroll
-                            for (int h = 0; h < kAttnMaxRep; ++h)
-                                if (h < n_rep) {
-                                    const float4 q0 = *reinterpret_cast<const float4*>(qs + h * D + gl * 4);
-                                    const float4 q1 = *reinterpret_cast<const float4*>(qs + h * D + D / 2 + gl * 4);
-                                    float s = kf[0] * q0.x;
-                                    s = fmaf(kf[1], q0.y, s); s = fmaf(kf[2], q0.z, s); s = fmaf(kf[3], q0.w, s);
-                                    s = fmaf(kf[4], q1.x, s); s = fmaf(kf[5], q1.y, s); s = fmaf(kf[6], q1.z, s); s = fmaf(kf[7], q1.w, s);
-#pragma unroll
-                                    for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-                                    if (gl == 0) sc[h * kKvPage + tok] = valid ? s : -INFINITY;
+                            for (int it = 0; it < BATCH; ++it) {
+                                const int tk = tb + it * NG;
+                                if (tk < tok1) {
+                                    const size_t base = (((size_t)__ldg(a.page_table + tk / kKvPage) * a.nkv + kvh) * kKvPage + tk % kKvPage) * D + gl * 8;
+                                    kw[it] = ldcg_u4(kpool + base);
+                                    vw[it] = ldcg_u4(vpool + base);
+                                } else {
+                                    kw[it] = make_uint4(0u, 0u, 0u, 0u);
+                                    vw[it] = kw[it];
                                 }
-                        }
-                        pk_named_sync();
-                        if (warp < n_rep) {
-                            const int h = warp;
-                            const float s0 = sc[h * kKvPage + lane], s1 = sc[h * kKvPage + lane + 32];
-                            const float m_old = mrun[h];
-                            const float m_new = fmaxf(m_old, warp_max(fmaxf(s0, s1)));
-                            float e0 = 0.f, e1 = 0.f, al = 1.f;
-                            if (m_new != -INFINITY) { e0 = expf(s0 - m_new); e1 = expf(s1 - m_new); al = expf(m_old - m_new); }
-                            const float sum = warp_sum(e0 + e1);
-                            sc[h * kKvPage + lane] = e0;
-                            sc[h * kKvPage + lane + 32] = e1;
-                            if (lane == 0) { alpha_s[h] = al; mrun[h] = m_new; lrun[h] = lrun[h] * al + sum; }
-                        }
-                        pk_named_sync();
-#pragma unroll
-                        for (int h = 0; h < kAttnMaxRep; ++h)
-                            if (h < n_rep) {
-                                const float al = alpha_s[h];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) acc[h][i] *= al;
                             }
 #pragma unroll
-                        for (int it = 0; it < NIT; ++it) {
-                            const int tok = it * G + warp * TPW + grp;
-                            const float vf[8] = {bf16lo(vw[it].x), bf16hi(vw[it].x), bf16lo(vw[it].y), bf16hi(vw[it].y),
-                                                 bf16lo(vw[it].z), bf16hi(vw[it].z), bf16lo(vw[it].w), bf16hi(vw[it].w)};
+                            for (int it = 0; it < BATCH; ++it) {
+                                const bool valid = tb + it * NG < tok1;
+                                const float kf[8] = {bf16lo(kw[it].x), bf16hi(kw[it].x), bf16lo(kw[it].y), bf16hi(kw[it].y),
+                                                     bf16lo(kw[it].z), bf16hi(kw[it].z), bf16lo(kw[it].w), bf16hi(kw[it].w)};
+                                const float vf[8] = {bf16lo(vw[it].x), bf16hi(vw[it].x), bf16lo(vw[it].y), bf16hi(vw[it].y),
+                                                     bf16lo(vw[it].z), bf16hi(vw[it].z), bf16lo(vw[it].w), bf16hi(vw[it].w)};
 #pragma unroll
-                            for (int h = 0; h < kAttnMaxRep; ++h)
-                                if (h < n_rep) {
-                                    const float pr = sc[h * kKvPage + tok];
+                                for (int h = 0; h < HG; ++h) {
+                                    float sv = kf[0] * qv[h][0];
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) acc[h][i] = fmaf(pr, vf[i], acc[h][i]);
+                                    for (int i = 1; i < 8; ++i) sv = fmaf(kf[i], qv[h][i], sv);
+#pragma unroll
+                                    for (int o = LPT / 2; o > 0; o >>= 1) sv += __shfl_xor_sync(0xFFFFFFFFu, sv, o);
+                                    if (valid) {      // uniform inside the lane group
+                                        const float m_new = fmaxf(mr[h], sv);
+                                        const float al = expf(mr[h] - m_new), pr = expf(sv - m_new);
+                                        lr[h] = lr[h] * al + pr;
+                                        mr[h] = m_new;
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) acc[h][i] = fmaf(acc[h][i], al, pr * vf[i]);
+                                    }
                                 }
+                            }
+                        }
+                        // the NG partial states meet in shared memory
+#pragma unroll
+                        for (int h = 0; h < HG; ++h) {
+                            float* dst = gacc + ((size_t)gidx * HG + h) * D + gl * 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dst[i] = acc[h][i];
+                            if (gl == 0) {
+                                gml[(gidx * HG + h) * 2] = mr[h];
+                                gml[(gidx * HG + h) * 2 + 1] = lr[h];
+                            }
                         }
                         pk_named_sync();
-                    }
-                    // reduce acc over the TPW token groups of the warp (shuffles), then over the 8 warps (shared memory)
+                        for (int i = tid; i < HG * D; i += kPkConsumers) {
+                            const int h = i / D, dd = i % D;
+                            if (h0 + h < n_rep) {
+                                float M = -INFINITY;
 #pragma unroll
-                    for (int h = 0; h < kAttnMaxRep; ++h)
-                        if (h < n_rep) {
+                                for (int g = 0; g < NG; ++g) M = fmaxf(M, gml[(g * HG + h) * 2]);
+                                float num = 0.f, den = 0.f;
+                                if (M != -INFINITY) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float v = acc[h][i];
-#pragma unroll
-                                for (int o = LPT; o < 32; o <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                                acc[h][i] = v;
+                                    for (int g = 0; g < NG; ++g) {
+                                        const float wg = expf(gml[(g * HG + h) * 2] - M);      // exp(-inf) = 0 for idle groups
+                                        num = fmaf(wg, gacc[((size_t)g * HG + h) * D + dd], num);
+                                        den = fmaf(wg, gml[(g * HG + h) * 2 + 1], den);
+                                    }
+                                }
+                                const size_t pidx = (size_t)(kvh * n_rep + h0 + h) * a.nsplit + split;
+                                a.part_acc[pidx * D + dd] = num;
+                                if (dd == 0) {
+                                    a.part_ml[pidx * 2] = M;
+                                    a.part_ml[pidx * 2 + 1] = den;
+                                }
                             }
                         }
-                    float* redbuf = xs + kAttnMaxRep * D;   // [8 warps][n_rep][D], after the q vector
-                    if (grp == 0) {
-#pragma unroll
-                        for (int h = 0; h < kAttnMaxRep; ++h)
-                            if (h < n_rep) {
-                                float* dst = redbuf + ((size_t)warp * n_rep + h) * D + gl * 8;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) dst[i] = acc[h][i];
-                            }
-                    }
-                    pk_named_sync();
-                    for (int i = tid; i < n_rep * D; i += kPkConsumers) {
-                        const int h = i / D, dd = i % D;
-                        float s = 0.f;
-#pragma unroll
-                        for (int w = 0; w < kPkConsumerWarps; ++w) s += redbuf[((size_t)w * n_rep + h) * D + dd];
-                        a.part_acc[(((size_t)(kvh * n_rep + h)) * a.nsplit + split) * D + dd] = s;
-                    }
-                    if (tid < n_rep) {
-                        float* ml = a.part_ml + ((size_t)(kvh * n_rep + tid) * a.nsplit + split) * 2;
-                        ml[0] = mrun[tid];
-                        ml[1] = lrun[tid];
+                        pk_named_sync();      // gacc / gml are reused by the next head group
                     }
                     __threadfence();
                     pk_named_sync();
@@ -616,7 +609,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                     pk_named_sync();
                     if (*s_flag) {
                         __threadfence();
-                        float* cm = redbuf;                 // [n_rep][nsplit] weights
+                        float* cm = xs;                      // [n_rep][nsplit] weights
                         float* cden = cm + kAttnMaxRep * a.nsplit;
                         if (warp < n_rep) {
                             const int h = warp;

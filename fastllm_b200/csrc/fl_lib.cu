@@ -487,7 +487,9 @@ static void plan_persistent(fl_cache& c) {
     if (w.H % 8 || nq % 8 || w.I % 8 || w.nqkv % 2 || w.V % 2) return;
     const int n_rep = w.nh / w.nkv;
     int kmax = std::max(w.H, std::max(nq, w.I));
-    p.xs_floats = (int)align_up((size_t)std::max(kmax, 8 * w.d * (1 + n_rep) + 8 * kNumSMs + 8), 4);
+    // attention scratch in the same region: [lane groups = 8 warps * 32/(d/8)][4 heads][d] + (m, l) pairs = 8192 + 512 floats,
+    // and the split-merge weights [8][nsplit] + 8
+    p.xs_floats = (int)align_up((size_t)std::max(std::max(kmax, 8192 + 512), 8 * kNumSMs + 16), 4);
     int rows = 0;
     for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) rows = std::max(rows, 2 * ((N / 2 + kNumSMs - 1) / kNumSMs + 1));
     p.partial_rows = rows;
@@ -595,6 +597,7 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     c.logits.alloc((size_t)max_batch * w.Vfull, true);
     if (w.tp > 1) {
         c.tp_buf.alloc((size_t)kPassRows * w.H);
+        c.resid2.alloc((size_t)kPassRows * w.H);
         c.tp_local.alloc((size_t)max_batch * w.V, true);
         c.tp_gather.alloc((size_t)w.tp * max_batch * w.V);
     }
@@ -652,13 +655,27 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
 
         launch(lc, "embed_gather", (uint64_t)M * w.H * 2, embed_gather_kernel, dim3((w.H / 8 + 255) / 256, M), dim3(256), 0,
                (const uint16_t*)w.embed, (const uint32_t*)c.ids.p, row_base, w.H, w.Vfull, c.resid.p);
+        // tensor parallelism: the all-reduced o_proj / down_proj output is added to the residual stream inside the NEXT
+        // RMSNorm prologue (which writes the advanced stream to the other of two buffers), not by a separate kernel
+        float* rcur = c.resid.p;
+        float* roth = c.resid2.p;
+        const float* pending = nullptr;
+        auto take_pending = [&](GemvArgs& ga) {
+            ga.x = rcur;
+            if (pending) {
+                ga.delta = pending; ga.resid_out = roth;
+                std::swap(rcur, roth);
+                pending = nullptr;
+            }
+        };
 
         for (int l = 0; l < w.L; ++l) {
             const LayerW& lw = w.layers[l];
             GemvArgs a{};
             a.row_base = row_base; a.t = t; a.eps = w.cfg.norm_eps;
             // K2+K3+K4+K5+K6: RMSNorm -> fused q|k|v GEMV (+bias) -> RoPE -> q store + in-place paged KV append
-            a.W = lw.wqkv; a.N = w.nqkv; a.K = w.H; a.x = c.resid.p; a.norm_w = lw.ln1; a.bias = lw.bqkv;
+            a.W = lw.wqkv; a.N = w.nqkv; a.K = w.H; a.norm_w = lw.ln1; a.bias = lw.bqkv;
+            take_pending(a);
             a.q_out = c.q.p; a.kpool = c.kpool.p + (size_t)l * c.layer_pool_elems; a.vpool = c.vpool.p + (size_t)l * c.layer_pool_elems;
             a.page_table = c.page_table.p; a.pt_stride = c.pages_per_seq; a.state = c.state.p;
             a.rope_cos = w.rope_cos; a.rope_sin = w.rope_sin; a.nh = w.nh; a.nkv = w.nkv; a.d = w.d; a.max_pos = w.max_pos;
@@ -682,7 +699,7 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
                 o.out = c.tp_buf.p; o.ldo = w.H;
                 launch_gemv<PRO_PLAIN, EPI_STORE>(lc, "gemv_o_partial", M, p_o, o);
                 tp_allreduce_sum(lc, c.tp_buf.p, (size_t)M * w.H);
-                launch(lc, "tp_resid_add", 0, add_rows_kernel, dim3(8), dim3(256), 0, c.resid.p, (const float*)c.tp_buf.p, M * w.H);
+                pending = c.tp_buf.p;
             } else {
                 launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_o_resid", M, p_o, o);
             }
@@ -690,7 +707,8 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
             // K14+K15: RMSNorm -> fused gate|up GEMV -> SiLU(gate) * up
             GemvArgs g{};
             g.row_base = row_base; g.t = t; g.eps = w.cfg.norm_eps;
-            g.W = lw.wgu; g.N = 2 * w.I; g.K = w.H; g.x = c.resid.p; g.norm_w = lw.ln2; g.out = c.act.p;
+            g.W = lw.wgu; g.N = 2 * w.I; g.K = w.H; g.norm_w = lw.ln2; g.out = c.act.p;
+            take_pending(g);
             launch_gemv<PRO_RMSNORM, EPI_SILU>(lc, "gemv_gateup_silu", M, p_gu, g);
 
             // K16: down_proj + residual add
@@ -701,7 +719,7 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
                 dn.out = c.tp_buf.p; dn.ldo = w.H;
                 launch_gemv<PRO_PLAIN, EPI_STORE>(lc, "gemv_down_partial", M, p_down, dn);
                 tp_allreduce_sum(lc, c.tp_buf.p, (size_t)M * w.H);
-                launch(lc, "tp_resid_add", 0, add_rows_kernel, dim3(8), dim3(256), 0, c.resid.p, (const float*)c.tp_buf.p, M * w.H);
+                pending = c.tp_buf.p;
             } else {
                 launch_gemv<PRO_PLAIN, EPI_RESID>(lc, "gemv_down_resid", M, p_down, dn);
             }
@@ -710,7 +728,8 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
             // K17 (+K18): final RMSNorm -> lm_head -> f32 logits of the last position + arg-max partials
             GemvArgs h{};
             h.row_base = row_base; h.t = t; h.eps = w.cfg.norm_eps;
-            h.W = w.lm_head; h.N = w.V; h.K = w.H; h.x = c.resid.p; h.norm_w = w.final_norm;
+            h.W = w.lm_head; h.N = w.V; h.K = w.H; h.norm_w = w.final_norm;
+            take_pending(h);
             h.out = c.logits.p; h.ldo = w.V; h.last_only = 1; h.amax_val = c.amax_val.p; h.amax_idx = c.amax_idx.p;
             if (w.tp > 1) {   // vocab-parallel head: this rank's slice; gathered + arg-maxed after the pass loop
                 h.out = c.tp_local.p; h.amax_val = nullptr; h.amax_idx = nullptr;

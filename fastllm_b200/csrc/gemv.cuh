@@ -37,6 +37,9 @@ struct GemvArgs {
     int N, K;
     const float* x;      // PRO_PLAIN: activations [M, K]; PRO_RMSNORM: residual stream [M, K]
     const float* norm_w; // PRO_RMSNORM: [K]
+    const float* delta;  // PRO_RMSNORM, optional [M, K]: x = resid + delta is normalised and CTA 0 writes the advanced residual
+    float* resid_out;    // stream to resid_out (a DIFFERENT buffer: other CTAs are still reading `x`).  Tensor parallelism:
+                         // delta = the all-reduced o_proj / down_proj output; this saves a separate residual-add kernel.
     float eps;
     float* out;          // EPI_STORE: [*, ldo]; EPI_RESID: residual [M, N] (+=); EPI_SILU: act [M, N/2]
     int ldo;
@@ -130,6 +133,23 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const GemvArgs a) {
                 for (int i = 0; i < 8; ++i) xr[m][j][i] = 0.f;
             }
         }
+    if (PRO == PRO_RMSNORM && a.delta != nullptr) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+                if (cv[j]) {
+                    const float4* dp = reinterpret_cast<const float4*>(a.delta + (size_t)m * a.K + (size_t)c[j] * 8);
+                    const float4 d0 = dp[0], d1 = dp[1];
+                    xr[m][j][0] += d0.x; xr[m][j][1] += d0.y; xr[m][j][2] += d0.z; xr[m][j][3] += d0.w;
+                    xr[m][j][4] += d1.x; xr[m][j][5] += d1.y; xr[m][j][6] += d1.z; xr[m][j][7] += d1.w;
+                    if (blockIdx.x == 0) {   // the residual stream itself is advanced exactly once
+                        float4* rp = reinterpret_cast<float4*>(a.resid_out + (size_t)m * a.K + (size_t)c[j] * 8);
+                        rp[0] = make_float4(xr[m][j][0], xr[m][j][1], xr[m][j][2], xr[m][j][3]);
+                        rp[1] = make_float4(xr[m][j][4], xr[m][j][5], xr[m][j][6], xr[m][j][7]);
+                    }
+                }
+    }
     if (PRO == PRO_RMSNORM) {
         // candle_nn::ops::rms_norm: m = sqrt(sum(x^2)/n + eps); y = x / m * w
         float ss[M];

@@ -115,6 +115,7 @@ struct fl_cache {
     fl::PkPlan pk;
     fl::DenseWs dw;
     fl::DevBuf<unsigned int> gbar;
+    fl::DevBuf<float> resid2;        // second residual buffer (tp > 1: the fused residual-add prologue ping-pongs)
     fl::DevBuf<float> tp_buf;        // [rows, H] partial o_proj / down_proj outputs awaiting the all-reduce (tp > 1)
     fl::DevBuf<float> tp_gather;     // [tp, max_batch, V] vocab-parallel logits gathered from all ranks
     fl::DevBuf<float> tp_local;      // [max_batch, V] this rank's logits slice
