@@ -54,6 +54,24 @@ def peaks(kind="hbm"):
     return (6650.0 if kind == "hbm" else 1400.0), "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_per_step():
+    """DRAM bytes per decode step of decode_persistent_kernel from the committed `ncu --set full` capture
+    (profiles/r01_persistent_full_raw.csv: one launch of 3 steps, Mistral-7B b=1, KV 2048); None if unavailable."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_persistent_full_raw.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        hdr, units, r = rows[0], rows[1], rows[2]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(r[i]) * scale[units[i]]
+        return tot / 3.0
+    except Exception:
+        return None
+
+
 def minilm_measure(local_rank, b, t, repeats, e2e_iters, warm=3):
     """-> dict(device ms/batch, e2e s/batch) for b x t synthetic sentences on this rank's GPU."""
     from fastllm_b200 import models
@@ -364,7 +382,11 @@ def run_ours(args, rank, world, local_rank):
     kv_bytes = batch * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 2 * 2 // (world if use_tp else 1)
     step_bytes = streamed + kv_bytes
     step_gbs = step_bytes / (ms / K / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    if pk and args.workload == "mistral7b_b1":
+        per_step = ncu_traffic_per_step()
+        traffic = per_step * 4 if per_step else None          # the profiled launch runs 4 steps
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dom_name,
                 "peak_source": peak_src, "kernel_share_of_step": gemv_ms / all_ms if all_ms else None,
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
