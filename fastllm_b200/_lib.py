@@ -56,6 +56,8 @@ SYMBOLS = {
     "fl_embed_timed": (_I, [_VP, _VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_float)]),
     "fl_comm_unique_id": (_I, [_VP]),
     "fl_comm_init": (_I, [_I, _I, _VP]),
+    "fl_comm_ipc_export": (_I, [_VP]),
+    "fl_comm_ipc_import": (_I, [_VP, _I, _I]),
     "fl_comm_destroy": (_I, []),
     "fl_prof_begin": (_I, []),
     "fl_prof_end": (_I, [C.c_char_p, _SZ]),

@@ -46,4 +46,22 @@ struct NcclApi {
 
 extern NcclApi g_nccl;
 
+// Peer-mapped exchange area of the persistent decode kernel's in-kernel all-reduce (CUDA IPC; NVLink P2P stores).
+// One fixed-layout 4 MiB buffer per process; every rank maps every peer's buffer.
+struct PeerComm {
+    static constexpr size_t kBytes = 4u << 20;
+    static constexpr int kMaxH = 16384, kMaxTp = 8;
+    static constexpr size_t kPartOff = 0;                                   // [2][8][kMaxH] f32 = 1 MiB
+    static constexpr size_t kFlagOff = 1u << 20;                            // [8][gridDim.x + 1] u32
+    static constexpr size_t kAmaxOff = (1u << 20) + (64u << 10);            // [8][2] f32
+    static constexpr size_t kErrOff = (1u << 20) + (68u << 10);             // int
+    static constexpr size_t kLogitsOff = (1u << 20) + (128u << 10);         // [Vfull] f32
+    static constexpr size_t kMaxVocab = (kBytes - kLogitsOff) / 4;
+    void* local = nullptr;
+    void* peer[kMaxTp] = {};
+    bool ready = false;
+    unsigned int ar_epoch = 0;      // exchanges performed so far (identical on every rank: same launch sequence)
+};
+extern PeerComm g_peer;
+
 }  // namespace fl

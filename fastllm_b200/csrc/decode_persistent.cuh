@@ -75,6 +75,14 @@ struct PkArgs {
     int nstages;
     int xs_floats;        // shared-memory activation vector capacity (floats)
     int partial_rows;     // rows of the per-warp partial buffer
+    // ---- tensor parallelism inside the kernel: all-reduce over NVLink peer memory (no NCCL call, no extra launch) ----
+    int tp, rank;                    // tp == 1: single GPU
+    float* peer_part[8];             // rank r's receive area [2 parities][tp sources][H] f32   (peer-mapped, r == rank: local)
+    unsigned int* peer_flag[8];      // rank r's flags [tp sources][gridDim.x + 1] u32, monotone exchange epochs
+    float* peer_amax[8];             // rank r's arg-max exchange slots [tp sources][2] (value, index bits)
+    float* peer_logits[8];           // rank r's full-vocabulary logits [Vfull]
+    unsigned int ar_epoch0;          // exchanges completed on this communicator before this launch
+    int* comm_err;                   // set to 1 when a peer did not show up within the spin budget
     int flags;            // bit 0: prefetch this CTA's KV pages into L2 at the top of P1
     int lookahead_bytes;  // how far (per CTA) the producer prefetches into L2 beyond the shared-memory ring
     long long* dbg;       // optional: CTA 0 writes %globaltimer at the phase boundaries of layer L/2 (FL_PK_DEBUG=1)
@@ -194,6 +202,25 @@ __device__ __forceinline__ void pk_grid_barrier(unsigned int* ctr, unsigned int&
         __threadfence();
     }
     pk_named_sync();
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// wait until the peer's flag reaches `epoch`; bounded (about 2 s) so that a missing peer becomes an error, not a hang
+__device__ __forceinline__ void pk_wait_flag(const unsigned int* flag, unsigned int epoch, int* err) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > 4000000000LL) {
+            *err = 1;
+            break;
+        }
+    }
 }
 
 template <int D>
@@ -368,6 +395,39 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         float v = pr[0];
         for (int k = 1; k < nslot; ++k) v += pr[k];
         return v;
+    };
+    // Row-parallel epilogue under tensor parallelism: resid[slice] += sum over ranks of this rank-local partial output.
+    // One-shot exchange over NVLink peer memory: every CTA PUSHES its partial row slice into every rank's receive area
+    // (tp x ~100 bytes), publishes a per-CTA flag with release.sys, waits for the same CTA of every peer, then sums the tp
+    // partials in rank order (identical on every rank, so the replicas stay bit-identical) and adds them to the residual.
+    unsigned int ar_epoch = a.ar_epoch0;
+    auto allreduce_resid_add = [&](const PkSlice& s) {
+        ar_epoch += 1;
+        const int par = ar_epoch & 1;
+        const int npair = (s.row_end - s.row_begin) / 2;
+        for (int e = tid; e < npair; e += kPkConsumers) {
+            const float2 v = make_float2(row_sum(s, 2 * e), row_sum(s, 2 * e + 1));
+            const size_t off = (size_t)(par * a.tp + a.rank) * a.H + s.row_begin + 2 * e;
+            for (int r = 0; r < a.tp; ++r) *reinterpret_cast<float2*>(a.peer_part[r] + off) = v;
+        }
+        __threadfence_system();
+        pk_named_sync();
+        if (tid < a.tp) {
+            st_release_sys(a.peer_flag[tid] + (size_t)a.rank * (ncta + 1) + cta, ar_epoch);
+            pk_wait_flag(a.peer_flag[a.rank] + (size_t)tid * (ncta + 1) + cta, ar_epoch, a.comm_err);
+        }
+        pk_named_sync();
+        const float* mine = a.peer_part[a.rank];
+        for (int e = tid; e < npair; e += kPkConsumers) {
+            float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
+            float2 v = __ldcg(p);
+            for (int r = 0; r < a.tp; ++r) {
+                const float2 y = __ldcg(reinterpret_cast<const float2*>(mine + (size_t)(par * a.tp + r) * a.H + s.row_begin + 2 * e));
+                v.x += y.x;
+                v.y += y.y;
+            }
+            *p = v;
+        }
     };
     auto block_sum = [&](float v) {   // sum over the 256 consumer threads
         v = warp_sum(v);
@@ -660,12 +720,16 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             {
                 const PkSlice s = consume(a.H, nq);
                 stamp(l);
-                for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                    float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
-                    float2 v = __ldcg(p);
-                    v.x += row_sum(s, 2 * e);
-                    v.y += row_sum(s, 2 * e + 1);
-                    *p = v;
+                if (a.tp > 1) {
+                    allreduce_resid_add(s);
+                } else {
+                    for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
+                        float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
+                        float2 v = __ldcg(p);
+                        v.x += row_sum(s, 2 * e);
+                        v.y += row_sum(s, 2 * e + 1);
+                        *p = v;
+                    }
                 }
             }
             stamp(l);
@@ -693,12 +757,16 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             {
                 const PkSlice s = consume(a.H, a.I);
                 stamp(l);
-                for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                    float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
-                    float2 v = __ldcg(p);
-                    v.x += row_sum(s, 2 * e);
-                    v.y += row_sum(s, 2 * e + 1);
-                    *p = v;
+                if (a.tp > 1) {
+                    allreduce_resid_add(s);
+                } else {
+                    for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
+                        float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
+                        float2 v = __ldcg(p);
+                        v.x += row_sum(s, 2 * e);
+                        v.y += row_sum(s, 2 * e + 1);
+                        *p = v;
+                    }
                 }
             }
             stamp(l);
@@ -713,12 +781,17 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             float bv = -INFINITY;
             int bi = -1;
             for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                const int ra = s.row_begin + 2 * e;
+                const int ra = a.rank * a.V + s.row_begin + 2 * e;      // index in the FULL vocabulary (vocab-parallel head)
                 const float va = row_sum(s, 2 * e), vb = row_sum(s, 2 * e + 1);
-                *reinterpret_cast<float2*>(a.logits + ra) = make_float2(va, vb);
+                if (a.tp > 1) {
+                    for (int r = 0; r < a.tp; ++r) *reinterpret_cast<float2*>(a.peer_logits[r] + ra) = make_float2(va, vb);
+                } else {
+                    *reinterpret_cast<float2*>(a.logits + ra) = make_float2(va, vb);
+                }
                 if (va >= bv) { bv = va; bi = ra; }
                 if (vb >= bv) { bv = vb; bi = ra + 1; }
             }
+            if (a.tp > 1) __threadfence_system();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
@@ -738,6 +811,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             }
         }
         pk_grid_barrier(a.gbar, epoch, tid);
+        if (a.tp > 1) ar_epoch += 1;      // the arg-max exchange below is exchange number 2L+1 of the step (uniform in every thread)
         if (cta == 0 && warp == 0) {
             float bv = -INFINITY;
             int bi = -1;
@@ -751,6 +825,28 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 const float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
                 const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
                 if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+            }
+            if (a.tp > 1) {   // exchange the per-rank winners (and, by cumulativity, make every rank's logits slice visible)
+                if (lane == 0) {
+                    for (int r = 0; r < a.tp; ++r) {
+                        a.peer_amax[r][a.rank * 2] = bv;
+                        a.peer_amax[r][a.rank * 2 + 1] = __int_as_float(bi);
+                    }
+                    __threadfence_system();
+                }
+                __syncwarp();
+                if (lane < a.tp) {
+                    st_release_sys(a.peer_flag[lane] + (size_t)a.rank * (ncta + 1) + ncta, ar_epoch);
+                    pk_wait_flag(a.peer_flag[a.rank] + (size_t)lane * (ncta + 1) + ncta, ar_epoch, a.comm_err);
+                }
+                __syncwarp();
+                bv = -INFINITY;
+                bi = -1;
+                for (int r = 0; r < a.tp; ++r) {
+                    const float ov = __ldcg(a.peer_amax[a.rank] + r * 2);
+                    const int oi = __float_as_int(__ldcg(a.peer_amax[a.rank] + r * 2 + 1));
+                    if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+                }
             }
             if (lane == 0) {
                 a.next_ids[0] = (uint32_t)bi;

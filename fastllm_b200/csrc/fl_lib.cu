@@ -19,6 +19,7 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 Profiler g_prof;
 NcclApi g_nccl;
+PeerComm g_peer;
 static std::atomic<int> g_device{-1};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -479,11 +480,12 @@ static void plan_persistent(fl_cache& c) {
     PkPlan& p = c.pk;
     p.ok = false;
     if (env_flag("FL_NO_PERSISTENT")) return;
-    if (w.tp > 1) return;                  // the persistent kernel has no in-kernel collective yet: TP uses the multi-kernel path
+    // tensor parallelism: the kernel all-reduces over peer-mapped memory, which needs the CUDA-IPC exchange area
+    if (w.tp > 1 && (!g_peer.ready || w.H > PeerComm::kMaxH || (size_t)w.Vfull > PeerComm::kMaxVocab || w.tp > PeerComm::kMaxTp)) return;
     if (w.cfg.arch == FL_ARCH_MIXTRAL) return;   // MoE runs on the dense path
     const int nq = w.nh * w.d;
     if (!(w.d == 64 || w.d == 128)) return;
-    if (w.H < 2048 || nq < 2048 || w.I < 2048) return;      // every row must span all 256 consumer threads
+    if (w.H < 2048 || nq < 256 || w.I < 256) return;        // small models stay on the multi-kernel path
     if (w.H % 8 || nq % 8 || w.I % 8 || w.nqkv % 2 || w.V % 2) return;
     const int n_rep = w.nh / w.nkv;
     int kmax = std::max(w.H, std::max(nq, w.I));
@@ -526,6 +528,19 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     a.trace = feedback ? c.trace.p : nullptr; a.trace_pos = c.trace_pos.p; a.gbar = c.gbar.p;
     a.nsteps = nsteps; a.feedback = feedback ? 1 : 0; a.nstages = c.pk.nstages; a.xs_floats = c.pk.xs_floats;
     a.partial_rows = c.pk.partial_rows;
+    a.tp = w.tp; a.rank = w.rank;
+    if (w.tp > 1) {
+        for (int r = 0; r < w.tp; ++r) {
+            uint8_t* base = (uint8_t*)g_peer.peer[r];
+            a.peer_part[r] = (float*)(base + PeerComm::kPartOff);
+            a.peer_flag[r] = (unsigned int*)(base + PeerComm::kFlagOff);
+            a.peer_amax[r] = (float*)(base + PeerComm::kAmaxOff);
+            a.peer_logits[r] = (float*)(base + PeerComm::kLogitsOff);
+        }
+        a.comm_err = (int*)((uint8_t*)g_peer.local + PeerComm::kErrOff);
+        a.ar_epoch0 = g_peer.ar_epoch;
+        g_peer.ar_epoch += (unsigned int)nsteps * (2u * (unsigned int)w.L + 1u);
+    }
     {
         const char* la = std::getenv("FL_PK_LOOKAHEAD_KB");
         a.lookahead_bytes = (la ? std::atoi(la) : 128) * 1024;
@@ -553,6 +568,8 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
         g_prof.entries.push_back(pe);
     }
     g_launches.fetch_add(1);
+    if (w.tp > 1)   // every rank received every logits slice in its exchange area: hand them to the usual logits buffer
+        FL_CUDA(cudaMemcpyAsync(c.logits.p, (uint8_t*)g_peer.local + PeerComm::kLogitsOff, (size_t)w.Vfull * 4, cudaMemcpyDeviceToDevice, c.stream));
     if (dbg) {
         static const char* names[] = {"P1 x(rmsnorm)", "P1 consume qkv", "P1 epilogue", "P1 grid barrier", "P2 attention", "P2 grid barrier",
                                       "P3 x", "P3 consume o", "P3 epilogue", "P3 grid barrier", "P4 x(rmsnorm)", "P4 consume gate/up",
@@ -1037,6 +1054,13 @@ using namespace fl;
         return FL_ERR_INVALID;                                     \
     }
 
+static void check_peer_error() {
+    if (!g_peer.ready) return;
+    int err = 0;
+    FL_CUDA(cudaMemcpy(&err, (uint8_t*)g_peer.local + PeerComm::kErrOff, 4, cudaMemcpyDeviceToHost));
+    FL_CHECK(err == 0, FL_ERR_NCCL, "tensor-parallel exchange timed out: a peer rank did not reach the same decode step");
+}
+
 static void use_device() {
     const int dev = g_device.load();
     FL_CHECK(dev >= 0, FL_ERR_STATE, "fl_init has not been called");
@@ -1226,6 +1250,7 @@ FL_EXPORT int fl_forward(fl_model* m, fl_cache* c, const uint32_t* ids, int b, i
         const size_t n = (size_t)b * c->w->Vfull;
         FL_CUDA(cudaMemcpyAsync(c->h_logits.p, c->logits.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
         FL_CUDA(cudaStreamSynchronize(c->stream));
+        check_peer_error();
         std::memcpy(logits_host, c->h_logits.p, n * 4);
     } catch (const fl::Error& e) {
         if (e.code == FL_ERR_CUDA) c->poisoned = true;
@@ -1243,6 +1268,7 @@ FL_EXPORT int fl_forward_greedy(fl_model* m, fl_cache* c, const uint32_t* ids, i
         run_forward(*c, ids, b, t, rope_offset);
         FL_CUDA(cudaMemcpyAsync(c->h_ids.p, c->next_ids.p, (size_t)b * 4, cudaMemcpyDeviceToHost, c->stream));
         FL_CUDA(cudaStreamSynchronize(c->stream));
+        check_peer_error();
         std::memcpy(next_ids, c->h_ids.p, (size_t)b * 4);
     } catch (const fl::Error& e) {
         if (e.code == FL_ERR_CUDA) c->poisoned = true;
@@ -1296,6 +1322,7 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
         }
         FL_CUDA(cudaEventRecord(e1, c->stream));
         FL_CUDA(cudaStreamSynchronize(c->stream));
+        check_peer_error();
         float ms = 0.f;
         FL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         cudaEventDestroy(e0);
@@ -1349,6 +1376,38 @@ FL_EXPORT int fl_comm_init(int rank, int world, const void* id_bytes) {
     g_nccl.check(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank), "ncclCommInitRank");
     g_nccl.rank = rank;
     g_nccl.world = world;
+    FL_API_END
+}
+FL_EXPORT int fl_comm_ipc_export(void* handle_64_bytes) {
+    FL_API_BEGIN
+    FL_CHECK(handle_64_bytes != nullptr, FL_ERR_INVALID, "NULL argument");
+    use_device();
+    if (!g_peer.local) {
+        FL_CUDA(cudaMalloc(&g_peer.local, PeerComm::kBytes));
+        FL_CUDA(cudaMemset(g_peer.local, 0, PeerComm::kBytes));
+        FL_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    FL_CUDA(cudaIpcGetMemHandle(&h, g_peer.local));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_64_bytes, &h, sizeof(h));
+    FL_API_END
+}
+FL_EXPORT int fl_comm_ipc_import(const void* handles, int world, int rank) {
+    FL_API_BEGIN
+    FL_CHECK(handles != nullptr && world >= 1 && world <= PeerComm::kMaxTp && rank >= 0 && rank < world, FL_ERR_INVALID, "bad arguments");
+    FL_CHECK(g_peer.local != nullptr, FL_ERR_STATE, "call fl_comm_ipc_export first");
+    use_device();
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            g_peer.peer[r] = g_peer.local;
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
+            FL_CUDA(cudaIpcOpenMemHandle(&g_peer.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    g_peer.ready = true;
     FL_API_END
 }
 FL_EXPORT int fl_comm_destroy(void) {

@@ -26,6 +26,14 @@ def init_tensor_parallel(rank: int, world: int, device: int):
     dist.broadcast(t, 0)
     raw = bytes(t.cpu().tolist())
     _lib.check(lib.fl_comm_init(rank, world, (C.c_uint8 * 128).from_buffer_copy(raw)))
+    if world > 1:
+        # peer-mapped exchange area for the persistent decode kernel's in-kernel all-reduce (CUDA IPC over NVLink)
+        h = (C.c_uint8 * 64)()
+        _lib.check(lib.fl_comm_ipc_export(h))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h))
+        allh = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        _lib.check(lib.fl_comm_ipc_import(allh, world, rank))
     return raw
 
 

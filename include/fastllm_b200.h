@@ -134,6 +134,10 @@ FL_EXPORT int fl_embed_timed(fl_model* m, const uint32_t* ids, const uint32_t* m
 /* ---- tensor / expert parallelism (one process per GPU; the library owns the NCCL communicator) -- */
 FL_EXPORT int fl_comm_unique_id(void* out_128_bytes);            /* rank 0 creates, the host side broadcasts it */
 FL_EXPORT int fl_comm_init(int rank, int world, const void* unique_id_128_bytes);
+/* Peer-memory exchange area of the persistent decode kernel's in-kernel all-reduce (CUDA IPC over NVLink): every rank exports
+ * its buffer handle, the host side all-gathers the 64-byte handles, every rank imports all of them ([world][64] bytes). */
+FL_EXPORT int fl_comm_ipc_export(void* handle_64_bytes);
+FL_EXPORT int fl_comm_ipc_import(const void* handles, int world, int rank);
 FL_EXPORT int fl_comm_destroy(void);
 
 /* ---- measurement hooks (bench.py / tests) ------------------------------------------------------- */

@@ -41,6 +41,9 @@ def test_tp2_matches_tp1(tmp_path):
     # expert parallelism (Mixtral): EP-2 == EP-1 == golden greedy ids
     assert r1["mixtral"]["ids"] == r2["mixtral"]["ids"] == r1["mixtral"]["golden_ids"]
     assert np.abs(np.array(r1["mixtral"]["logits"]) - np.array(r2["mixtral"]["logits"])).max() < 3e-3
+    # persistent decode kernel with the in-kernel NVLink all-reduce (TP-2) against the single-GPU persistent kernel
+    assert r1["wide"]["ids"] == r2["wide"]["ids"] and r1["wide"]["loop_ids"] == r2["wide"]["loop_ids"]
+    assert np.abs(np.array(r1["wide"]["logits"]) - np.array(r2["wide"]["logits"])).max() < 6e-3
     one, two = r1["mistral"], r2["mistral"]
     assert one["ids"] == two["ids"]
     assert np.abs(np.array(one["logits"]) - np.array(two["logits"])).max() < 3e-3

@@ -38,6 +38,22 @@ def gpu_main(out_path):
         p3 = np.stack([g["prompt"], g["prompt"][::-1], np.roll(g["prompt"], 3)]).astype(np.uint32)
         l3 = c3.forward(p3, 0)
         res[name] = {"ids": [int(i) for i in ids], "logits": np.stack(logits).tolist(), "synth_logits": l2[0, 0].tolist(), "batch3": l3.tolist()}
+    # true-width 2-layer Mistral-7B: batch-1 decode runs in the persistent kernel, whose all-reduce goes over NVLink peer memory
+    cfw = models.ConfigFile(4096, 14336, 32000, 2, 32, 8, 1e-5, 10000.0, 256, 4096, tp_rank=rank, tp_size=world)
+    mw, _ = models.MistralWithConfig.initialize_model(cfw, None, "bf16", local, random_seed=0, std=0.02)
+    cw = models.DeviceCache(mw.dev, 1, 200)
+    from oracle import synth
+    pw = synth.token_ids(1, 32000, (1, 70))
+    tok = cw.forward_greedy(pw, 0)
+    step_ids, step_logits = [], []
+    for s_ in range(5):
+        lg = cw.forward(tok.reshape(1, 1), 70 + s_)                  # one persistent launch per step
+        step_logits.append(lg[0].tolist())
+        tok = np.array([models.sample_argmax(lg[0])], dtype=np.uint32)
+        step_ids.append(int(tok[0]))
+    loop_ids, _ = cw.decode_greedy_loop(tok, 75, 6)                   # six steps inside one launch
+    res["wide"] = {"ids": step_ids, "logits": step_logits, "loop_ids": [int(i) for i in loop_ids[:, 0]]}
+    del cw, mw
     # Mixtral: expert parallelism (experts sharded across ranks, attention replicated, one all-reduce per MoE block)
     cfg, w, g = golden_weights("mixtral")
     cf = models.ConfigFile(cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers, cfg.num_attention_heads,
