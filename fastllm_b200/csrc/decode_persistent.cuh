@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             const size_t off = (size_t)(par * a.tp + a.rank) * a.H + s.row_begin + 2 * e;
             for (int r = 0; r < a.tp; ++r) *reinterpret_cast<float2*>(a.peer_part[r] + off) = v;
         }
-        __threadfence_system();
+        // no per-thread system fence: the CTA barrier orders every thread's pushes before the flag writers' st.release.sys,
+        // which is cumulative at system scope (PTX memory model), so one release per peer publishes the whole slice
         pk_named_sync();
         if (tid < a.tp) {
             st_release_sys(a.peer_flag[tid] + (size_t)a.rank * (ncta + 1) + cta, ar_epoch);
