@@ -31,6 +31,8 @@ struct AttnArgs {
     float* part_ml;        // [rows, nh, nsplit, 2]
     int* counters;         // [rows, nkv], zero between launches
     float* out;            // [rows, nh*d]
+    uint16_t* out_hi;      // attn_mma.cuh kernels, optional: write the output as the hi/lo bf16 pair the o_proj GEMM consumes
+    uint16_t* out_lo;      // (instead of `out`)
     int nh, nkv, t, row_base;
     int sliding_window;    // <= 0: none
     float qscale;          // q is multiplied by this (1/sqrt(d))

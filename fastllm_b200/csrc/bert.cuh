@@ -6,6 +6,7 @@
 //   pool_l2_kernel    : masked mean pooling (divisor = mask_count * hidden [sic], :346-368) + L2 normalise (:341-344)
 #pragma once
 #include "common.cuh"
+#include "mma.cuh"
 
 namespace fl {
 
@@ -76,22 +77,6 @@ static __global__ void layernorm_kernel(const float* __restrict__ x, const float
 }
 
 // ---- fused small-head attention (t <= 128, d = 32) on mma.sync m16n8k16 bf16 ------------------------------------------
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { return pack_bf16x2(lo, hi); }
-
 constexpr int kBertS = 128;      // max tokens per sentence handled by the fused kernel
 constexpr int kBertD = 32;       // head dim
 constexpr int kBertLd = 40;      // padded smem row (80 bytes): conflict-free ldmatrix

@@ -4,6 +4,7 @@
 #include <sstream>
 
 #include "attn_decode.cuh"
+#include "attn_mma.cuh"
 #include "comm.cuh"
 #include "decode_persistent.cuh"
 #include "dense_ops.cuh"
@@ -111,6 +112,32 @@ static void launch_attn(LaunchCtx& lc, int d, int nsplit, int nkv, int rows, siz
         case 128: launch(lc, "attn_decode", bytes, attn_decode_kernel<128>, g, b, smem, a); break;
         default: throw Error(FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
     }
+}
+
+// tensor-core attention of the dense path (attn_mma.cuh): batched decode (one CTA per split x kv head x sequence) or prefill
+// (one CTA per 64-query tile x q head x sequence)
+static size_t attn_mma_smem_bytes(int d, bool decode) { return (size_t)((decode ? 32 : 2 * kPrefillBM) + 4 * kKvPage) * d * 2; }
+
+template <int D>
+static void attn_mma_set_attrs() {
+    FL_CUDA(cudaFuncSetAttribute(attn_gqa_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_mma_smem_bytes(D, true)));
+    FL_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_mma_smem_bytes(D, false)));
+}
+
+static void launch_attn_mma(LaunchCtx& lc, int d, bool decode, dim3 g, uint64_t bytes, const AttnArgs& a) {
+    const size_t smem = attn_mma_smem_bytes(d, decode);
+    const dim3 b(kMmaAttnThreads);
+    const char* tag = decode ? "attn_gqa_decode" : "attn_prefill";
+#define FL_ATTN_CASE(D)                                                             \
+    case D:                                                                         \
+        if (decode) launch(lc, tag, bytes, attn_gqa_decode_kernel<D>, g, b, smem, a); \
+        else launch(lc, tag, bytes, attn_prefill_kernel<D>, g, b, smem, a);         \
+        break;
+    switch (d) {
+        FL_ATTN_CASE(16) FL_ATTN_CASE(32) FL_ATTN_CASE(64) FL_ATTN_CASE(128)
+        default: throw Error(FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
+    }
+#undef FL_ATTN_CASE
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -634,6 +661,12 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
         case 64: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
         default: FL_CUDA(cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); break;
     }
+    switch (w.d) {
+        case 16: attn_mma_set_attrs<16>(); break;
+        case 32: attn_mma_set_attrs<32>(); break;
+        case 64: attn_mma_set_attrs<64>(); break;
+        default: attn_mma_set_attrs<128>(); break;
+    }
     FL_CUDA(cudaDeviceSynchronize());
 }
 
@@ -773,7 +806,6 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
 // ------------------------------------------------------------------------------------------------------------------
 // Dense (tcgen05) path: prefill and batched decode with 3+ activation rows
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDenseAttnChunk = 64;
 constexpr int kDenseMaxSplit = 8;     // split-K slices (only when there are too few output tiles to fill the GPU)
 
 static void ensure_dense_ws(fl_cache& c, int rows) {
@@ -795,7 +827,7 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
         d.xhi2.alloc(R * kmax); d.xlo2.alloc(R * kmax);
         d.moe_out.alloc(R * w.H); d.route_w.alloc(R * w.E);
     }
-    d.chunk = std::min(rows, kDenseAttnChunk);
+    d.chunk = std::min(rows, kMaxBatch);            // split partials of the batched-decode attention: one row per sequence
     d.part_acc.alloc((size_t)d.chunk * w.nh * c.nsplit * w.d);
     d.part_ml.alloc((size_t)d.chunk * w.nh * c.nsplit * 2);
     d.counters.alloc((size_t)d.chunk * w.nkv, true);
@@ -887,21 +919,22 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
         QkvEpiArgs qa{ks, (long long)R * w.nqkv, d.y.p, lw.bqkv, d.q.p, kpool, vpool, c.page_table.p, c.pages_per_seq, c.state.p, w.rope_cos,
                       w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t, w.nqkv};
         launch(lc, "dense_qkv_rope_append", 0, dense_qkv_epi_kernel, dim3((w.nqkv / 2 + 255) / 256, R), dim3(256), 0, qa);
-        for (int r0 = 0; r0 < R; r0 += d.chunk) {
-            const int rows = std::min(d.chunk, R - r0);
+        {   // K7-K11 on tensor cores; the output lands as the hi/lo bf16 operands of the o_proj GEMM
             AttnArgs at{};
-            at.q = d.q.p + (size_t)r0 * nq; at.kpool = kpool; at.vpool = vpool; at.page_table = c.page_table.p; at.pt_stride = c.pages_per_seq;
+            at.q = d.q.p; at.kpool = kpool; at.vpool = vpool; at.page_table = c.page_table.p; at.pt_stride = c.pages_per_seq;
             at.state = c.state.p; at.part_acc = d.part_acc.p; at.part_ml = d.part_ml.p; at.counters = d.counters.p;
-            at.out = d.attn.p + (size_t)r0 * nq; at.nh = w.nh; at.nkv = w.nkv; at.t = t; at.row_base = r0;
+            at.out_hi = d.xhi.p; at.out_lo = d.xlo.p; at.nh = w.nh; at.nkv = w.nkv; at.t = t; at.row_base = 0;
             at.sliding_window = windowed ? w.cfg.sliding_window : 0; at.qscale = qscale;
-            // enough (row, kv head) pairs already fill the GPU: fewer, longer splits stream pages through the 2-stage ring
-            const int nsp = std::max(1, std::min(c.nsplit, (3 * kNumSMs + rows * w.nkv - 1) / (rows * w.nkv)));
-            launch_attn(lc, w.d, nsp, w.nkv, rows, attn_smem, (uint64_t)rows * (c.kv_len + t) * w.nkv * w.d * 4, at);
-        }
-        {   // attention output -> hi/lo
-            PrepArgs pa{};
-            pa.src = d.attn.p; pa.K = nq;
-            prep("dense_split", pa, R);
+            const uint64_t kv_bytes = (uint64_t)b * (c.kv_len + t) * w.nkv * w.d * 4;
+            if (t == 1) {
+                // ~4 waves of 3 resident CTAs per SM; a split streams at least one 64-token page
+                const int npages = (c.kv_len + t + kKvPage - 1) / kKvPage;
+                const int want = (12 * kNumSMs + b * w.nkv - 1) / (b * w.nkv);
+                const int nsp = std::max(1, std::min(std::min(c.nsplit, npages), want));
+                launch_attn_mma(lc, w.d, true, dim3(nsp, w.nkv, b), kv_bytes, at);
+            } else {
+                launch_attn_mma(lc, w.d, false, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
+            }
         }
         ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p);
         const float* delta = d.y.p;

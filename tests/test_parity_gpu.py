@@ -236,3 +236,32 @@ def test_mixtral_router_known_answers_and_batch():
     err = float(np.abs(np.stack(logits) - np.stack(o_logits)).max())
     print(f"mixtral true-width layer: max-abs logits err vs oracle (bf16 KV) {err:.3e}")
     assert ids == o_ids and err <= KERNEL_TOL_WIDE
+
+
+@pytest.mark.parametrize("name,b,t,steps", [("llama_gqa8", 3, 150, 3), ("qwen2", 4, 131, 3), ("mistral", 5, 70, 2),
+                                            ("mistral_sw70", 3, 200, 2)])
+def test_tensor_core_attention_long_context(name, b, t, steps):
+    """attn_prefill_kernel / attn_gqa_decode_kernel (attn_mma.cuh): prompts spanning several 64-query tiles and 64-token KV pages,
+    GQA groups of 8 / 7 / 2 heads, a sliding window that starts inside a later page than the query tile's first key, then
+    batched decode steps (one CTA per split x kv head x sequence) -- against the oracle with the same bf16 KV rounding."""
+    from dataclasses import replace
+    from fastllm_b200 import models
+    if name == "mistral_sw70":
+        cfg = replace(TINY["mistral"], sliding_window=70)
+    else:
+        cfg = TINY[name]
+    cfg = replace(cfg, max_position_embeddings=512)
+    w = ocl.synth_weights(cfg, 11, 0.08)
+    model, _ = product_model(cfg, w)
+    prompts = synth.token_ids(31, cfg.vocab_size, (b, t))
+    oracle = ocl.CausalLM(cfg, w, kv_dtype="bf16")
+    cache = models.DeviceCache(model.dev, b, t + steps + 1)
+    want, got = oracle.forward(prompts, 0), cache.forward(prompts, 0)
+    errs = [float(np.abs(want - got).max())]
+    for s in range(steps):
+        nxt = np.array([[models.sample_argmax(r)] for r in got], dtype=np.uint32)
+        assert [models.sample_argmax(r) for r in want] == [int(x) for x in nxt[:, 0]]
+        want, got = oracle.forward(nxt, t + s), cache.forward(nxt, t + s)
+        errs.append(float(np.abs(want - got).max()))
+    print(f"{name} b={b} t={t}: max-abs logits err per call {['%.2e' % e for e in errs]}")
+    assert max(errs) <= KERNEL_TOL
