@@ -21,7 +21,7 @@ class FlConfig(C.Structure):
                 ("num_key_value_heads", C.c_int32), ("max_position_embeddings", C.c_int32),
                 ("sliding_window", C.c_int32), ("qkv_bias", C.c_int32), ("num_local_experts", C.c_int32),
                 ("num_experts_per_tok", C.c_int32), ("norm_eps", C.c_float), ("rope_theta", C.c_double),
-                ("tp_rank", C.c_int32), ("tp_size", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("tp_rank", C.c_int32), ("tp_size", C.c_int32), ("ep_dp_attention", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class FastllmError(RuntimeError):

@@ -180,7 +180,7 @@ void bert_random_init(BertModel& m, uint64_t seed, float stdv) {
         const uint64_t ts = tensor_seed(seed, n.c_str());
         const RowMap map{r.row0, 0, 0, 0};
         if (r.mat)
-            synth_fill_bf16_kernel<<<kNumSMs * 4, 256>>>((uint16_t*)r.base, r.rows, r.cols, ts, stdv, map);
+            synth_fill_bf16_kernel<<<kNumSMs * 4, 256>>>((uint16_t*)r.base, r.rows, r.cols, r.cols, ts, stdv, map);
         else if (is_ln_w)
             fill_f32_kernel<<<4, 256>>>((float*)r.base + r.row0, r.rows, 1.0f);
         else

@@ -173,18 +173,33 @@ static void build_weights(Weights& w) {
         FL_CHECK(w.E >= 1 && w.E <= 64 && w.top_k >= 1 && w.top_k <= 8 && w.top_k <= w.E, FL_ERR_INVALID, "bad Mixtral expert counts");
         FL_CHECK(w.E % w.ep == 0, FL_ERR_UNSUPPORTED, "expert parallelism needs num_local_experts divisible by the world size");
         w.E_local = w.E / w.ep;
+        w.ep_dp = w.ep > 1 && c.ep_dp_attention != 0;
     }
     FL_CHECK(w.rank >= 0 && w.rank < std::max(w.tp, w.ep), FL_ERR_INVALID, "tp_rank out of range");
     if (w.tp > 1) {
         // column-parallel q/k/v (by head) and gate/up, row-parallel o_proj and down_proj, vocab-parallel lm_head
-        FL_CHECK(nh_f % w.tp == 0 && nkv_f % w.tp == 0, FL_ERR_UNSUPPORTED, "tensor parallelism needs heads and kv heads divisible by tp_size");
+        FL_CHECK((nkv_f % w.tp == 0 && nh_f % w.tp == 0) || (w.tp > nkv_f && w.tp % nkv_f == 0), FL_ERR_UNSUPPORTED,
+                 "tensor parallelism needs heads and kv heads divisible by tp_size, or tp_size a multiple of the kv heads");
         FL_CHECK(c.intermediate_size % (8 * w.tp) == 0 && c.vocab_size % (2 * w.tp) == 0, FL_ERR_UNSUPPORTED,
                  "tensor parallelism needs intermediate_size % (8 tp) == 0 and vocab_size % (2 tp) == 0");
     }
     w.H = c.hidden_size; w.L = c.num_hidden_layers;
     w.I = c.intermediate_size / w.tp; w.Vfull = c.vocab_size; w.V = c.vocab_size / w.tp;
-    w.nh = nh_f / w.tp;
-    w.nkv = nkv_f / w.tp;
+    const int trank = w.tp > 1 ? w.rank : 0;       // under expert parallelism (tp == 1) the attention weights are replicated
+    if (w.tp <= nkv_f) {
+        w.nh = nh_f / w.tp; w.nkv = nkv_f / w.tp;
+        w.q_head0 = trank * w.nh; w.q_real = w.nh; w.kv_head0 = trank * w.nkv;
+    } else {
+        // more ranks than kv heads (Qwen2.5-7B at TP-8: 28 q / 4 kv heads): every kv head lives on rep = tp / nkv ranks, and the
+        // group's query heads are dealt out ceil(group / rep) per rank; the last rank of a group pads with zero heads
+        // (zero q rows and zero o_proj columns contribute nothing)
+        const int rep = w.tp / nkv_f, group = nh_f / nkv_f, hpr = (group + rep - 1) / rep;
+        const int kvh = trank / rep, sub = trank % rep;
+        w.nh = hpr; w.nkv = 1;
+        w.q_head0 = kvh * group + sub * hpr;
+        w.q_real = std::max(0, std::min(hpr, group - sub * hpr));
+        w.kv_head0 = kvh;
+    }
     w.d = w.H / nh_f;
     w.max_pos = c.max_position_embeddings;
     w.nqkv = (w.nh + 2 * w.nkv) * w.d;
@@ -252,6 +267,7 @@ struct TensorRoute {
     enum Kind { BF16_MAT, F32_VEC } kind;
     void* base;
     int64_t rows, cols;             // LOCAL block held by this rank ([rows, cols] or [rows])
+    int64_t ld;                     // leading dimension of the local matrix in elements (>= cols; > cols: zero-padded heads)
     RowMap map;
     int64_t full_rows, full_cols;   // shape the caller hands over (the full HF tensor)
     int64_t src_row0, src_col0;     // window of the full tensor this rank keeps
@@ -262,15 +278,26 @@ static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
                   rk = w.tp > 1 ? w.rank : 0;   // under expert parallelism (tp == 1) every dense tensor is replicated
     // row-sharded matrix: local rows [rk*rows, (rk+1)*rows) of a [tp*rows, cols] tensor; col-sharded: the same along columns
     auto mat_rows = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m, bool sharded) {
-        r = {TensorRoute::BF16_MAT, base, rows, cols, m, sharded ? rows * tp : rows, cols, sharded ? rk * rows : 0, 0};
+        r = {TensorRoute::BF16_MAT, base, rows, cols, cols, m, sharded ? rows * tp : rows, cols, sharded ? rk * rows : 0, 0};
         return true;
     };
     auto mat_cols = [&](uint16_t* base, int64_t rows, int64_t cols, RowMap m) {
-        r = {TensorRoute::BF16_MAT, base, rows, cols, m, rows, cols * tp, 0, rk * cols};
+        r = {TensorRoute::BF16_MAT, base, rows, cols, cols, m, rows, cols * tp, 0, rk * cols};
         return true;
     };
     auto vec = [&](float* base, int64_t rows, RowMap m, bool sharded) {
-        r = {TensorRoute::F32_VEC, base, rows, 1, m, sharded ? rows * tp : rows, 1, sharded ? rk * rows : 0, 0};
+        r = {TensorRoute::F32_VEC, base, rows, 1, 1, m, sharded ? rows * tp : rows, 1, sharded ? rk * rows : 0, 0};
+        return true;
+    };
+    // attention projections: head windows of the full tensors (w.q_head0 / w.q_real / w.kv_head0, see build_weights)
+    const int64_t nh_f = w.cfg.num_attention_heads, nkv_f = w.cfg.num_key_value_heads > 0 ? w.cfg.num_key_value_heads : nh_f;
+    const int64_t qreal = (int64_t)w.q_real * d, q0 = (int64_t)w.q_head0 * d, k0 = (int64_t)w.kv_head0 * d;
+    auto head_rows = [&](uint16_t* base, int64_t rows, RowMap m, int64_t full_heads, int64_t row0) {
+        r = {TensorRoute::BF16_MAT, base, rows, H, H, m, full_heads * d, H, row0, 0};
+        return true;
+    };
+    auto head_vec = [&](float* base, int64_t rows, RowMap m, int64_t full_heads, int64_t row0) {
+        r = {TensorRoute::F32_VEC, base, rows, 1, 1, m, full_heads * d, 1, row0, 0};
         return true;
     };
     const RowMap ident{0, 0, 0, 0};
@@ -289,15 +316,18 @@ static bool route_tensor(Weights& w, const std::string& name, TensorRoute& r) {
     const RowMap ropeq{0, 1, (int32_t)d, 0}, ropek{nq, 1, (int32_t)d, 0}, vmap{nq + nk, 0, 0, 0};
     if (rest == "input_layernorm.weight") return vec(lw.ln1, H, ident, false);
     if (rest == "post_attention_layernorm.weight") return vec(lw.ln2, H, ident, false);
-    if (rest == "self_attn.q_proj.weight") return mat_rows(lw.wqkv, nq, H, ropeq, true);
-    if (rest == "self_attn.k_proj.weight") return mat_rows(lw.wqkv, nk, H, ropek, true);
-    if (rest == "self_attn.v_proj.weight") return mat_rows(lw.wqkv, nk, H, vmap, true);
+    if (rest == "self_attn.q_proj.weight") return head_rows(lw.wqkv, qreal, ropeq, nh_f, q0);
+    if (rest == "self_attn.k_proj.weight") return head_rows(lw.wqkv, nk, ropek, nkv_f, k0);
+    if (rest == "self_attn.v_proj.weight") return head_rows(lw.wqkv, nk, vmap, nkv_f, k0);
     if (w.cfg.qkv_bias) {
-        if (rest == "self_attn.q_proj.bias") return vec(lw.bqkv, nq, ropeq, true);
-        if (rest == "self_attn.k_proj.bias") return vec(lw.bqkv, nk, ropek, true);
-        if (rest == "self_attn.v_proj.bias") return vec(lw.bqkv, nk, vmap, true);
+        if (rest == "self_attn.q_proj.bias") return head_vec(lw.bqkv, qreal, ropeq, nh_f, q0);
+        if (rest == "self_attn.k_proj.bias") return head_vec(lw.bqkv, nk, ropek, nkv_f, k0);
+        if (rest == "self_attn.v_proj.bias") return head_vec(lw.bqkv, nk, vmap, nkv_f, k0);
     }
-    if (rest == "self_attn.o_proj.weight") return mat_cols(lw.wo, H, nq, ident);
+    if (rest == "self_attn.o_proj.weight") {
+        r = {TensorRoute::BF16_MAT, lw.wo, H, qreal, nq, ident, H, nh_f * d, 0, q0};
+        return true;
+    }
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {
         if (rest == "block_sparse_moe.gate.weight") return vec(lw.wgate, (int64_t)w.E * H, ident, false);   // [E, H] kept in f32
         const std::string ep = "block_sparse_moe.experts.";
@@ -376,8 +406,10 @@ static void put_tensor(Weights& w, const char* name, int dtype, const int64_t* s
     if (r.kind == TensorRoute::BF16_MAT) {
         uint16_t* dst = (uint16_t*)r.base;
         const size_t rowb = (size_t)r.cols * 2;
-        if (r.map.mode == 0) {
-            FL_CUDA(cudaMemcpy(dst + r.map.dst_row0 * r.cols, bits.data(), (size_t)numel * 2, cudaMemcpyHostToDevice));
+        if (numel == 0) {
+            // a rank that holds only padding heads of this tensor
+        } else if (r.map.mode == 0) {
+            FL_CUDA(cudaMemcpy2D(dst + r.map.dst_row0 * r.ld, (size_t)r.ld * 2, bits.data(), rowb, rowb, (size_t)r.rows, cudaMemcpyHostToDevice));
         } else if (r.map.mode == 2) {
             FL_CUDA(cudaMemcpy2D(dst + (size_t)r.map.lane * r.cols, 2 * rowb, bits.data(), rowb, rowb, (size_t)r.rows,
                                  cudaMemcpyHostToDevice));
@@ -411,7 +443,7 @@ static void random_init(Weights& w, uint64_t seed, float stdv) {
         const bool is_norm = n.size() >= 11 && n.compare(n.size() - 11, 11, "norm.weight") == 0;
         const uint64_t ts = tensor_seed(seed, n.c_str());
         if (r.kind == TensorRoute::BF16_MAT) {
-            synth_fill_bf16_kernel<<<kNumSMs * 8, 256>>>((uint16_t*)r.base, r.rows, r.cols, ts, stdv, r.map,
+            synth_fill_bf16_kernel<<<kNumSMs * 8, 256>>>((uint16_t*)r.base, r.rows, r.cols, r.ld, ts, stdv, r.map,
                                                          SrcWin{r.src_row0, r.src_col0, r.full_cols});
         } else if (is_norm) {
             fill_f32_kernel<<<8, 256>>>((float*)r.base, r.rows, 1.0f);
@@ -491,6 +523,30 @@ static void tp_allreduce_sum(LaunchCtx& lc, float* buf, size_t count) {
 static void tp_allgather(LaunchCtx& lc, const float* send, float* recv, size_t count) {
     FL_CHECK(g_nccl.comm != nullptr, FL_ERR_STATE, "tensor parallelism: fl_comm_init has not been called");
     g_nccl.check(g_nccl.AllGather(send, recv, count, ncclFloat32, g_nccl.comm, lc.stream), "ncclAllGather");
+    if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+// All-to-all over the communicator (grouped ncclSend / ncclRecv, ONE fused NCCL launch for all segments): for every segment,
+// rank r receives block `r` of every peer's send buffer into recv[src * bytes ...].  `replicate`: every peer gets the SAME
+// block (send holds one block: the expert-parallel dispatch, where a token's row goes to the expert ranks), else send holds
+// `world` blocks (the expert-parallel combine, where expert outputs travel back to the rank that owns the sequence).
+struct A2aSeg {
+    const void* send;
+    void* recv;
+    size_t bytes;       // per peer
+    bool replicate;
+};
+static void ep_alltoall(LaunchCtx& lc, const A2aSeg* segs, int nseg) {
+    FL_CHECK(g_nccl.comm != nullptr, FL_ERR_STATE, "expert parallelism: fl_comm_init has not been called");
+    g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
+    for (int i = 0; i < nseg; ++i) {
+        const A2aSeg& sg = segs[i];
+        for (int p = 0; p < g_nccl.world; ++p) {
+            const uint8_t* sp = (const uint8_t*)sg.send + (sg.replicate ? 0 : (size_t)p * sg.bytes);
+            g_nccl.check(g_nccl.Send(sp, sg.bytes, ncclUint8, p, g_nccl.comm, lc.stream), "ncclSend");
+            g_nccl.check(g_nccl.Recv((uint8_t*)sg.recv + (size_t)p * sg.bytes, sg.bytes, ncclUint8, p, g_nccl.comm, lc.stream), "ncclRecv");
+        }
+    }
+    g_nccl.check(g_nccl.GroupEnd(), "ncclGroupEnd");
     if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
@@ -820,12 +876,18 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     const size_t kmax = std::max<size_t>(std::max<size_t>(w.H, nq), w.I);
     const size_t nmax = std::max<size_t>(std::max<size_t>(w.nqkv, 2 * (size_t)w.I), std::max<size_t>(w.H, w.V));
     d.xhi.alloc(R * kmax); d.xlo.alloc(R * kmax);
-    d.y.alloc(R * nmax * (R <= 128 ? kDenseMaxSplit : 1));
+    const size_t Rm = w.ep_dp ? R * (size_t)w.ep : R;        // rows the expert GEMMs see
+    d.moe_rows = Rm;
+    d.y.alloc(Rm * nmax * (Rm <= 128 ? kDenseMaxSplit : 1));
     d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {
-        d.xhi2.alloc(R * kmax); d.xlo2.alloc(R * kmax);
-        d.moe_out.alloc(R * w.H); d.route_w.alloc(R * w.E);
+        d.xhi2.alloc(Rm * kmax); d.xlo2.alloc(Rm * kmax);
+        d.moe_out.alloc(Rm * w.H); d.route_w.alloc(R * w.E);
+        if (w.ep_dp) {
+            d.g_xhi.alloc(Rm * w.H); d.g_xlo.alloc(Rm * w.H); d.g_route.alloc(Rm * w.E);
+            d.comb.alloc(Rm * w.H);
+        }
     }
     d.chunk = std::min(rows, kMaxBatch);            // split partials of the batched-decode attention: one row per sequence
     d.part_acc.alloc((size_t)d.chunk * w.nh * c.nsplit * w.d);
@@ -958,18 +1020,39 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             // HBM-bound on the expert weights either way.
             launch(lc, "moe_router", 0, moe_router_kernel, dim3(R), dim3(256), 0, (const uint16_t*)d.xhi.p, (const uint16_t*)d.xlo.p, w.H,
                    (const float*)lw.wgate, w.E, w.top_k, d.route_w.p);
+            // expert parallelism with data-parallel attention: DISPATCH -- this rank's rows (hi/lo halves + routing weights)
+            // travel to the expert ranks, which then see the rows of all ranks in rank-major order
+            const int Rm = w.ep_dp ? R * w.ep : R;
+            const uint16_t* ex_hi = d.xhi.p;
+            const uint16_t* ex_lo = d.xlo.p;
+            const float* ex_route = d.route_w.p;
+            if (w.ep_dp) {
+                const A2aSeg segs[3] = {{d.xhi.p, d.g_xhi.p, (size_t)R * w.H * 2, true}, {d.xlo.p, d.g_xlo.p, (size_t)R * w.H * 2, true},
+                                        {d.route_w.p, d.g_route.p, (size_t)R * w.E * 4, true}};
+                ep_alltoall(lc, segs, 3);
+                ex_hi = d.g_xhi.p; ex_lo = d.g_xlo.p; ex_route = d.g_route.p;
+            }
             for (int j = 0; j < w.E_local; ++j) {
                 const int e = w.rank * w.E_local + j;
-                int ke = dense_gemm(c, lc, "gemm_tc_moe_w13", R, 2 * w.I, w.H, lw.tm_ewgu[j], d.y.p);
-                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ke,
-                       (long long)R * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p);
-                ke = dense_gemm(c, lc, "gemm_tc_moe_w2", R, w.H, w.I, lw.tm_ewdown[j], d.y.p, d.xhi2.p, d.xlo2.p);
-                launch(lc, "moe_accum", 0, moe_accum_kernel, dim3((w.H + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ke,
-                       (long long)R * w.H, w.H, (const float*)d.route_w.p, w.E, e, j == 0 ? 1 : 0, d.moe_out.p);
+                int ke = dense_gemm(c, lc, "gemm_tc_moe_w13", Rm, 2 * w.I, w.H, lw.tm_ewgu[j], d.y.p, ex_hi, ex_lo);
+                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, Rm), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)Rm * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p);
+                ke = dense_gemm(c, lc, "gemm_tc_moe_w2", Rm, w.H, w.I, lw.tm_ewdown[j], d.y.p, d.xhi2.p, d.xlo2.p);
+                launch(lc, "moe_accum", 0, moe_accum_kernel, dim3((w.H + 255) / 256, Rm), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)Rm * w.H, w.H, ex_route, w.E, e, j == 0 ? 1 : 0, d.moe_out.p);
             }
-            if (w.ep > 1) tp_allreduce_sum(lc, d.moe_out.p, (size_t)R * w.H);    // expert parallelism: combine = sum over ranks
             delta = d.moe_out.p;
             ks = 1;
+            if (w.ep_dp) {
+                // COMBINE: the weighted expert outputs of rank p's rows travel back to rank p; the owner sums the ep partial
+                // outputs in rank order inside the next residual-add prologue (fixed order: deterministic)
+                const A2aSeg seg{d.moe_out.p, d.comb.p, (size_t)R * w.H * 4, false};
+                ep_alltoall(lc, &seg, 1);
+                delta = d.comb.p;
+                ks = w.ep;
+            } else if (w.ep > 1) {
+                tp_allreduce_sum(lc, d.moe_out.p, (size_t)R * w.H);    // attention replicated: combine = sum over ranks
+            }
         } else {
             ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
             launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
@@ -1252,8 +1335,8 @@ FL_EXPORT int fl_cache_fill_synthetic(fl_cache* c, int batch, int kv_len, uint64
     FL_CHECK(batch >= 1 && batch <= c->max_batch && kv_len >= 0 && kv_len <= c->max_seq, FL_ERR_INVALID, "bad synthetic fill size");
     use_device();
     const RowMap ident{0, 0, 0, 0};
-    synth_fill_bf16_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->kpool.p, 1, (int64_t)c->kpool.n, tensor_seed(seed, "kv.k"), 0.5f, ident);
-    synth_fill_bf16_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->vpool.p, 1, (int64_t)c->vpool.n, tensor_seed(seed, "kv.v"), 0.5f, ident);
+    synth_fill_bf16_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->kpool.p, 1, (int64_t)c->kpool.n, (int64_t)c->kpool.n, tensor_seed(seed, "kv.k"), 0.5f, ident);
+    synth_fill_bf16_kernel<<<kNumSMs * 8, 256, 0, c->stream>>>(c->vpool.p, 1, (int64_t)c->vpool.n, (int64_t)c->vpool.n, tensor_seed(seed, "kv.v"), 0.5f, ident);
     reset_state_kernel<<<1, 256, 0, c->stream>>>(c->state.p, kv_len);
     g_launches.fetch_add(3);
     FL_CUDA(cudaStreamSynchronize(c->stream));

@@ -35,8 +35,13 @@ struct Weights {
     int H = 0, I = 0, V = 0, L = 0, nh = 0, nkv = 0, d = 0, max_pos = 0;
     int nqkv = 0;               // (nh + 2 nkv) * d   (nh, nkv, I, V, nqkv are LOCAL to this tensor-parallel rank)
     int tp = 1, rank = 0;       // tensor-parallel size / rank of this process
+    // this rank's attention heads: full-model q heads [q_head0, q_head0 + q_real) (nh - q_real trailing local heads are zero
+    // padding: tp > kv heads replicates a kv head on tp / nkv ranks and splits its query group between them), kv heads
+    // [kv_head0, kv_head0 + nkv)
+    int q_head0 = 0, q_real = 0, kv_head0 = 0;
     int E = 0, top_k = 0;       // Mixtral: experts / experts per token
     int ep = 1, E_local = 0;    // expert parallelism: this rank holds experts [rank * E_local, (rank + 1) * E_local)
+    bool ep_dp = false;         // expert parallelism with data-parallel attention (fl_config.ep_dp_attention)
     int Vfull = 0;              // full vocabulary (embedding table rows, logits length); V = Vfull / tp rows of lm_head live here
     int device = 0;
     DevBuf<uint8_t> slab;       // every weight lives in this one allocation
@@ -73,6 +78,11 @@ struct DenseWs {
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
     DevBuf<float> moe_out, route_w;
+    // expert parallelism with data-parallel attention: dispatch / combine staging (all rows of all ranks, rank-major)
+    size_t moe_rows = 0;         // rows the expert GEMMs see (rows, or rows * ep)
+    DevBuf<uint16_t> g_xhi, g_xlo;   // [ep * rows, H] gathered block inputs
+    DevBuf<float> g_route;           // [ep * rows, E]
+    DevBuf<float> comb;              // [ep sources][rows, H] expert outputs returned to this rank
     DevBuf<float> part_acc, part_ml;
     DevBuf<int> counters;
 };

@@ -52,13 +52,14 @@ struct RowMap {
 struct SrcWin {
     int64_t row0, col0, cols_full;   // cols_full == 0: the block is the whole tensor
 };
-static __global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols, uint64_t tseed, float stdv, RowMap map,
+// `ld` = leading dimension of the destination matrix (== cols unless the local matrix carries zero-padded columns).
+static __global__ void synth_fill_bf16_kernel(uint16_t* dst, int64_t rows, int64_t cols, int64_t ld, uint64_t tseed, float stdv, RowMap map,
                                               SrcWin win = SrcWin{0, 0, 0}) {
     int64_t n = rows * cols;
     const int64_t cf = win.cols_full ? win.cols_full : cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / cols, c = i - r * cols;
-        dst[map.map(r) * cols + c] = synth_bf16(tseed, (uint64_t)((r + win.row0) * cf + c + win.col0), stdv);
+        dst[map.map(r) * ld + c] = synth_bf16(tseed, (uint64_t)((r + win.row0) * cf + c + win.col0), stdv);
     }
 }
 

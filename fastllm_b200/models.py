@@ -176,6 +176,7 @@ class ConfigFile:
     tp_size: int = 1                   # (for Mixtral the same two fields mean expert-parallel rank / size)
     num_local_experts: int = 0         # Mixtral
     num_experts_per_tok: int = 2
+    ep_dp_attention: bool = False      # Mixtral expert parallelism: sequences data-parallel, tokens all-to-all to the experts
 
 
 def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: int, qkv_bias: bool) -> FlConfig:
@@ -191,6 +192,7 @@ def _fl_config(arch: str, cf: ConfigFile, default_max_pos: int, sliding_window: 
     c.rope_theta = float(cf.rope_theta if cf.rope_theta is not None else 10000.0)
     c.tp_rank, c.tp_size = cf.tp_rank, cf.tp_size
     c.num_local_experts, c.num_experts_per_tok = cf.num_local_experts, cf.num_experts_per_tok
+    c.ep_dp_attention = 1 if cf.ep_dp_attention else 0
     return c
 
 

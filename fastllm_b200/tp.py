@@ -37,16 +37,40 @@ def init_tensor_parallel(rank: int, world: int, device: int):
     return raw
 
 
+def head_layout(nh: int, nkv: int, rank: int, tp: int):
+    """(q_head0, q_real, nh_local, kv_head0, nkv_local) of `rank`: the statement of build_weights() in csrc/fl_lib.cu.
+    tp <= kv heads: an equal split by head.  tp > kv heads (Qwen2.5-7B at TP-8: 28 q / 4 kv heads): every kv head lives on
+    rep = tp / nkv ranks and its query group is dealt out ceil(group / rep) heads per rank, the last rank of a group padding
+    with zero heads (zero q rows, zero o_proj columns)."""
+    if tp <= nkv:
+        assert nh % tp == 0 and nkv % tp == 0
+        return rank * (nh // tp), nh // tp, nh // tp, rank * (nkv // tp), nkv // tp
+    assert tp % nkv == 0
+    rep, group = tp // nkv, nh // nkv
+    hpr = -(-group // rep)
+    kvh, sub = divmod(rank, rep)
+    return kvh * group + sub * hpr, max(0, min(hpr, group - sub * hpr)), hpr, kvh, 1
+
+
 def shard_window(name: str, shape, nh: int, nkv: int, rank: int, tp: int):
     """(row slice, col slice) of the FULL HF tensor `name` kept by `rank` of `tp` (None = whole axis)."""
     rows = shape[0]
     if tp == 1 or name in ("model.embed_tokens.weight", "model.norm.weight") or name.endswith("layernorm.weight"):
         return slice(None), slice(None)
-    if name == "lm_head.weight" or ".q_proj." in name or ".k_proj." in name or ".v_proj." in name or \
-            ".gate_proj." in name or ".up_proj." in name:
-        n = rows // tp                      # q/k/v rows are head-major, so an equal row split is a split by head
+    q0, qn, _, k0, kn = head_layout(nh, nkv, rank, tp)
+    if ".q_proj." in name:
+        d = rows // nh
+        return slice(q0 * d, (q0 + qn) * d), slice(None)
+    if ".k_proj." in name or ".v_proj." in name:
+        d = rows // nkv
+        return slice(k0 * d, (k0 + kn) * d), slice(None)
+    if ".o_proj." in name:
+        d = shape[1] // nh
+        return slice(None), slice(q0 * d, (q0 + qn) * d)
+    if name == "lm_head.weight" or ".gate_proj." in name or ".up_proj." in name:
+        n = rows // tp
         return slice(rank * n, (rank + 1) * n), slice(None)
-    if ".o_proj." in name or ".down_proj." in name:
+    if ".down_proj." in name:
         n = shape[1] // tp
         return slice(None), slice(rank * n, (rank + 1) * n)
     raise KeyError(name)

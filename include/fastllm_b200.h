@@ -81,8 +81,11 @@ typedef struct fl_config {
     float norm_eps;                    /* rms_norm_eps, or layer_norm_eps for BERT layers (embeddings LN is 1e-12) */
     double rope_theta;
     int32_t tp_rank;                   /* tensor-parallel rank / size of THIS process (1 process per GPU) */
-    int32_t tp_size;                   /* 0 or 1 => no tensor parallelism */
-    int32_t reserved[6];
+    int32_t tp_size;                   /* 0 or 1 => no tensor parallelism (Mixtral: the same two fields are the expert-parallel rank / size) */
+    int32_t ep_dp_attention;           /* Mixtral, tp_size > 1: 1 => sequences are data-parallel (every rank is called with ITS slice of the batch,
+                                          same [b, t] shape on every rank) and tokens travel to the experts and back by all-to-all;
+                                          0 => every rank is called with the whole batch (attention replicated, expert outputs all-reduced) */
+    int32_t reserved[5];
 } fl_config;
 
 /* ---- process / device -------------------------------------------------------------------------- */

@@ -41,9 +41,15 @@ def test_tp2_matches_tp1(tmp_path):
     # expert parallelism (Mixtral): EP-2 == EP-1 == golden greedy ids
     assert r1["mixtral"]["ids"] == r2["mixtral"]["ids"] == r1["mixtral"]["golden_ids"]
     assert np.abs(np.array(r1["mixtral"]["logits"]) - np.array(r2["mixtral"]["logits"])).max() < 3e-3
+    # expert parallelism with data-parallel attention + dispatch/combine all-to-all: same logits as one GPU running all 4 sequences
+    assert np.abs(np.array(r1["mixtral_dp"]) - np.array(r2["mixtral_dp"])).max() < 3e-3
     # persistent decode kernel with the in-kernel NVLink all-reduce (TP-2) against the single-GPU persistent kernel
     assert r1["wide"]["ids"] == r2["wide"]["ids"] and r1["wide"]["loop_ids"] == r2["wide"]["loop_ids"]
     assert np.abs(np.array(r1["wide"]["logits"]) - np.array(r2["wide"]["logits"])).max() < 6e-3
+    # Qwen2 with more ranks than kv heads: replicated kv head + zero-padded query heads
+    assert r1["qwen2"]["ids"] == r2["qwen2"]["ids"] == r1["qwen2"]["golden_ids"]
+    for k in ("logits", "synth_logits", "batch3"):
+        assert np.abs(np.array(r1["qwen2"][k]) - np.array(r2["qwen2"][k])).max() < 3e-3, k
     one, two = r1["mistral"], r2["mistral"]
     assert one["ids"] == two["ids"]
     assert np.abs(np.array(one["logits"]) - np.array(two["logits"])).max() < 3e-3

@@ -38,6 +38,20 @@ def gpu_main(out_path):
         p3 = np.stack([g["prompt"], g["prompt"][::-1], np.roll(g["prompt"], 3)]).astype(np.uint32)
         l3 = c3.forward(p3, 0)
         res[name] = {"ids": [int(i) for i in ids], "logits": np.stack(logits).tolist(), "synth_logits": l2[0, 0].tolist(), "batch3": l3.tolist()}
+    # tiny Qwen2 (7 q heads, 1 kv head): at TP-2 the kv head is replicated and the query group padded to 4 + 4 heads
+    cfg, w, g = golden_weights("qwen2")
+    cf = models.ConfigFile(cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers, cfg.num_attention_heads,
+                           cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, cfg.max_position_embeddings, cfg.sliding_window,
+                           tp_rank=rank, tp_size=world)
+    model, cache = models.QwenWithConfig.initialize_model(cf, w, "bf16", local)
+    ids, logits = models.Model(model, cache, eos_token_id=None).generate(g["prompt"], len(g["faithful_ids"]), return_logits=True)
+    model2, cache2 = models.QwenWithConfig.initialize_model(cf, None, "bf16", local, random_seed=int(g["seed"]), std=float(g["std"]))
+    l2 = model2.forward(np.asarray(g["prompt"], dtype=np.uint32)[None], 0, cache2)
+    c3 = models.DeviceCache(model.dev, 3, 64)
+    p3 = np.stack([g["prompt"], g["prompt"][::-1], np.roll(g["prompt"], 3)]).astype(np.uint32)
+    res["qwen2"] = {"ids": [int(i) for i in ids], "logits": np.stack(logits).tolist(), "synth_logits": l2[0, 0].tolist(),
+                    "batch3": c3.forward(p3, 0).tolist(), "golden_ids": [int(i) for i in g["faithful_ids"]]}
+    del c3, model, model2
     # true-width 2-layer Mistral-7B: batch-1 decode runs in the persistent kernel, whose all-reduce goes over NVLink peer memory
     cfw = models.ConfigFile(4096, 14336, 32000, 2, 32, 8, 1e-5, 10000.0, 256, 4096, tp_rank=rank, tp_size=world)
     mw, _ = models.MistralWithConfig.initialize_model(cfw, None, "bf16", local, random_seed=0, std=0.02)
@@ -62,6 +76,21 @@ def gpu_main(out_path):
     model, cache = models.MixtralWithConfig.initialize_model(cf, w, "bf16", local)
     ids, logits = models.Model(model, cache, eos_token_id=None).generate(g["prompt"], len(g["faithful_ids"]), return_logits=True)
     res["mixtral"] = {"ids": [int(i) for i in ids], "logits": np.stack(logits).tolist(), "golden_ids": [int(i) for i in g["faithful_ids"]]}
+    # Mixtral, expert parallelism with data-parallel attention: every rank runs ITS slice of a 4-sequence batch, tokens travel to
+    # the experts and back by all-to-all (dispatch / combine); prefill + two decode steps
+    cf_dp = replace(cf, ep_dp_attention=True)
+    mdp, _ = models.MixtralWithConfig.initialize_model(cf_dp, w, "bf16", local)
+    p4 = np.stack([np.roll(g["prompt"], k) for k in range(4)]).astype(np.uint32)
+    per = 4 // world
+    mine = p4[rank * per:(rank + 1) * per]
+    cdp = models.DeviceCache(mdp.dev, per, 64)
+    outs = [cdp.forward(mine, 0)]
+    for s_ in range(2):
+        nxt = np.array([[models.sample_argmax(r)] for r in outs[-1]], dtype=np.uint32)
+        outs.append(cdp.forward(nxt, mine.shape[1] + s_))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.stack(outs).tolist())
+    res["mixtral_dp"] = np.concatenate([np.array(x) for x in gathered], axis=1).tolist()      # [3 calls, 4 sequences, V]
     if rank == 0:
         json.dump(res, open(out_path, "w"))
     dist.barrier()
@@ -97,6 +126,31 @@ def cpu_main(out_path):
     d = cfg.head_dim
     ok = ok and ws[p + "self_attn.q_proj.weight"].shape[0] == cfg.num_attention_heads // world * d
     ok = ok and ws[p + "self_attn.k_proj.weight"].shape[0] == cfg.num_key_value_heads // world * d
+    # more ranks than kv heads (tiny Qwen2: 7 q heads, 1 kv head at TP-2 -- the Qwen2.5-7B TP-8 situation): the kv head is
+    # replicated, the query group is dealt 4 + 3 heads; attention per local head + row-parallel o_proj, all-reduced, must equal
+    # the unsharded attention block
+    qcfg, qw, _ = golden_weights("qwen2")
+    nh, nkv, dq = qcfg.num_attention_heads, qcfg.num_key_value_heads, qcfg.head_dim
+    qs = tp.shard_weights(qw, nh, nkv, rank, world)
+    q0, qn, nhl, k0, kn = tp.head_layout(nh, nkv, rank, world)
+    ok = ok and (q0, qn, nhl, k0, kn) == ((0, 4, 4, 0, 1) if rank == 0 else (4, 3, 4, 0, 1))
+    xq = np.random.default_rng(1).standard_normal((6, qcfg.hidden_size)).astype(np.float32)
+
+    def attn_block(wts, heads, kvheads):
+        q = (ops.linear(xq, wts[p + "self_attn.q_proj.weight"]) + wts[p + "self_attn.q_proj.bias"]).reshape(6, heads, dq)
+        k = (ops.linear(xq, wts[p + "self_attn.k_proj.weight"]) + wts[p + "self_attn.k_proj.bias"]).reshape(6, kvheads, dq)
+        v = (ops.linear(xq, wts[p + "self_attn.v_proj.weight"]) + wts[p + "self_attn.v_proj.bias"]).reshape(6, kvheads, dq)
+        outs = []
+        for h in range(heads):
+            kv = 0          # one kv head in this config (replicated on both ranks)
+            sc = q[:, h] @ k[:, kv].T / np.sqrt(dq)
+            sc = np.where(np.tril(np.ones((6, 6), dtype=bool)), sc, -np.inf)
+            outs.append(ops.softmax_last_dim(sc.astype(np.float32)) @ v[:, kv])
+        return ops.linear(np.concatenate(outs, axis=1).astype(np.float32), wts[p + "self_attn.o_proj.weight"])
+
+    part_a = torch.from_numpy(attn_block(qs, qn, kn))
+    dist.all_reduce(part_a)
+    ok = ok and bool(np.abs(part_a.numpy() - attn_block(qw, nh, nkv)).max() < 1e-4)
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:
