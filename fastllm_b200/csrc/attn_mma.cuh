@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_prefill_kernel(const Att
     // heaviest (latest) query tiles first: the causal range grows with the tile index
     const int qt = gridDim.x - 1 - blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
     const int n_rep = a.nh / a.nkv, kvh = head / n_rep;
+    pdl_launch_dependents();
+    pdl_wait();
     const int i0 = qt * kPrefillBM;
     const int kv_base = a.state->kv_base[seq];
     const int sw = a.sliding_window;

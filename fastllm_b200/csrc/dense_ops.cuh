@@ -45,6 +45,8 @@ struct PrepArgs {
 
 // one CTA per output row, float4-vectorised (K % 4 == 0); up to 1024 threads so a 4096-wide row is one load per thread
 static __global__ void __launch_bounds__(1024) dense_prep_kernel(const PrepArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32];
     const int orow = blockIdx.x;
     const int row = a.last_only ? (orow + 1) * a.t - 1 : orow;
@@ -114,6 +116,8 @@ struct QkvEpiArgs {
 
 // bias + RoPE (rotate-half) + q store + paged KV append; thread per column pair, grid.y = row
 static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.y;
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair * 2 >= a.nqkv) return;
@@ -153,6 +157,8 @@ static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
 // act = silu(gate) * up from the interleaved gate|up GEMM output, written directly as the hi/lo split the down GEMM reads
 static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int I, uint16_t* __restrict__ xhi,
                                                uint16_t* __restrict__ xlo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= I) return;
@@ -174,6 +180,8 @@ static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int 
 // take top_k, renormalise by their sum; route_w[row][e] = weight or 0.  One CTA per row.
 static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* __restrict__ xhi, const uint16_t* __restrict__ xlo, int H,
                                                                 const float* __restrict__ wgate, int E, int top_k, float* __restrict__ route_w) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[8];
     __shared__ float logit[64];
     const int row = blockIdx.x;
@@ -213,6 +221,8 @@ static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* 
 // moe_out[row] (=|+=) route_w[row][e] * sum over split-K slices of y[row]   (index_add of the weighted expert output)
 static __global__ void moe_accum_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int H, const float* __restrict__ route_w,
                                         int E, int e, int first, float* __restrict__ moe_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H) return;
@@ -227,6 +237,8 @@ static __global__ void moe_accum_kernel(const float* __restrict__ y, int nsl, lo
 // (also folds the split-K slices of the lm_head GEMM into the f32 logits buffer the caller reads)
 static __global__ void __launch_bounds__(256) dense_argmax_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int V,
                                                                   float* __restrict__ logits, uint32_t* __restrict__ next_ids) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sv[8];
     __shared__ int si[8];
     float* l = logits + (size_t)blockIdx.x * V;

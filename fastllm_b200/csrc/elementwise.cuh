@@ -79,10 +79,14 @@ static __global__ void advance_state_kernel(StepState* st, int b, int t, int rop
 // ---- tensor-parallel glue -------------------------------------------------------------------------------------------------
 // resid += delta (the all-reduced o_proj / down_proj output)
 static __global__ void add_rows_kernel(float* __restrict__ resid, const float* __restrict__ delta, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) resid[i] += delta[i];
 }
 // out = sum over split-K slices (fixed order)
 static __global__ void sum_slices_kernel(const float* __restrict__ y, int nsl, long long stride, int n, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < nsl; ++k) s += y[(size_t)k * stride + i];
@@ -91,6 +95,8 @@ static __global__ void sum_slices_kernel(const float* __restrict__ y, int nsl, l
 }
 // vocab-parallel logits gathered rank-major [tp][rows][Vl] -> row-major [rows][tp * Vl]
 static __global__ void tp_logits_kernel(const float* __restrict__ g, int tp, int rows, int Vl, float* __restrict__ logits) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = tp * rows * Vl;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int r = i / (rows * Vl), rem = i % (rows * Vl), row = rem / Vl, c = rem % Vl;

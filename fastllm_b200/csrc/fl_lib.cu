@@ -862,7 +862,9 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
 // ------------------------------------------------------------------------------------------------------------------
 // Dense (tcgen05) path: prefill and batched decode with 3+ activation rows
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDenseMaxSplit = 8;     // split-K slices (only when there are too few output tiles to fill the GPU)
+constexpr int kDenseMaxSplit = 16;    // upper bound on the split-K slices of a decode GEMM (see pick_ksplit)
+
+static int pick_ksplit(int tiles, int nk, int R);
 
 static void ensure_dense_ws(fl_cache& c, int rows) {
     DenseWs& d = c.dw;
@@ -878,7 +880,17 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     d.xhi.alloc(R * kmax); d.xlo.alloc(R * kmax);
     const size_t Rm = w.ep_dp ? R * (size_t)w.ep : R;        // rows the expert GEMMs see
     d.moe_rows = Rm;
-    d.y.alloc(Rm * nmax * (Rm <= 128 ? kDenseMaxSplit : 1));
+    {   // GEMM output: [ks][rows, N] for the largest N * ks over the model's GEMM shapes at this row count
+        size_t need = Rm * nmax;
+        auto consider = [&](size_t rows, size_t N, size_t K) {
+            const int ks = rows <= 128 ? pick_ksplit((int)((N + 127) / 128), (int)((K + kGemmBK - 1) / kGemmBK), (int)rows) : 1;
+            need = std::max(need, rows * N * (size_t)ks);
+        };
+        consider(R, w.nqkv, w.H); consider(R, w.H, nq); consider(R, w.V, w.H);
+        consider(Rm, 2 * (size_t)w.I, w.H); consider(Rm, w.H, w.I);
+        for (size_t r = 1; r <= std::min<size_t>(R, kMaxBatch); ++r) consider(r, w.V, w.H);     // the lm_head runs on one row per sequence
+        d.y.alloc(need);
+    }
     d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {
@@ -897,14 +909,43 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
 }
 
 template <int BN, int EPI, int DUAL>
-static void launch_gemm_tc(cudaStream_t st, int items, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g) {
+static void launch_gemm_tc(cudaStream_t st, bool pdl, int items, const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g) {
     const size_t smem = gemm_smem_bytes(BN, DUAL);
     static bool attr_set = false;
     if (!attr_set) {
         FL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    gemm_tc_kernel<BN, EPI, DUAL><<<std::min(items, kNumSMs), kGemmThreads, smem, st>>>(a, a2, b, g);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min(items, kNumSMs));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    FL_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, DUAL>, a, a2, b, g));
+}
+
+// Split-K factor of a swap-AB (decode) GEMM: the one whose work items (output tiles x k slices) fill whole waves of the 148
+// persistent CTAs best, counting the padding of the last k slice; fewer, longer items win ties (pipeline fill / epilogue per item).
+// The consumer sums the slices in a fixed order, so a row's bytes read grow with ks: capped by the row count.
+static int pick_ksplit(int tiles, int nk, int R) {
+    const int maxks = std::max(1, std::min(std::min(kDenseMaxSplit, std::max(2, 256 / std::max(R, 1))), nk / 4));
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ks = 1; ks <= maxks; ++ks) {
+        const long long items = (long long)tiles * ks;
+        const long long waves = (items + kNumSMs - 1) / kNumSMs;
+        const int nkps = (nk + ks - 1) / ks;
+        const double eff = (double)items / (double)(waves * kNumSMs) * (double)nk / (double)(ks * nkps);
+        if (eff > best_eff * 1.03) { best_eff = eff; best = ks; }
+    }
+    return best;
 }
 
 // out[ks][R, N] (f32, row stride N, slice stride R*N) = (xhi + xlo)[R, K] . W[N, K]^T; returns the number of split-K slices,
@@ -918,10 +959,10 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
     const int nk = (K + kGemmBK - 1) / kGemmBK;
     const bool swap = R <= 128;
     const int tiles = swap ? (N + 127) / 128 : ((R + kGemmBM - 1) / kGemmBM) * ((N + 127) / 128);
-    int ks = 1;
-    if (swap && tiles < 2 * kNumSMs) ks = std::max(1, std::min(std::min(nk / 4, kDenseMaxSplit), (2 * kNumSMs + tiles - 1) / tiles));
+    const int ks = swap ? pick_ksplit(tiles, nk, R) : 1;
     ProfEntry pe;
     const bool prof = g_prof.on && !lc.capturing;
+    const bool pdl = lc.pdl && !prof;
     if (prof) {
         pe.tag = tag;
         pe.bytes = (uint64_t)N * K * 2;
@@ -934,15 +975,15 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, bn), lo = make_tmap_bf16(xlo, R, K, K, bn);
         GemmArgs g{N, R, K, nullptr, nullptr, 0, out, N, ks, (long long)R * N};     // M = weight rows, N = activation rows
         switch (bn) {
-            case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
-            case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
-            case 64: launch_gemm_tc<64, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
-            default: launch_gemm_tc<128, GEPI_F32_T, DUAL_B>(lc.stream, tiles * ks, tmW, hi, lo, g); break;
+            case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+            case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+            case 64: launch_gemm_tc<64, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+            default: launch_gemm_tc<128, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
         }
     } else {
         const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, kGemmBM), lo = make_tmap_bf16(xlo, R, K, K, kGemmBM);
         GemmArgs g{R, N, K, nullptr, nullptr, 0, out, N, 1, (long long)R * N};
-        launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, tiles, hi, lo, tmW, g);
+        launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
     }
     if (prof) {
         FL_CUDA(cudaEventRecord(pe.e1, lc.stream));
@@ -958,7 +999,6 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
     const int R = b * t;
     const int nq = w.nh * w.d;
     const bool saved_pdl = lc.pdl;
-    lc.pdl = false;                       // the tcgen05 GEMMs do not take part in programmatic dependent launch
     const float qscale = (float)(1.0 / std::sqrt((double)w.d));
     const bool windowed = (w.cfg.arch != FL_ARCH_LLAMA) && w.cfg.sliding_window > 0 && t > 1;
     const size_t attn_smem = attn_smem_bytes(w.d, w.nh / w.nkv);

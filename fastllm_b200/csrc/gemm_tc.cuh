@@ -153,6 +153,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nkps = (nk + ksplit - 1) / ksplit;          // k-blocks per split
     const int ntiles = mt * nt * ksplit;                  // work items: (m tile, n tile, k split), k split fastest
 
+    // programmatic dependent launch: the next kernel's prologue may start now; our own prologue (barriers, TMEM, descriptor
+    // fetch) overlaps the previous kernel's tail.  Everything that touches dependent memory is ordered behind the producer's
+    // griddepcontrol.wait below (MMA waits for TMA, the epilogue waits for MMA).
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
@@ -175,6 +179,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            pdl_wait();
+            asm volatile("fence.proxy.async;" ::: "memory");      // the previous kernel's generic-proxy stores -> TMA reads
             uint32_t c = 0;
             for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
                 const int tile = item / ksplit, ks = item % ksplit;
