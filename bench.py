@@ -36,7 +36,10 @@ WORKLOADS = {
     "qwen25_7b_b1": ("qwen25_7b", 1, 2048, "Qwen2.5-7B bf16 decode, batch 1, 2k context"),
     "mistral7b_b64": ("mistral7b", 64, 2048, "Mistral-7B-v0.1 bf16 decode, batch 64, 2k context"),
     "minilm_256x128": ("minilm", 256, 128, "all-MiniLM-L6-v2 (BertModel) embeddings, batch 256 x seq 128"),
+    "mixtral8x7b_b32": ("mixtral8x7b", 32, 2048, "Mixtral-8x7B bf16 top-2 MoE decode, batch 32, 2k context"),
+    "qwen25_7b_prefill4k": ("qwen25_7b", 1, 4096, "Qwen2.5-7B bf16 prefill 4096 tokens (+ 256 decode steps reported beside it)"),
 }
+QWEN_PREFILL_TFLOP_4K = 56.83         # 53.46 linear + 3.37 causal attention
 MINILM_FLOP_PER_TOKEN = 22.41e6      # 2 x 10.617 M linear + 4 T H 6 attention at T = 128
 
 
@@ -272,6 +275,11 @@ def run_reference(args, rank):
     if rank != 0:
         return
     arch, batch, ctx, desc = WORKLOADS[args.workload]
+    if args.workload in ("mixtral8x7b_b32", "qwen25_7b_prefill4k"):
+        print(json.dumps({"impl": "reference", "unavailable": f"no CPU leg for workload {args.workload}: the reference does not wire Mixtral "
+                          "and a 4096-token f32 prefill of a 7B model does not fit a bounded CPU sample; the decode workloads carry the CPU baseline"}),
+              flush=True)
+        return
     v, sample, threads, n = cpu_decode_sample(oracle_config(arch), batch, ctx, args.steps, max(1, min(args.warmup, 3)), 150.0)
     line = {"impl": "reference", "metric": "decode_tokens_per_s", "value": v, "unit": "tok/s", "n_gpus": args.gpus, "steps": n,
             "warmup": args.warmup, "ms_per_step": 1000.0 * batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -285,24 +293,45 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------------
+def _setup_dist(world, local_rank):
+    import torch
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return dist
+
+
+def decode_loop_ms(cache, batch, ctx, steps, warm):
+    """Device-resident greedy decode of `steps` steps from KV length ctx -> CUDA-event ms on the library's stream."""
+    first = np.full((batch,), 5, dtype=np.uint32)
+    cache.fill_synthetic(batch, ctx)
+    cache.decode_greedy_loop(first, ctx, warm)
+    cache.fill_synthetic(batch, ctx)
+    _, ms = cache.decode_greedy_loop(first, ctx, steps)
+    return ms
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from dataclasses import replace
     from fastllm_b200 import models, presets, tp as fltp
     arch, batch, ctx, desc = WORKLOADS[args.workload]
     cls, cf = presets.PRESETS[arch]
-    dist = None
-    # Mistral / Qwen2 shard with tensor parallelism (NCCL all-reduce over NVLink, strong scaling); TinyLlama runs as
-    # independent batch-data-parallel replicas (no collective, weak scaling) -- BASELINE.json configs / SURVEY.md section 8e.
+    # Mistral / Qwen2 shard with tensor parallelism (strong scaling; batch-1 decode all-reduces over NVLink peer memory inside the
+    # persistent kernel, the dense path through NCCL); Mixtral shards its experts (expert parallelism, sequences data-parallel,
+    # dispatch / combine all-to-all); TinyLlama runs as independent batch-data-parallel replicas (no collective, weak scaling)
+    # -- BASELINE.json configs / SURVEY.md section 8e.
     use_tp = world > 1 and arch in ("mistral7b", "qwen25_7b")
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        if use_tp:
-            fltp.init_tensor_parallel(rank, world, local_rank)
-            cf = replace(cf, tp_rank=rank, tp_size=world)
-    jobs = 1 if (use_tp or world == 1) else world       # independent model instances in the job
+    use_ep = world > 1 and arch == "mixtral8x7b"
+    dist = _setup_dist(world, local_rank)
+    if use_tp or use_ep:
+        fltp.init_tensor_parallel(rank, world, local_rank)
+        cf = replace(cf, tp_rank=rank, tp_size=world, ep_dp_attention=use_ep)
+    sharded = use_tp or use_ep
+    jobs = 1 if (sharded or world == 1) else world       # independent model instances in the job
+    local_batch = batch // world if use_ep else batch    # expert parallelism: the sequences are dealt out to the ranks
 
     def barrier():
         if dist is not None:
@@ -312,15 +341,14 @@ def run_ours(args, rank, world, local_rank):
     model, _ = cls.initialize_model(cf, None, "bf16", local_rank, random_seed=0, std=0.02)
     K, W = args.steps, args.warmup
     cap = ctx + max(K, W, 16) + 8
-    cache = models.DeviceCache(model.dev, batch, cap)
-    first = np.full((batch,), 5, dtype=np.uint32)
-    launches0 = models.launch_count()
+    cache = models.DeviceCache(model.dev, local_batch, cap)
+    first = np.full((local_batch,), 5, dtype=np.uint32)
 
     # ---- device-resident decode: W warm-up steps, then exactly K timed steps -------------------------------------------
     with ClockSampler(local_rank) as clk:
-        cache.fill_synthetic(batch, ctx)
+        cache.fill_synthetic(local_batch, ctx)
         cache.decode_greedy_loop(first, ctx, W)
-        cache.fill_synthetic(batch, ctx)                      # back to KV length = ctx for the timed region
+        cache.fill_synthetic(local_batch, ctx)                # back to KV length = ctx for the timed region
         barrier()
         l0 = models.launch_count()
         t_wall0 = time.time()
@@ -336,11 +364,11 @@ def run_ours(args, rank, world, local_rank):
     value = jobs * batch * K / (ms / 1e3)
 
     # ---- end to end through the reference-facing call: host ids -> fl_forward -> host logits -> host arg-max ------------
-    cache.fill_synthetic(batch, ctx)
-    ids = first.reshape(batch, 1).copy()
+    cache.fill_synthetic(local_batch, ctx)
+    ids = first.reshape(local_batch, 1).copy()
     for s in range(min(W, 4)):
         logits = cache.forward(ids, ctx + s)
-    cache.fill_synthetic(batch, ctx)
+    cache.fill_synthetic(local_batch, ctx)
     barrier()
     t0 = time.perf_counter()
     for s in range(K):
@@ -353,13 +381,13 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e = jobs * batch * K / float(t_e.item())
 
-    if rank != 0 and not use_tp:
+    if rank != 0 and not sharded:
         barrier()
         return
 
-    # ---- roofline of the dominant kernel family (GEMV weight streaming), measured live with CUDA events ----------------
-    # (under tensor parallelism every rank runs this pass: the forward contains collectives)
-    cache.fill_synthetic(batch, ctx)
+    # ---- roofline of the dominant kernel (family), measured live with CUDA events ---------------------------------------
+    # (under tensor / expert parallelism every rank runs this pass: the forward contains collectives)
+    cache.fill_synthetic(local_batch, ctx)
     models.prof_begin()
     cache.decode_greedy_loop(first, ctx, 4)
     prof = models.prof_end()
@@ -369,6 +397,9 @@ def run_ours(args, rank, world, local_rank):
     pk = [p for p in prof if p["kernel"] == "decode_persistent"]
     if pk:      # batch-1: the whole step is ONE persistent kernel; its algorithmic bytes = streamed weights + KV read
         dom, dom_name = pk, "decode_persistent_kernel<D> (whole decode step: weight stream + attention + arg-max, 4 steps per launch here)"
+    elif any(p["kernel"].startswith("gemm_tc_") for p in prof):   # dense path: tcgen05 swap-AB weight-streaming GEMMs
+        dom = [p for p in prof if p["kernel"].startswith("gemm_tc_")]
+        dom_name = "gemm_tc_kernel<BN, F32_T, DUAL_B> family (tcgen05 swap-AB split-K weight streaming: qkv, o, gate|up / experts, down, lm_head)"
     else:       # multi-kernel path: the GEMV family dominates
         dom = [p for p in prof if p["kernel"].startswith("gemv_")]
         dom_name = "gemv_kernel<M,CPT,PRO,EPI> family (qkv+rope, o+resid, gate/up+silu, down+resid, lm_head)"
@@ -377,29 +408,42 @@ def run_ours(args, rank, world, local_rank):
     all_ms = sum(p["ms"] for p in prof)
     peak, peak_src = peaks()
     achieved = gemv_bytes / (gemv_ms / 1e3) / 1e9 if gemv_ms > 0 else 0.0
-    streamed = model.dev.streamed_bytes()                  # this rank's shard under TP
+    streamed = model.dev.streamed_bytes()                  # this rank's shard under TP / EP
     head_dim = cf.hidden_size // cf.num_attention_heads
-    kv_bytes = batch * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 2 * 2 // (world if use_tp else 1)
+    kv_bytes = local_batch * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 2 * 2 // (world if use_tp else 1)
     step_bytes = streamed + kv_bytes
     step_gbs = step_bytes / (ms / K / 1e3) / 1e9
     traffic = None
-    if pk and args.workload == "mistral7b_b1":
+    if pk and args.workload == "mistral7b_b1" and world == 1:
         per_step = ncu_traffic_per_step()
         traffic = per_step * 4 if per_step else None          # the profiled launch runs 4 steps
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dom_name,
                 "peak_source": peak_src, "kernel_share_of_step": gemv_ms / all_ms if all_ms else None,
-                "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
+                "whole_step": {"algorithmic_bytes_per_gpu": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
                                "frac_of_nominal_8tbs": step_gbs / 8000.0},
                 "per_kernel": prof}
 
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and arch != "mixtral8x7b":
         v, sample, threads, _ = cpu_decode_sample(oracle_config(arch), batch, ctx, 4, 1, 40.0)
         cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
 
     secondary = None
-    if world == 1:     # the metric's second half (BASELINE.json: "MiniLM embeddings/s"), measured in the same run
+    sweep = None
+    if world == 1 and args.workload == "mistral7b_b1":
+        # the rest of the headline metric (BASELINE.json: "Mistral-7B bs=1..64; MiniLM embeddings/s"), measured in the same run
+        sweep = []
+        try:
+            for bb in (8, 64):
+                cb = models.DeviceCache(model.dev, bb, ctx + 80)
+                msb = decode_loop_ms(cb, bb, ctx, 64, 4) / 64
+                by = streamed + bb * ctx * cf.num_hidden_layers * cf.num_key_value_heads * head_dim * 4
+                sweep.append({"batch": bb, "context": ctx, "value": bb / (msb / 1e3), "unit": "tok/s", "ms_per_step": msb,
+                              "algorithmic_bytes": by, "achieved_gbs": by / (msb / 1e3) / 1e9, "hbm_frac": by / (msb / 1e3) / 1e9 / peak})
+                del cb
+        except Exception as ex:
+            sweep.append({"error": str(ex)})
         try:
             r = minilm_measure(local_rank, 256, 128, 20, 5)
             secondary = {"metric": "embeddings_per_s", "workload": WORKLOADS["minilm_256x128"][3], "value": 256 / (r["ms"] / 1e3),
@@ -407,16 +451,98 @@ def run_ours(args, rank, world, local_rank):
                          "tensor_tflops": MINILM_FLOP_PER_TOKEN * 256 * 128 / (r["ms"] / 1e3) / 1e12}
         except Exception as ex:   # never lose the headline line over the secondary one
             secondary = {"error": str(ex)}
+    if world == 1:
+        par = "single GPU"
+    elif use_tp:
+        par = (f"tp{world}: column/row tensor parallel; batch-1 decode all-reduces (x2 per layer) over NVLink peer memory inside the "
+               f"persistent kernel, vocab-parallel logits / arg-max exchange")
+    elif use_ep:
+        par = (f"ep{world}: {cf.num_local_experts // world} expert(s) per GPU, {local_batch} sequences per GPU (attention data-parallel), "
+               f"dispatch + combine all-to-all per layer (grouped ncclSend/Recv)")
+    else:
+        par = f"{world} independent replicas (batch-data-parallel)"
     line = {"metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if use_tp else "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": desc, "batch": batch, "context": ctx, "l2": "inputs larger than L2 (weights streamed once per step)",
-                       "parallelism": "single GPU" if world == 1 else (f"tp{world}: column/row tensor parallel, NCCL all-reduce x2 per layer + vocab-parallel all-gather"
-                                                                       if use_tp else f"{world} independent replicas (batch-data-parallel)"),
-                       "kv_cache": "bf16 paged, synthetic prefill", "weights": "synthetic N(0,0.02^2)-like bf16, seed 0"},
+                       "parallelism": par, "kv_cache": "bf16 paged, synthetic prefill", "weights": "synthetic N(0,0.02^2)-like bf16, seed 0"},
             "clocks": clk.summary(t_wall0, t_wall1),
-            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": int(batch * 4), "d2h_bytes_per_step": int(batch * cf.vocab_size * 4)},
-            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}
+            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": int(local_batch * 4), "d2h_bytes_per_step": int(local_batch * cf.vocab_size * 4)},
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "batch_sweep": sweep}
+    print(json.dumps(line), flush=True)
+    barrier()
+
+
+def run_prefill(args, rank, world, local_rank):
+    """Qwen2.5-7B: a "step" is one 4096-token prefill from an empty cache (tensor-core bound); the 256 decode steps that follow
+    in BASELINE.json's config are timed once and reported beside it."""
+    import torch
+    from dataclasses import replace
+    from fastllm_b200 import models, presets, tp as fltp
+    arch, batch, T, desc = WORKLOADS[args.workload]
+    cls, cf = presets.PRESETS[arch]
+    dist = _setup_dist(world, local_rank)
+    if world > 1:
+        fltp.init_tensor_parallel(rank, world, local_rank)
+        cf = replace(cf, tp_rank=rank, tp_size=world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model, _ = cls.initialize_model(cf, None, "bf16", local_rank, random_seed=0, std=0.02)
+    K, W = min(args.steps, 16), min(args.warmup, 3)
+    ids = (np.arange(T, dtype=np.uint64) * 7919 % 150000 + 3).astype(np.uint32)[None]
+    cache = models.DeviceCache(model.dev, 1, T + 264)
+    with ClockSampler(local_rank) as clk:
+        for _ in range(W):
+            cache.reset(); cache.forward_greedy(ids, 0)
+        barrier()
+        l0 = models.launch_count()
+        t_wall0 = time.time()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            cache.reset()
+            nxt = cache.forward_greedy(ids, 0)                  # host ids in (H2D 16 KB), next id out (D2H): the e2e call IS the step
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / K
+        barrier()
+        t_wall1 = time.time()
+        launches = models.launch_count() - l0
+        _, dec_ms = cache.decode_greedy_loop(nxt, T, 256)
+        time.sleep(0.12)
+    tt = torch.tensor([dt, dec_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt, dec_ms = float(tt[0]), float(tt[1])
+    cache.reset()
+    models.prof_begin(); cache.forward_greedy(ids, 0); prof = models.prof_end()
+    if rank != 0:
+        barrier()
+        return
+    dev_ms = sum(p["ms"] for p in prof)
+    gemm_ms = sum(p["ms"] for p in prof if p["kernel"].startswith("gemm_tc_"))
+    peak, src = peaks("tensor")
+    tflop = QWEN_PREFILL_TFLOP_4K * T / 4096
+    lin_tflop = 53.46 * T / 4096
+    line = {"metric": "prefill_tokens_per_s", "value": T / dt, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "batch": 1, "prompt_tokens": T, "l2": "weights (14 GB) and activations exceed L2",
+                       "parallelism": "single GPU" if world == 1 else f"tp{world}: column/row tensor parallel, NCCL all-reduce x2 per layer",
+                       "weights": "synthetic N(0,0.02^2)-like bf16, seed 0"},
+            "clocks": clk.summary(t_wall0, t_wall1),
+            "e2e": {"value": T / dt, "unit": "tok/s", "h2d_bytes_per_step": int(T * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": lin_tflop / world / (gemm_ms / 1e3), "peak": peak, "unit": "TFLOP/s",
+                         "frac": lin_tflop / world / (gemm_ms / 1e3) / peak, "traffic": None,
+                         "kernel": "gemm_tc_kernel<128, F32, DUAL_A> (tcgen05 prefill GEMMs; algorithmic linear FLOPs per GPU / their CUDA-event time; "
+                                   "the hi/lo activation split issues 2x these FLOPs on the tensor pipe)",
+                         "peak_source": src, "kernel_share_of_step": gemm_ms / dev_ms if dev_ms else None,
+                         "whole_step": {"algorithmic_tflop": tflop, "achieved_tflops_per_gpu": tflop / world / dt, "frac": tflop / world / dt / peak},
+                         "per_kernel": prof},
+            "decode_after_prefill": {"steps": 256, "ms_per_step": dec_ms / 256, "tok_per_s": 256 / (dec_ms / 1e3)},
+            "cpu_baseline": None}
     print(json.dumps(line), flush=True)
     barrier()
 
@@ -452,6 +578,8 @@ def main():
         g.build()
     if args.workload == "minilm_256x128":
         run_minilm(args, rank, world, local_rank)
+    elif args.workload == "qwen25_7b_prefill4k":
+        run_prefill(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

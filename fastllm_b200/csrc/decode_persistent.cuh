@@ -139,6 +139,30 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
+// L2 eviction-priority hints for the weight stream.  Weights are read exactly once per step, and the L2 lookahead cursor runs
+// ahead of the demand loads: under the default (LRU-like) policy the OLDEST lines in L2 are the prefetched-but-not-yet-consumed
+// ones, so a deep lookahead evicts exactly the lines it is about to need (measured: 512 KB/CTA lookahead = 1.5x the HBM traffic).
+// Demand loads therefore carry evict_first (the line is dead once it is in shared memory) and prefetches evict_last.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk_hint(const void* gsrc, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(gsrc), "r"(bytes), "l"(policy) : "memory");
+}
+
 // Weight matrix of global phase g of a step: g = 4*layer + {0:qkv, 1:o, 2:gate|up, 3:down}, g = 4*L: lm_head.
 __device__ __forceinline__ void pk_phase(const PkArgs& a, int g, const uint16_t*& W, int& N, int& K) {
     if (g == 4 * a.L) { W = a.lm_head; N = a.V; K = a.H; return; }
@@ -266,22 +290,27 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         ld.init(a, cta, ncta);
         pf.init(a, cta, ncta);
         int ahead = 0;
+        const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+        const bool hint_ld = (a.flags & 2) != 0, hint_pf = (a.flags & 4) != 0;
         while (ld.valid) {
             while (pf.valid && ahead < a.lookahead_bytes) {
                 const uint16_t* src;
                 uint32_t bytes;
                 pf.get(src, bytes);
-                prefetch_l2_bulk(src, bytes);
+                if (hint_pf) prefetch_l2_bulk_hint(src, bytes, pol_last);
+                else prefetch_l2_bulk(src, bytes);
                 ahead += (int)bytes;
                 pf.advance(a, cta, ncta);
             }
             const uint16_t* src;
             uint32_t bytes;
             ld.get(src, bytes);
+            if (a.flags & 8) src = ld.W + (size_t)ld.s.row_begin * ld.K;   // DEV experiment: always this CTA's first chunk (L2-resident): consumer-bound rate
             const int st = c % NS;
             mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
             mbar_expect_tx(&full[st], bytes);
-            bulk_g2s(ring + (size_t)st * kPkStageBytes, src, bytes, &full[st]);
+            if (hint_ld) bulk_g2s_hint(ring + (size_t)st * kPkStageBytes, src, bytes, &full[st], pol_first);
+            else bulk_g2s(ring + (size_t)st * kPkStageBytes, src, bytes, &full[st]);
             ahead -= (int)bytes;
             ld.advance(a, cta, ncta);
             ++c;
