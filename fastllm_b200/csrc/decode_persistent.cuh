@@ -8,9 +8,14 @@
 //     shared-memory stages full with cp.async.bulk (TMA engine) + mbarrier.  The stream is decoupled from the compute
 //     phases: while consumers sit in a grid barrier, an epilogue or the attention phase, the ring is already filling with
 //     the NEXT phase's weights, so HBM keeps streaming across phase boundaries.
-//   * consumers: per chunk, all 8 warps sweep each staged row (LDS.128 weights, f32 activations from shared memory,
-//     f32 FMA), warp-shuffle reduce, per-warp partials in shared memory, one cross-warp sum per phase followed by the
-//     same fused epilogues as gemv.cuh (RMSNorm prologue; bias+RoPE+KV append; residual add; SiLU*up; logits+arg-max).
+//   * consumers: a chunk is a 16-row x 1024-column block of the weight matrix: ONE 3-D TMA request that lands as
+//     [column block][row][128 B] with the 128-byte swizzle keyed by the row (bank-conflict-free ldmatrix).  The 8 warps split its 64 k-steps; each k-step is ONE mma.sync m16n8k16: A = the bf16 weight tile
+//     straight from shared memory (ldmatrix, no unpack instructions), B = the activation vector split hi + lo into two bf16
+//     columns (~16 mantissa bits, products exact, f32 accumulate), so y[row] = D[row][0] + D[row][1] falls out of the
+//     accumulator fragment without a single shuffle.  ~35 instructions per warp per 32 KB chunk (the CUDA-core version
+//     needed ~170 and was the bottleneck: measured 1030 clk/chunk against the 770 clk/chunk the L2 can deliver).
+//     Per-warp partials land in shared memory, one cross-warp sum per phase, then the same fused epilogues as gemv.cuh
+//     (RMSNorm prologue; bias+RoPE+KV append; residual add; SiLU*up; logits+arg-max).
 //   * phases of a layer are separated by a grid barrier (monotonic atomic counter, release/acquire fences); data that
 //     crosses CTAs is read with ld.global.cg (L2) because L1 is not coherent across SMs.
 //   * attention: split-K over the sequence, (kv_head, split) items spread over the CTAs, K/V read straight from the paged
@@ -20,15 +25,21 @@
 #pragma once
 #include "attn_decode.cuh"
 #include "common.cuh"
+#include "dense_ops.cuh"
+#include "gemm_tc.cuh"
 #include "gemv.cuh"
+#include "mma.cuh"
 
 namespace fl {
 
 constexpr int kPkConsumerWarps = 8;
 constexpr int kPkConsumers = kPkConsumerWarps * 32;
 constexpr int kPkThreads = kPkConsumers + 32;
-constexpr int kPkStageBytes = 32768;
+constexpr int kPkBlockRows = 16;                       // rows per chunk = M of the MMA
+constexpr int kPkChunkCols = 1024;                     // columns per chunk
+constexpr int kPkStageBytes = kPkBlockRows * kPkChunkCols * 2;     // 32 KB: ONE 3-D TMA request (see make_tmap_pk)
 constexpr int kPkMaxStages = 6;
+constexpr int kPkMaxNormK = 8192;                      // RMSNorm prologue keeps the row in registers (hidden size limit)
 
 struct PkLayer {
     const uint16_t* wqkv;
@@ -57,7 +68,9 @@ struct PkArgs {
     StepState* state;
     float* resid;      // [H]
     float* q;          // [nh*d]
-    float* attn_out;   // [nh*d]
+    float* attn_out;   // [nh*d]   (unused by this kernel since the hi/lo hand-over below)
+    uint16_t* xhl;     // hi/lo bf16 hand-over of the two plain activation vectors, written by their producers so the consumers'
+                       // x-load is a straight copy: attn hi [nq] | attn lo [nq] | act hi [I] | act lo [I]
     float* act;        // [I]
     float* logits;     // [V]
     float* part_acc;   // [nh, nsplit, d]
@@ -73,7 +86,9 @@ struct PkArgs {
     unsigned int* gbar;   // grid-barrier counter, zero at launch
     int nsteps, feedback;
     int nstages;
-    int xs_floats;        // shared-memory activation vector capacity (floats)
+    int xs_floats;        // shared-memory activation / scratch region capacity (floats)
+    int kcap;             // largest K of any phase rounded up to whole chunks (x_hi at xs, x_lo at xs + (kcap + 8) bf16)
+    const CUtensorMap* tmaps;   // [4 L + 1] weight-stream descriptors, indexed by the phase id g
     int partial_rows;     // rows of the per-warp partial buffer
     // ---- tensor parallelism inside the kernel: all-reduce over NVLink peer memory (no NCCL call, no extra launch) ----
     int tp, rank;                    // tp == 1: single GPU
@@ -90,34 +105,22 @@ struct PkArgs {
 
 // ---- chunk schedule shared by producer and consumers --------------------------------------------------------------
 struct PkSlice {
-    int row_begin, row_end;   // even-aligned row range of this CTA
-    int rpc;                  // rows per chunk (row fits in a stage)
-    int nseg;                 // >1: a row is cut into nseg segments of seg_pieces 16-byte pieces
-    int seg_pieces;
-    int K8;
+    int row_begin, row_end;   // 8-aligned row range of this CTA
+    int nblocks;              // 16-row blocks (the last one may hold 8 rows)
+    int ncc;                  // column chunks per block
     int nchunks;
+    int K;
 };
 
 __device__ __forceinline__ PkSlice pk_slice(int N, int K, int cta, int ncta) {
     PkSlice s;
-    const int npairs = N >> 1;
-    s.row_begin = 2 * (int)((long long)npairs * cta / ncta);
-    s.row_end = 2 * (int)((long long)npairs * (cta + 1) / ncta);
-    s.K8 = K >> 3;
-    const int rowbytes = K * 2;
-    const int rows = s.row_end - s.row_begin;
-    if (rowbytes <= kPkStageBytes) {
-        const int fit = kPkStageBytes / rowbytes;
-        s.rpc = fit >= 8 ? 8 : (fit >= 4 ? 4 : (fit >= 2 ? 2 : 1));   // power of two: 8 / rpc warps share one row
-        s.nseg = 1;
-        s.seg_pieces = s.K8;
-        s.nchunks = (rows + s.rpc - 1) / s.rpc;
-    } else {
-        s.rpc = 1;
-        s.nseg = (rowbytes + kPkStageBytes - 1) / kPkStageBytes;
-        s.seg_pieces = (s.K8 + s.nseg - 1) / s.nseg;
-        s.nchunks = rows * s.nseg;
-    }
+    const int units = N >> 3;
+    s.row_begin = 8 * (int)((long long)units * cta / ncta);
+    s.row_end = 8 * (int)((long long)units * (cta + 1) / ncta);
+    s.nblocks = (s.row_end - s.row_begin + kPkBlockRows - 1) / kPkBlockRows;
+    s.ncc = (K + kPkChunkCols - 1) / kPkChunkCols;
+    s.nchunks = s.nblocks * s.ncc;
+    s.K = K;
     return s;
 }
 
@@ -193,19 +196,11 @@ struct PkCursor {
         }
     }
     __device__ void init(const PkArgs& a, int cta, int ncta) { step = 0; g = 0; enter(a, cta, ncta); }
-    __device__ void get(const uint16_t*& src, uint32_t& bytes) const {
-        if (s.nseg == 1) {
-            const int r0 = s.row_begin + i * s.rpc;
-            const int nr = min(s.rpc, s.row_end - r0);
-            src = W + (size_t)r0 * K;
-            bytes = (uint32_t)nr * K * 2;
-        } else {
-            const int r = s.row_begin + i / s.nseg, seg = i % s.nseg;
-            const int p0 = seg * s.seg_pieces;
-            const int np = min(s.seg_pieces, s.K8 - p0);
-            src = W + (size_t)r * K + (size_t)p0 * 8;
-            bytes = (uint32_t)np * 16;
-        }
+    // chunk i = (block i / ncc, column chunk i % ncc) -> TMA coordinates (first row, first 64-column block)
+    __device__ void get(int& row0, int& kb0) const {
+        const int blk = i / s.ncc, cc = i - blk * s.ncc;
+        row0 = s.row_begin + blk * kPkBlockRows;
+        kb0 = cc * (kPkChunkCols / 64);
     }
     __device__ void advance(const PkArgs& a, int cta, int ncta) {
         if (++i < s.nchunks) return;
@@ -262,6 +257,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     int* s_flag = reinterpret_cast<int*>(lrun + 8);
     __shared__ __align__(8) uint64_t full[kPkMaxStages];
     __shared__ __align__(8) uint64_t empty[kPkMaxStages];
+    __shared__ __align__(16) uint16_t zero16[8];      // the all-zero columns of the MMA B operand
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, ncta = gridDim.x;
@@ -275,6 +271,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         }
         mbar_fence_init();
     }
+    if (tid < 8) zero16[tid] = 0;
     __syncthreads();
 
     // =================================================================================================================
@@ -283,35 +280,35 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     if (warp == kPkConsumerWarps) {
         if (lane != 0) return;
         // Two cursors over the same schedule: `ld` feeds the shared-memory ring, `pf` runs up to lookahead_bytes ahead of
-        // it issuing L2 prefetches, so HBM keeps streaming into the 126 MB L2 while the ring is full and the consumers
-        // are busy with an epilogue, a grid barrier or the attention phase; the ring then refills at L2 speed.
+        // it issuing L2 prefetches so the ring refills at L2 latency after a compute gap.
         unsigned int c = 0;   // running chunk counter -> stage = c % NS, use = c / NS
         PkCursor ld, pf;
         ld.init(a, cta, ncta);
         pf.init(a, cta, ncta);
         int ahead = 0;
-        const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
-        const bool hint_ld = (a.flags & 2) != 0, hint_pf = (a.flags & 4) != 0;
+        const uint64_t pol_first = l2_policy_evict_first();
         while (ld.valid) {
             while (pf.valid && ahead < a.lookahead_bytes) {
-                const uint16_t* src;
-                uint32_t bytes;
-                pf.get(src, bytes);
-                if (hint_pf) prefetch_l2_bulk_hint(src, bytes, pol_last);
-                else prefetch_l2_bulk(src, bytes);
-                ahead += (int)bytes;
+                int row0, kb0;
+                pf.get(row0, kb0);
+                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(a.tmaps + pf.g), "r"(0), "r"(row0), "r"(kb0)
+                             : "memory");
+                ahead += kPkStageBytes;
                 pf.advance(a, cta, ncta);
             }
-            const uint16_t* src;
-            uint32_t bytes;
-            ld.get(src, bytes);
-            if (a.flags & 8) src = ld.W + (size_t)ld.s.row_begin * ld.K;   // DEV experiment: always this CTA's first chunk (L2-resident): consumer-bound rate
+            int row0, kb0;
+            ld.get(row0, kb0);
+            if (a.flags & 8) { row0 = ld.s.row_begin; kb0 = 0; }   // DEV experiment: always this CTA's first chunk (L2-resident)
             const int st = c % NS;
             mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
-            mbar_expect_tx(&full[st], bytes);
-            if (hint_ld) bulk_g2s_hint(ring + (size_t)st * kPkStageBytes, src, bytes, &full[st], pol_first);
-            else bulk_g2s(ring + (size_t)st * kPkStageBytes, src, bytes, &full[st]);
-            ahead -= (int)bytes;
+            mbar_expect_tx(&full[st], kPkStageBytes);      // the whole box always arrives (out-of-range parts as zeros)
+            // weights are dead once staged: evict_first keeps the L2 for the lookahead and the KV cache
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                    smem_u32(ring + (size_t)st * kPkStageBytes)),
+                "l"(a.tmaps + ld.g), "r"(0), "r"(row0), "r"(kb0), "r"(smem_u32(&full[st])), "l"(pol_first)
+                : "memory");
+            ahead -= kPkStageBytes;
             ld.advance(a, cta, ncta);
             ++c;
         }
@@ -324,105 +321,75 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     unsigned int c = 0;       // chunk counter, in lock-step with the producer's
     unsigned int epoch = 0;   // grid-barrier epoch
 
-    // y = W_slice . xs for this CTA's rows.  Within a chunk every warp owns ONE contiguous piece range of ONE row
-    // (8 / rpc warps share a row), so there is a single warp-shuffle reduction per warp per 32 KB chunk; the per-warp
-    // partial sums land in partial[(row - row_begin) * 8 + slot] and are added up in the phase epilogue.
-    auto dot_range = [&](const uint4* wrow, const float4* xlo, const float4* xhi, int lo, int hi) {
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        int p = lo + lane;
-        for (; p + 96 < hi; p += 128) {
-            const uint4 w0 = wrow[p], w1 = wrow[p + 32], w2 = wrow[p + 64], w3 = wrow[p + 96];
-            const float4 a0 = xlo[p], b0 = xhi[p], a1 = xlo[p + 32], b1 = xhi[p + 32];
-            const float4 a2 = xlo[p + 64], b2 = xhi[p + 64], a3 = xlo[p + 96], b3 = xhi[p + 96];
-            const float x0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-            const float x1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
-            const float x2[8] = {a2.x, a2.y, a2.z, a2.w, b2.x, b2.y, b2.z, b2.w};
-            const float x3[8] = {a3.x, a3.y, a3.z, a3.w, b3.x, b3.y, b3.z, b3.w};
-            acc0 = dot8(w0, x0, acc0);
-            acc1 = dot8(w1, x1, acc1);
-            acc2 = dot8(w2, x2, acc2);
-            acc3 = dot8(w3, x3, acc3);
-        }
-        for (; p < hi; p += 32) {
-            const uint4 w0 = wrow[p];
-            const float4 a0 = xlo[p], b0 = xhi[p];
-            const float x0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-            acc0 = dot8(w0, x0, acc0);
-        }
-        return warp_sum((acc0 + acc1) + (acc2 + acc3));
-    };
+    // activation vector of the current phase as two bf16 vectors (x = hi + lo), the B operand of the MMAs
+    uint16_t* xh = reinterpret_cast<uint16_t*>(xs);
+    uint16_t* xl = xh + a.kcap + 8;          // +16 bytes: x_hi[k] and x_lo[k] sit in different bank groups
+    const int g = lane >> 2, tq = lane & 3;
+
+    // y = W_slice . x for this CTA's rows.  Chunk = 16 rows x <= 1024 columns; warp w takes k-steps w, w+8, ...; the f32
+    // accumulator fragment lives in registers across the column chunks of a row block, and at the block's last chunk the
+    // lanes with tq == 0 hold y[row g] = D[g][0] + D[g][1] (hi + lo column) and y[row g+8]: no shuffles.  Per-warp partial
+    // sums land in partial[(row - row_begin) * 8 + warp] and are added up in the phase epilogue.
+    long long dbg_wait = 0;
+    int dbg_layer = -1, dbg_phase = 0;
     auto consume = [&](int N, int K) -> PkSlice {
         const PkSlice s = pk_slice(N, K, cta, ncta);
-        const float4* xs4 = reinterpret_cast<const float4*>(xs);
-        if (s.nseg == 1) {
-            // Register-resident activations: within a phase a lane always multiplies the same <= 8 column pieces
-            // (p = lo + lane + 32 j; rpc is chosen so that a warp's share of a row is <= 256 pieces), so its slice of x
-            // is loaded from shared memory ONCE per phase; the streaming loop is then 1 LDS.128 (weights) + 8 unpack +
-            // 8 FMA per 16 bytes -- a third of the shared-memory traffic of reading x per piece.
-            constexpr int XR = 8;
-            const int wpr = kPkConsumerWarps / s.rpc;            // warps per row
-            const int my_row = warp / wpr, sub = warp % wpr;
-            const int per = (s.K8 + wpr - 1) / wpr;
-            const int lo = sub * per, hi = min(lo + per, s.K8);
-            float xr[XR][8];
+        dbg_wait = 0;
+        // ldmatrix row addresses of this lane: A = weight tile rows (lane & 15), +8 columns for lanes 16-31;
+        // B = [n = lane & 7][8 consecutive k]: n == 0 -> x_hi, n == 1 -> x_lo, other n -> zeros; lanes 8-15 take k + 8
+        // staged tile: [column block kb][row r][128 B], 16-byte piece p of a row stored at p ^ (r & 7) (TMA SWIZZLE_128B).
+        // k-step ks = warp + 8 j covers pieces 2 (ks & 3) + {0, 1} of column block ks >> 2, so for a given lane the piece is
+        // the same for every j and the k-steps of a warp are 4096 bytes apart.
+        const int ar = lane & 15;
+        const uint32_t a_off = (uint32_t)(warp >> 2) * 2048u + (uint32_t)ar * 128u + (uint32_t)(((((warp & 3) << 1) | (lane >> 4)) ^ (ar & 7)) << 4);
+        const int bn = lane & 7, bk = ((lane >> 3) & 1) * 8;
+        const uint16_t* xrow = bn == 0 ? xh : (bn == 1 ? xl : zero16);
+        const int xmul = bn < 2 ? 1 : 0;          // the zero rows always read the same 16 bytes
+        float acc[2][4];
+        int i = 0;
+        for (int blk = 0; blk < s.nblocks; ++blk) {
 #pragma unroll
-            for (int j = 0; j < XR; ++j) {
-                const int p = lo + lane + 32 * j;
-                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0;
-                if (p < hi) { a0 = xs4[p]; b0 = xs4[s.K8 + p]; }
-                xr[j][0] = a0.x; xr[j][1] = a0.y; xr[j][2] = a0.z; xr[j][3] = a0.w;
-                xr[j][4] = b0.x; xr[j][5] = b0.y; xr[j][6] = b0.z; xr[j][7] = b0.w;
-            }
-            for (int i = 0; i < s.nchunks; ++i, ++c) {
+            for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = 0.f;
+            for (int cc = 0; cc < s.ncc; ++cc, ++i, ++c) {
                 const int st = c % NS;
+                const long long tw0 = a.dbg ? clock64() : 0;
                 mbar_wait(&full[st], (c / NS) & 1);
-                const int r0 = s.row_begin + i * s.rpc;
-                const int nr = min(s.rpc, s.row_end - r0);
-                if (my_row < nr) {
-                    const uint4* wrow = reinterpret_cast<const uint4*>(ring + (size_t)st * kPkStageBytes + (size_t)my_row * K * 2);
-                    uint4 wv[XR];
+                if (a.dbg) dbg_wait += clock64() - tw0;
+                const uint8_t* tile = ring + (size_t)st * kPkStageBytes + a_off;
+                const int col0 = cc * kPkChunkCols;
+                // all fragment loads of the chunk first (independent, in flight together), then the MMAs (two accumulator chains)
+                constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
+                const uint16_t* xcol = xrow + (size_t)xmul * (col0 + bk + warp * 16);
 #pragma unroll
-                    for (int j = 0; j < XR; ++j) {
-                        const int p = lo + lane + 32 * j;
-                        wv[j] = (p < hi) ? wrow[p] : make_uint4(0u, 0u, 0u, 0u);
+                for (int h = 0; h < KPW; h += 4) {
+                    uint32_t af[4][4], bf[4][2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ldmatrix_x4(af[j], tile + (h + j) * 4096);
+                        ldmatrix_x2(bf[j], xcol + (size_t)xmul * ((h + j) * kPkConsumerWarps * 16));
                     }
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < XR; ++j) acc[j & 3] = dot8(wv[j], xr[j], acc[j & 3]);
-                    const float v = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
-                    if (lane == 0) partial[(size_t)(r0 + my_row - s.row_begin) * kPkConsumerWarps + sub] = v;
+                    for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j & 1], af[j], bf[j]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[st]);
             }
-        } else {
-            // rows longer than a stage (e.g. Qwen2.5 down_proj, K = 18944): each chunk is a row segment swept by all warps
-            for (int i = 0; i < s.nchunks; ++i, ++c) {
-                const int st = c % NS;
-                mbar_wait(&full[st], (c / NS) & 1);
-                const int r = s.row_begin + i / s.nseg, seg = i % s.nseg;
-                const int p0 = seg * s.seg_pieces;
-                const int np = min(s.seg_pieces, s.K8 - p0);
-                const int sper = (np + kPkConsumerWarps - 1) / kPkConsumerWarps;
-                const int slo = warp * sper, shi = min(slo + sper, np);
-                const float v = dot_range(reinterpret_cast<const uint4*>(ring + (size_t)st * kPkStageBytes), xs4 + p0, xs4 + s.K8 + p0, slo, shi);
-                if (lane == 0) {
-                    float* dst = &partial[(size_t)(r - s.row_begin) * kPkConsumerWarps + warp];
-                    *dst = (seg == 0) ? v : (*dst + v);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
+            if (tq == 0) {
+                float* pr = partial + (size_t)(blk * kPkBlockRows + g) * kPkConsumerWarps + warp;
+                pr[0] = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
+                pr[8 * kPkConsumerWarps] = (acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3]);
             }
         }
+        if (a.dbg != nullptr && cta == 0 && tid == 0 && dbg_layer == a.L / 2) a.dbg[32 + (dbg_phase++ & 3)] = dbg_wait * 1000 + s.nchunks;
         pk_named_sync();   // partial[] complete
         return s;
     };
-    // sum of the per-warp partials of one row (slots actually written: 8 / rpc, or all 8 for segmented rows)
+    // sum of the 8 per-warp partials of one row
     auto row_sum = [&](const PkSlice& s, int local_row) {
         const float* pr = partial + (size_t)local_row * kPkConsumerWarps;
-        const int nslot = (s.nseg == 1) ? kPkConsumerWarps / s.rpc : kPkConsumerWarps;
         float v = pr[0];
-        for (int k = 1; k < nslot; ++k) v += pr[k];
+#pragma unroll
+        for (int k = 1; k < kPkConsumerWarps; ++k) v += pr[k];
         return v;
     };
     // Row-parallel epilogue under tensor parallelism: resid[slice] += sum over ranks of this rank-local partial output.
@@ -469,36 +436,69 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         pk_named_sync();
         return s;
     };
-    // xs = rms_norm(src) * norm_w      (candle_nn::ops::rms_norm, as in gemv.cuh)
-    // xs = rms_norm(src) * norm_w      (candle_nn::ops::rms_norm, as in gemv.cuh)
+    // x = hi + lo with two packed conversions per pair (cvt.rn.bf16x2.f32: the same round-to-nearest-even as split_hi_lo)
+    auto split2 = [](float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+        hi2 = pack_bf16x2(x0, x1);
+        lo2 = pack_bf16x2(x0 - bf16lo(hi2), x1 - bf16hi(hi2));
+    };
+    auto store_x4 = [&](int i, const float4& v) {      // x[4i .. 4i+3] -> hi / lo bf16
+        uint32_t h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0);
+        split2(v.z, v.w, h1, l1);
+        reinterpret_cast<uint2*>(xh)[i] = make_uint2(h0, h1);
+        reinterpret_cast<uint2*>(xl)[i] = make_uint2(l0, l1);
+    };
+    auto zero_x_tail = [&](int K) {     // columns [K, next multiple of 1024): the weight side is zero-filled, x must be finite
+        const int kpad = (K + kPkChunkCols - 1) / kPkChunkCols * kPkChunkCols;
+        for (int i = K / 4 + tid; i < kpad / 4; i += kPkConsumers) {
+            reinterpret_cast<uint2*>(xh)[i] = make_uint2(0u, 0u);
+            reinterpret_cast<uint2*>(xl)[i] = make_uint2(0u, 0u);
+        }
+    };
+    // x = rms_norm(src) * norm_w      (candle_nn::ops::rms_norm, as in gemv.cuh); the row stays in registers between the passes
     auto load_x_rmsnorm = [&](const float* src, bool src_is_embed_row, const uint16_t* erow, const float* norm_w, int K,
                               float* resid_out) {
+        constexpr int NV = kPkMaxNormK / 4 / kPkConsumers;      // float4 per thread
+        float4 v[NV];
         float ss = 0.f;
-        for (int i = tid; i < K / 4; i += kPkConsumers) {
-            float4 v;
-            if (src_is_embed_row) {
-                const uint2 e = __ldg(reinterpret_cast<const uint2*>(erow) + i);
-                v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
-                if (resid_out) reinterpret_cast<float4*>(resid_out)[i] = v;
-            } else {
-                v = __ldcg(reinterpret_cast<const float4*>(src) + i);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = tid + j * kPkConsumers;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < K / 4) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(norm_w) + i));
+                if (src_is_embed_row) {
+                    const uint2 e = __ldg(reinterpret_cast<const uint2*>(erow) + i);
+                    v[j] = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
+                    if (resid_out) reinterpret_cast<float4*>(resid_out)[i] = v[j];
+                } else {
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+                }
+                ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
             }
-            reinterpret_cast<float4*>(xs)[(i & 1) * (K >> 3) + (i >> 1)] = v;   // [half][chunk][4]: conflict-free LDS.128
-            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
         }
         const float tot = block_sum(ss);
         const float m = sqrtf(tot / (float)K + a.eps);
-        for (int i = tid; i < K / 4; i += kPkConsumers) {
-            float4 v = reinterpret_cast<float4*>(xs)[(i & 1) * (K >> 3) + (i >> 1)];
-            const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w) + i);
-            v.x = v.x / m * w.x; v.y = v.y / m * w.y; v.z = v.z / m * w.z; v.w = v.w / m * w.w;
-            reinterpret_cast<float4*>(xs)[(i & 1) * (K >> 3) + (i >> 1)] = v;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = tid + j * kPkConsumers;
+            if (i < K / 4) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(norm_w) + i);
+                store_x4(i, make_float4(v[j].x / m * wv.x, v[j].y / m * wv.y, v[j].z / m * wv.z, v[j].w / m * wv.w));
+            }
         }
+        zero_x_tail(K);
         pk_named_sync();
     };
-    auto load_x_plain = [&](const float* src, int K) {
-        for (int i = tid; i < K / 4; i += kPkConsumers)
-            reinterpret_cast<float4*>(xs)[(i & 1) * (K >> 3) + (i >> 1)] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+    // plain activation vectors arrive already split (written hi | lo by their producers): a straight L2 -> shared copy
+    auto load_x_plain = [&](const uint16_t* hi, int K) {
+        const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+        const uint4* l4 = reinterpret_cast<const uint4*>(hi + K);
+        for (int i = tid; i < K / 8; i += kPkConsumers) {
+            reinterpret_cast<uint4*>(xh)[i] = ldcg_u4(h4 + i);
+            reinterpret_cast<uint4*>(xl)[i] = ldcg_u4(l4 + i);
+        }
+        zero_x_tail(K);
         pk_named_sync();
     };
 
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
 
             // ---------------- P1: RMSNorm -> q|k|v (+bias) -> RoPE -> q store + KV append ----------------
             dbg_i = 0;
+            dbg_layer = l;
             stamp(l);
             if (a.flags & 1) {   // pull the K/V pages of this CTA's attention item(s) of this layer towards L2 while P1 runs
                 const int npages = (len + kKvPage - 1) / kKvPage;
@@ -732,8 +733,12 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                                 }
                             }
                             const float den = cden[h];
-                            reinterpret_cast<float4*>(a.attn_out + (size_t)(kvh * n_rep + h) * D)[c4] =
-                                make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
+                            uint32_t h0, l0, h1, l1;
+                            split2(num.x / den, num.y / den, h0, l0);
+                            split2(num.z / den, num.w / den, h1, l1);
+                            const size_t oi = (size_t)(kvh * n_rep + h) * D + c4 * 4;
+                            *reinterpret_cast<uint2*>(a.xhl + oi) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2*>(a.xhl + nq + oi) = make_uint2(l0, l1);
                         }
                         if (tid == 0) a.counters[kvh] = 0;
                     }
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             stamp(l);
 
             // ---------------- P3: o_proj + residual add ----------------
-            load_x_plain(a.attn_out, nq);
+            load_x_plain(a.xhl, nq);
             stamp(l);
             {
                 const PkSlice s = consume(a.H, nq);
@@ -774,7 +779,11 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 stamp(l);
                 for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
                     const float g = row_sum(s, 2 * e), u = row_sum(s, 2 * e + 1);
-                    a.act[(s.row_begin >> 1) + e] = g / (1.f + expf(-g)) * u;
+                    const float av = g / (1.f + expf(-g)) * u;
+                    uint16_t ah, al;
+                    split_hi_lo(av, ah, al);
+                    a.xhl[2 * nq + (s.row_begin >> 1) + e] = ah;
+                    a.xhl[2 * nq + a.I + (s.row_begin >> 1) + e] = al;
                 }
             }
             stamp(l);
@@ -782,7 +791,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             stamp(l);
 
             // ---------------- P5: down_proj + residual add ----------------
-            load_x_plain(a.act, a.I);
+            load_x_plain(a.xhl + 2 * nq, a.I);
             stamp(l);
             {
                 const PkSlice s = consume(a.H, a.I);

@@ -41,6 +41,23 @@ CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64
     return m;
 }
 
+// Weight matrix [N, K] bf16 (K % 64 == 0) as the persistent decode kernel streams it: a 3-D view {64 columns, N rows, K/64
+// column blocks} whose box {64, 16, 16} is ONE 32 KB request = 16 rows x 1024 columns, landing in shared memory as
+// [column block][row][128 bytes] with the 128-byte swizzle keyed by the row: conflict-free ldmatrix of 16 x 16 tiles.
+// Out-of-range rows / column blocks are zero-filled by the TMA engine (no tail handling in the kernel).
+CUtensorMap make_tmap_pk(const void* ptr, uint64_t N, uint64_t K) {
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {64, N, K / 64};
+    const cuuint64_t strides[2] = {K * 2, 128};
+    const cuuint32_t box[3] = {64, 16, 16};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FL_CHECK(r == CUDA_SUCCESS, -2, "cuTensorMapEncodeTiled (3-D weight stream) failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
 template <int EPI>
 static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
     constexpr int BN = 128;

@@ -509,6 +509,19 @@ static void finalize(Weights& w) {
         pk[l] = PkLayer{w.layers[l].wqkv, w.layers[l].bqkv, w.layers[l].wo, w.layers[l].wgu, w.layers[l].wdown, w.layers[l].ln1, w.layers[l].ln2};
     w.pk_layers.alloc(w.L);
     FL_CUDA(cudaMemcpy(w.pk_layers.p, pk.data(), pk.size() * sizeof(PkLayer), cudaMemcpyHostToDevice));
+    const uint64_t nqk = (uint64_t)w.nh * w.d;
+    if (w.cfg.arch != FL_ARCH_MIXTRAL && w.H % 64 == 0 && nqk % 64 == 0 && w.I % 64 == 0) {
+        std::vector<CUtensorMap> tm;
+        for (int l = 0; l < w.L; ++l) {
+            tm.push_back(make_tmap_pk(w.layers[l].wqkv, w.nqkv, w.H));
+            tm.push_back(make_tmap_pk(w.layers[l].wo, w.H, nqk));
+            tm.push_back(make_tmap_pk(w.layers[l].wgu, 2 * (uint64_t)w.I, w.H));
+            tm.push_back(make_tmap_pk(w.layers[l].wdown, w.H, w.I));
+        }
+        tm.push_back(make_tmap_pk(w.lm_head, w.V, w.H));
+        w.pk_tmaps.alloc(tm.size());
+        FL_CUDA(cudaMemcpy(w.pk_tmaps.p, tm.data(), tm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }
     w.finalized = true;
 }
 
@@ -569,15 +582,16 @@ static void plan_persistent(fl_cache& c) {
     const int nq = w.nh * w.d;
     if (!(w.d == 64 || w.d == 128)) return;
     if (w.H < 2048 || nq < 256 || w.I < 256) return;        // small models stay on the multi-kernel path
-    if (w.H % 8 || nq % 8 || w.I % 8 || w.nqkv % 2 || w.V % 2) return;
-    const int n_rep = w.nh / w.nkv;
-    int kmax = std::max(w.H, std::max(nq, w.I));
+    // MMA weight stream: row slices in units of 8 rows, k-steps of 16 columns; the RMSNorm prologue keeps a row in registers
+    if (w.pk_tmaps.p == nullptr || w.nqkv % 8 || w.V % 8 || w.H > kPkMaxNormK) return;
+    // x_hi / x_lo are zero-padded to whole 1024-column chunks (the weight tail of the last chunk is zero-filled by TMA)
+    int kmax = (std::max(w.H, std::max(nq, w.I)) + kPkChunkCols - 1) / kPkChunkCols * kPkChunkCols;
     // attention scratch in the same region: [lane groups = 8 warps * 32/(d/8)][4 heads][d] + (m, l) pairs = 8192 + 512 floats,
     // and the split-merge weights [8][nsplit] + 8
-    p.xs_floats = (int)align_up((size_t)std::max(std::max(kmax, 8192 + 512), 8 * kNumSMs + 16), 4);
+    p.xs_floats = (int)align_up((size_t)std::max(std::max(kmax + 16, 8192 + 512), 8 * kNumSMs + 16), 4);
     int rows = 0;
-    for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) rows = std::max(rows, 2 * ((N / 2 + kNumSMs - 1) / kNumSMs + 1));
-    p.partial_rows = rows;
+    for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) rows = std::max(rows, 8 * ((N / 8 + kNumSMs - 1) / kNumSMs + 1));
+    p.partial_rows = (rows + kPkBlockRows - 1) / kPkBlockRows * kPkBlockRows;      // whole 16-row blocks
     const size_t fixed = (size_t)p.xs_floats * 4 + (size_t)p.partial_rows * kPkConsumerWarps * 4 + (size_t)kAttnMaxRep * kKvPage * 4 + 64 * 4;
     const size_t avail = 232448 - 2048;   // 227 KB opt-in limit minus static shared memory and slack
     if (fixed + 2 * (size_t)kPkStageBytes > avail) return;
@@ -611,6 +625,10 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     a.trace = feedback ? c.trace.p : nullptr; a.trace_pos = c.trace_pos.p; a.gbar = c.gbar.p;
     a.nsteps = nsteps; a.feedback = feedback ? 1 : 0; a.nstages = c.pk.nstages; a.xs_floats = c.pk.xs_floats;
     a.partial_rows = c.pk.partial_rows;
+    if (c.pk_xhl.p == nullptr) c.pk_xhl.alloc(2 * ((size_t)w.nh * w.d + w.I) + 64, true);
+    a.xhl = c.pk_xhl.p;
+    a.kcap = (std::max(w.H, std::max(w.nh * w.d, w.I)) + kPkChunkCols - 1) / kPkChunkCols * kPkChunkCols;
+    a.tmaps = w.pk_tmaps.p;
     a.tp = w.tp; a.rank = w.rank;
     if (w.tp > 1) {
         for (int r = 0; r < w.tp; ++r) {
@@ -657,9 +675,11 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
         static const char* names[] = {"P1 x(rmsnorm)", "P1 consume qkv", "P1 epilogue", "P1 grid barrier", "P2 attention", "P2 grid barrier",
                                       "P3 x", "P3 consume o", "P3 epilogue", "P3 grid barrier", "P4 x(rmsnorm)", "P4 consume gate/up",
                                       "P4 epilogue", "P4 grid barrier", "P5 x", "P5 consume down", "P5 epilogue", "P5 grid barrier"};
-        long long h[19];
+        long long h[40];
         FL_CUDA(cudaStreamSynchronize(c.stream));
         FL_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[FL_PK_DEBUG] warp 0 of CTA 0, clocks waiting for weights / chunks per phase: qkv %lld/%lld o %lld/%lld gateup %lld/%lld down %lld/%lld\n",
+                h[32] / 1000, h[32] % 1000, h[33] / 1000, h[33] % 1000, h[34] / 1000, h[34] % 1000, h[35] / 1000, h[35] % 1000);
         fprintf(stderr, "[FL_PK_DEBUG] layer %d, CTA 0 phase times (us):", w.L / 2);
         for (int i = 0; i < 18; ++i) fprintf(stderr, " %s=%.2f;", names[i], (h[i + 1] - h[i]) / 1000.0);
         fprintf(stderr, " layer total=%.2f\n", (h[18] - h[0]) / 1000.0);

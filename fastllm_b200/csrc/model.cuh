@@ -50,6 +50,7 @@ struct Weights {
     float* final_norm = nullptr;
     std::vector<LayerW> layers;
     DevBuf<PkLayer> pk_layers;  // device copy of the per-layer pointers for the persistent decode kernel
+    DevBuf<CUtensorMap> pk_tmaps; // [4 L + 1] 3-D TMA descriptors of the weight stream (phase g = 4 layer + {qkv, o, gate|up, down}; lm_head last)
     float* rope_cos = nullptr;  // [max_pos, d/2]
     float* rope_sin = nullptr;
     std::set<std::string> have; // tensor names that arrived
@@ -125,6 +126,7 @@ struct fl_cache {
     fl::PkPlan pk;
     fl::DenseWs dw;
     fl::DevBuf<unsigned int> gbar;
+    fl::DevBuf<uint16_t> pk_xhl;    // persistent decode kernel: hi/lo bf16 hand-over of attn_out and the MLP activation
     fl::DevBuf<float> resid2;        // second residual buffer (tp > 1: the fused residual-add prologue ping-pongs)
     fl::DevBuf<float> tp_buf;        // [rows, H] partial o_proj / down_proj outputs awaiting the all-reduce (tp > 1)
     fl::DevBuf<float> tp_gather;     // [tp, max_batch, V] vocab-parallel logits gathered from all ranks
