@@ -11,7 +11,8 @@
 //   * consumers: a chunk is a 16-row x 1024-column block of the weight matrix: ONE 3-D TMA request that lands as
 //     [column block][row][128 B] with the 128-byte swizzle keyed by the row (bank-conflict-free ldmatrix).  The 8 warps split its 64 k-steps; each k-step is ONE mma.sync m16n8k16: A = the bf16 weight tile
 //     straight from shared memory (ldmatrix, no unpack instructions), B = the activation vector split hi + lo into two bf16
-//     columns (~16 mantissa bits, products exact, f32 accumulate), so y[row] = D[row][0] + D[row][1] falls out of the
+//     columns (~16 mantissa bits, products exact, f32 accumulate; the other six columns are don't-care), so
+//     y[row] = D[row][0] + D[row][1] falls out of the
 //     accumulator fragment without a single shuffle.  ~35 instructions per warp per 32 KB chunk (the CUDA-core version
 //     needed ~170 and was the bottleneck: measured 1030 clk/chunk against the 770 clk/chunk the L2 can deliver).
 //     Per-warp partials land in shared memory, one cross-warp sum per phase, then the same fused epilogues as gemv.cuh
@@ -257,7 +258,6 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     int* s_flag = reinterpret_cast<int*>(lrun + 8);
     __shared__ __align__(8) uint64_t full[kPkMaxStages];
     __shared__ __align__(8) uint64_t empty[kPkMaxStages];
-    __shared__ __align__(16) uint16_t zero16[8];      // the all-zero columns of the MMA B operand
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, ncta = gridDim.x;
@@ -271,7 +271,6 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         }
         mbar_fence_init();
     }
-    if (tid < 8) zero16[tid] = 0;
     __syncthreads();
 
     // =================================================================================================================
@@ -336,15 +335,15 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         const PkSlice s = pk_slice(N, K, cta, ncta);
         dbg_wait = 0;
         // ldmatrix row addresses of this lane: A = weight tile rows (lane & 15), +8 columns for lanes 16-31;
-        // B = [n = lane & 7][8 consecutive k]: n == 0 -> x_hi, n == 1 -> x_lo, other n -> zeros; lanes 8-15 take k + 8
+        // B = [n = lane & 7][8 consecutive k]: n == 1 -> x_lo, every other n -> x_hi (columns 2-7 of D are never read, so those
+        // rows need not be zero: re-reading x_hi is a broadcast and keeps the load bank-conflict-free); lanes 8-15 take k + 8
         // staged tile: [column block kb][row r][128 B], 16-byte piece p of a row stored at p ^ (r & 7) (TMA SWIZZLE_128B).
         // k-step ks = warp + 8 j covers pieces 2 (ks & 3) + {0, 1} of column block ks >> 2, so for a given lane the piece is
         // the same for every j and the k-steps of a warp are 4096 bytes apart.
         const int ar = lane & 15;
         const uint32_t a_off = (uint32_t)(warp >> 2) * 2048u + (uint32_t)ar * 128u + (uint32_t)(((((warp & 3) << 1) | (lane >> 4)) ^ (ar & 7)) << 4);
         const int bn = lane & 7, bk = ((lane >> 3) & 1) * 8;
-        const uint16_t* xrow = bn == 0 ? xh : (bn == 1 ? xl : zero16);
-        const int xmul = bn < 2 ? 1 : 0;          // the zero rows always read the same 16 bytes
+        const uint16_t* xrow = bn == 1 ? xl : xh;
         float acc[2][4];
         int i = 0;
         for (int blk = 0; blk < s.nblocks; ++blk) {
@@ -359,14 +358,14 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 const int col0 = cc * kPkChunkCols;
                 // all fragment loads of the chunk first (independent, in flight together), then the MMAs (two accumulator chains)
                 constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
-                const uint16_t* xcol = xrow + (size_t)xmul * (col0 + bk + warp * 16);
+                const uint16_t* xcol = xrow + (col0 + bk + warp * 16);
 #pragma unroll
                 for (int h = 0; h < KPW; h += 4) {
                     uint32_t af[4][4], bf[4][2];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         ldmatrix_x4(af[j], tile + (h + j) * 4096);
-                        ldmatrix_x2(bf[j], xcol + (size_t)xmul * ((h + j) * kPkConsumerWarps * 16));
+                        ldmatrix_x2(bf[j], xcol + (h + j) * kPkConsumerWarps * 16);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j & 1], af[j], bf[j]);

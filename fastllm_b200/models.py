@@ -260,7 +260,9 @@ class _CausalBase:
         if tensors is None:
             dev.random_init(0 if random_seed is None else random_seed, std)
         else:
-            for name, arr in tensors.items():
+            # a dict, or any iterable of (name, array) -- e.g. safetensors_io.iter_tensors(dir), which hands over views of the
+            # memory-mapped checkpoint one tensor at a time (huggingface.rs:81-130 without the whole-file reads)
+            for name, arr in (tensors.items() if hasattr(tensors, "items") else tensors):
                 dev.put_tensor(name, np.asarray(arr))
         dev.finalize()
         self = cls(dev, cfg)

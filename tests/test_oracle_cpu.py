@@ -93,3 +93,30 @@ def test_bf16_rounding_is_rne():
     import torch
     want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
     assert (synth.round_bf16(x) == want).all()
+
+
+def test_safetensors_ingest_round_trip(tmp_path):
+    """safetensors_io: single-file and sharded (index.json weight_map) checkpoints come back bit-identical through the
+    memory-mapped reader, in f32 / f16 / bf16-bits, with the reference's file-selection rule (huggingface.rs:83-121)."""
+    import json
+    from fastllm_b200 import safetensors_io as sio
+    rng = np.random.default_rng(0)
+    a = {"model.embed_tokens.weight": rng.standard_normal((7, 5)).astype(np.float32),
+         "model.norm.weight": rng.standard_normal((5,)).astype(np.float16),
+         "lm_head.weight": rng.integers(0, 65535, (7, 5)).astype(np.uint16)}
+    d1 = tmp_path / "single"
+    d1.mkdir()
+    sio.write_safetensors(str(d1 / "model.safetensors"), a)
+    got = {k: np.array(v) for k, v in sio.iter_tensors(str(d1))}
+    assert set(got) == set(a) and all(got[k].dtype == a[k].dtype and np.array_equal(got[k], a[k]) for k in a)
+    d2 = tmp_path / "sharded"
+    d2.mkdir()
+    names = list(a)
+    sio.write_safetensors(str(d2 / "model-00001-of-00002.safetensors"), {names[0]: a[names[0]]})
+    sio.write_safetensors(str(d2 / "model-00002-of-00002.safetensors"), {n: a[n] for n in names[1:]})
+    json.dump({"weight_map": {names[0]: "model-00001-of-00002.safetensors", names[1]: "model-00002-of-00002.safetensors",
+                              names[2]: "model-00002-of-00002.safetensors"}}, open(d2 / "model.safetensors.index.json", "w"))
+    got = {k: np.array(v) for k, v in sio.iter_tensors(str(d2))}
+    assert set(got) == set(a) and all(np.array_equal(got[k], a[k]) for k in a)
+    with pytest.raises(FileNotFoundError):
+        list(sio.iter_tensors(str(tmp_path)))
