@@ -215,11 +215,11 @@ __device__ __forceinline__ void pk_grid_barrier(unsigned int* ctr, unsigned int&
     pk_named_sync();
     epoch += 1;
     if (tid == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // arrive: a release-reduction (no return value, so no round trip before the poll starts); the CTA barrier above
+        // orders every consumer thread's writes before it (cumulativity), the acquire loads below order the reads after it
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
         const unsigned int target = epoch * gridDim.x;
         while (ld_acquire_gpu(ctr) < target) { }
-        __threadfence();
     }
     pk_named_sync();
 }
@@ -465,7 +465,6 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             const int i = tid + j * kPkConsumers;
             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < K / 4) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(norm_w) + i));
                 if (src_is_embed_row) {
                     const uint2 e = __ldg(reinterpret_cast<const uint2*>(erow) + i);
                     v[j] = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
@@ -473,17 +472,27 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 } else {
                     v[j] = __ldcg(reinterpret_cast<const float4*>(src) + i);
                 }
-                ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
             }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {      // rows past K hold zeros
+            ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
         }
         const float tot = block_sum(ss);
         const float m = sqrtf(tot / (float)K + a.eps);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int i = tid + j * kPkConsumers;
-            if (i < K / 4) {
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(norm_w) + i);
-                store_x4(i, make_float4(v[j].x / m * wv.x, v[j].y / m * wv.y, v[j].z / m * wv.z, v[j].w / m * wv.w));
+        for (int h = 0; h < NV; h += 4) {       // norm weights four loads at a time (L2-resident: prefetched a phase earlier)
+            float4 wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = tid + (h + j) * kPkConsumers;
+                wv[j] = i < K / 4 ? __ldg(reinterpret_cast<const float4*>(norm_w) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = tid + (h + j) * kPkConsumers;
+                const float4 x = v[h + j];
+                if (i < K / 4) store_x4(i, make_float4(x.x / m * wv[j].x, x.y / m * wv[j].y, x.z / m * wv[j].z, x.w / m * wv[j].w));
             }
         }
         zero_x_tail(K);
@@ -501,6 +510,10 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         pk_named_sync();
     };
 
+    // pull a small f32 vector (norm weights of an upcoming phase) towards L2 well before its prologue needs it
+    auto prefetch_vec = [&](const float* p, int n) {
+        for (int i = tid * 32; i < n; i += kPkConsumers * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
+    };
     int dbg_i = 0;
     auto stamp = [&](int l) {
         if (a.dbg != nullptr && cta == 0 && tid == 0 && l == a.L / 2) {
@@ -528,6 +541,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             uint16_t* vpool = a.vpool + (size_t)l * a.layer_pool_elems;
 
             // ---------------- P1: RMSNorm -> q|k|v (+bias) -> RoPE -> q store + KV append ----------------
+            prefetch_vec(lw.ln2, a.H);                                         // needed by P4, ~25 us from now
             dbg_i = 0;
             dbg_layer = l;
             stamp(l);
@@ -749,6 +763,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             stamp(l);
 
             // ---------------- P3: o_proj + residual add ----------------
+            prefetch_vec(l + 1 < a.L ? a.layers[l + 1].ln1 : a.final_norm, a.H);   // needed by the next P1 / the head
             load_x_plain(a.xhl, nq);
             stamp(l);
             {
