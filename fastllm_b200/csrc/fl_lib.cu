@@ -913,6 +913,7 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     }
     d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
+    if (w.cfg.arch != FL_ARCH_MIXTRAL && R > 128) { d.xhi2.alloc(R * (size_t)w.I); d.xlo2.alloc(R * (size_t)w.I); }
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {
         d.xhi2.alloc(Rm * kmax); d.xlo2.alloc(Rm * kmax);
         d.moe_out.alloc(Rm * w.H); d.route_w.alloc(R * w.E);
@@ -974,7 +975,7 @@ static int pick_ksplit(int tiles, int nk, int R) {
 //             N = R tile, the result is stored transposed; the only large shared-memory traffic is the weight stream.
 //   R  > 128 (prefill): tokens are the M dimension, 128 x 128 output tiles.
 static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N, int K, const CUtensorMap& tmW, float* out,
-                      const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr) {
+                      const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, uint16_t* silu_hi = nullptr, uint16_t* silu_lo = nullptr) {
     if (!xhi) { xhi = c.dw.xhi.p; xlo = c.dw.xlo.p; }
     const int nk = (K + kGemmBK - 1) / kGemmBK;
     const bool swap = R <= 128;
@@ -1002,8 +1003,13 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         }
     } else {
         const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, kGemmBM), lo = make_tmap_bf16(xlo, R, K, K, kGemmBM);
-        GemmArgs g{R, N, K, nullptr, nullptr, 0, out, N, 1, (long long)R * N};
-        launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+        if (silu_hi != nullptr) {       // prefill gate|up: SiLU(gate) * up + hi/lo split fused into the epilogue
+            GemmArgs g{R, N, K, nullptr, nullptr, 0, silu_hi, N / 2, 1, 0, silu_lo};
+            launch_gemm_tc<128, GEPI_SILU_HL, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+        } else {
+            GemmArgs g{R, N, K, nullptr, nullptr, 0, out, N, 1, (long long)R * N};
+            launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+        }
     }
     if (prof) {
         FL_CUDA(cudaEventRecord(pe.e1, lc.stream));
@@ -1114,10 +1120,15 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 tp_allreduce_sum(lc, d.moe_out.p, (size_t)R * w.H);    // attention replicated: combine = sum over ranks
             }
         } else {
-            ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
-            launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
-                   (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
-            ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
+            if (R > 128) {      // prefill: the gate|up epilogue writes the down_proj operand directly
+                dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p, nullptr, nullptr, d.xhi2.p, d.xlo2.p);
+                ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p, d.xhi2.p, d.xlo2.p);
+            } else {
+                ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
+                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
+                       (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
+                ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
+            }
             delta = d.y.p;
             tp_reduce();
         }

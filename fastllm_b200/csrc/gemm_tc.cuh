@@ -18,7 +18,7 @@
 
 namespace fl {
 
-enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5 };
+enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5, GEPI_SILU_HL = 6 };
 enum : int { DUAL_NONE = 0, DUAL_A = 1, DUAL_B = 2 };
 
 constexpr int kGemmBM = 128;
@@ -35,6 +35,7 @@ struct GemmArgs {
     int ldo;
     int ksplit;                 // >1: K is cut into ksplit ranges handled by different work items (GEPI_F32 / GEPI_ATOMIC_F32)
     long long split_stride;     // GEPI_F32 with ksplit > 1: split s writes its partial sums to out + s * split_stride (deterministic)
+    void* out2 = nullptr;       // GEPI_SILU_HL: the lo half ([M, ldo] bf16, like `out` = the hi half)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -273,6 +274,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     pk[e >> 1] = pack_bf16x2(v0, v1);
                                 }
                                 *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        }
+                    } else if (EPI == GEPI_SILU_HL) {
+                        // gate|up GEMM of the prefill: columns interleave gate_j (even) and up_j (odd); act_j = silu(gate_j) * up_j
+                        // is written straight as the hi/lo bf16 operand of the down_proj GEMM ([M, N/2] each)
+                        uint16_t* oh = reinterpret_cast<uint16_t*>(g.out) + (size_t)row * g.ldo + (col >> 1);
+                        uint16_t* ol = reinterpret_cast<uint16_t*>(g.out2) + (size_t)row * g.ldo + (col >> 1);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 16) {
+                            if (col + j < g.N) {
+                                uint32_t ph[4], pl[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float g0 = __uint_as_float(r[j + 4 * e]), u0 = __uint_as_float(r[j + 4 * e + 1]);
+                                    const float g1 = __uint_as_float(r[j + 4 * e + 2]), u1 = __uint_as_float(r[j + 4 * e + 3]);
+                                    const float a0 = g0 / (1.f + expf(-g0)) * u0, a1 = g1 / (1.f + expf(-g1)) * u1;
+                                    ph[e] = pack_bf16x2(a0, a1);
+                                    pl[e] = pack_bf16x2(a0 - bf16lo(ph[e]), a1 - bf16hi(ph[e]));
+                                }
+                                *reinterpret_cast<uint4*>(oh + (j >> 1)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                *reinterpret_cast<uint4*>(ol + (j >> 1)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                             }
                         }
                     } else if (EPI == GEPI_F32_T) {
