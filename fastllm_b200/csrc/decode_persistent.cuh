@@ -40,6 +40,7 @@ constexpr int kPkBlockRows = 16;                       // rows per chunk = M of 
 constexpr int kPkChunkCols = 1024;                     // columns per chunk
 constexpr int kPkStageBytes = kPkBlockRows * kPkChunkCols * 2;     // 32 KB: ONE 3-D TMA request (see make_tmap_pk)
 constexpr int kPkMaxStages = 6;
+constexpr int kPkMaxSlots = 96;                        // blocks one CTA can process per phase (static share + pool cap)
 constexpr int kPkMaxNormK = 8192;                      // RMSNorm prologue keeps the row in registers (hidden size limit)
 
 struct PkLayer {
@@ -90,6 +91,8 @@ struct PkArgs {
     int xs_floats;        // shared-memory activation / scratch region capacity (floats)
     int kcap;             // largest K of any phase rounded up to whole chunks (x_hi at xs, x_lo at xs + (kcap + 8) bf16)
     const CUtensorMap* tmaps;   // [4 L + 1] weight-stream descriptors, indexed by the phase id g
+    int static_num;             // static share of a phase's blocks in 32nds (the rest is the pool)
+    unsigned int* pool;         // [4 L + 1] ticket counters of the phases' dynamic block pools (zero between uses)
     int partial_rows;     // rows of the per-warp partial buffer
     // ---- tensor parallelism inside the kernel: all-reduce over NVLink peer memory (no NCCL call, no extra launch) ----
     int tp, rank;                    // tp == 1: single GPU
@@ -104,26 +107,38 @@ struct PkArgs {
     long long* dbg;       // optional: CTA 0 writes %globaltimer at the phase boundaries of layer L/2 (FL_PK_DEBUG=1)
 };
 
-// ---- chunk schedule shared by producer and consumers --------------------------------------------------------------
-struct PkSlice {
-    int row_begin, row_end;   // 8-aligned row range of this CTA
-    int nblocks;              // 16-row blocks (the last one may hold 8 rows)
-    int ncc;                  // column chunks per block
-    int nchunks;
-    int K;
+// ---- block schedule ---------------------------------------------------------------------------------------------------
+// A phase's weight matrix is cut into 16-row blocks.  Every CTA owns a STATIC share of contiguous blocks; the remaining
+// ~16 % form a pool that the producers drain one block at a time through an atomic ticket counter: a CTA whose stream runs
+// ahead (the L2->SM delivery rate differs by +-13 % between SMs, reproducibly) frees its ring slots sooner, reaches the pool
+// sooner and takes more of it, so all CTAs reach the phase's grid barrier together.  Which CTA computes a row never changes
+// its value (the whole dot product of a row lives in one CTA, summed in a fixed order), so results stay bit-reproducible.
+// Tensor parallelism keeps the split static (no pool): the in-kernel all-reduce pairs the same CTA on every rank.
+struct PkSplit {
+    int s0, s1;        // static block range of this CTA
+    int pool0, npool;  // pool = blocks [pool0, pool0 + npool)
+    int ncc;           // column chunks per block
 };
+constexpr int kPkStaticNum = 30;      // default static share of a phase's blocks, in 32nds (PkArgs.static_num)
+constexpr int kPkPoolCap = 8;      // pool blocks one CTA may take per phase (bounds the per-CTA partial-sum buffer)
 
-__device__ __forceinline__ PkSlice pk_slice(int N, int K, int cta, int ncta) {
-    PkSlice s;
-    const int units = N >> 3;
-    s.row_begin = 8 * (int)((long long)units * cta / ncta);
-    s.row_end = 8 * (int)((long long)units * (cta + 1) / ncta);
-    s.nblocks = (s.row_end - s.row_begin + kPkBlockRows - 1) / kPkBlockRows;
-    s.ncc = (K + kPkChunkCols - 1) / kPkChunkCols;
-    s.nchunks = s.nblocks * s.ncc;
-    s.K = K;
-    return s;
+__device__ __forceinline__ PkSplit pk_split(int N, int K, int cta, int ncta, bool dynamic, int static_num) {
+    PkSplit p;
+    const int nblk = N / kPkBlockRows;
+    p.ncc = (K + kPkChunkCols - 1) / kPkChunkCols;
+    if (dynamic) {
+        const int S = (int)((long long)nblk * static_num / 32) / ncta;
+        p.s0 = cta * S; p.s1 = p.s0 + S;
+        p.pool0 = ncta * S; p.npool = nblk - p.pool0;
+    } else {
+        p.s0 = (int)((long long)nblk * cta / ncta); p.s1 = (int)((long long)nblk * (cta + 1) / ncta);
+        p.pool0 = nblk; p.npool = 0;
+    }
+    return p;
 }
+
+// per-stage message from the producer to the consumers (shared memory, published by the stage's mbarrier)
+constexpr int kPkMetaEnd = 1 << 30;      // no data in this stage: the phase is over for this CTA
 
 __device__ __forceinline__ void pk_named_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kPkConsumers) : "memory"); }
 
@@ -179,37 +194,6 @@ __device__ __forceinline__ void pk_phase(const PkArgs& a, int g, const uint16_t*
     }
 }
 
-// Walks this CTA's chunk schedule (every step, every phase, every chunk) in consumption order.
-struct PkCursor {
-    int step, g, i, K;
-    const uint16_t* W;
-    PkSlice s;
-    bool valid;
-    __device__ void enter(const PkArgs& a, int cta, int ncta) {
-        while (true) {
-            if (step >= a.nsteps) { valid = false; return; }
-            int N;
-            pk_phase(a, g, W, N, K);
-            s = pk_slice(N, K, cta, ncta);
-            i = 0;
-            if (s.nchunks > 0) { valid = true; return; }
-            if (++g > 4 * a.L) { g = 0; ++step; }
-        }
-    }
-    __device__ void init(const PkArgs& a, int cta, int ncta) { step = 0; g = 0; enter(a, cta, ncta); }
-    // chunk i = (block i / ncc, column chunk i % ncc) -> TMA coordinates (first row, first 64-column block)
-    __device__ void get(int& row0, int& kb0) const {
-        const int blk = i / s.ncc, cc = i - blk * s.ncc;
-        row0 = s.row_begin + blk * kPkBlockRows;
-        kb0 = cc * (kPkChunkCols / 64);
-    }
-    __device__ void advance(const PkArgs& a, int cta, int ncta) {
-        if (++i < s.nchunks) return;
-        if (++g > 4 * a.L) { g = 0; ++step; }
-        enter(a, cta, ncta);
-    }
-};
-
 // Grid barrier among the consumer threads of all CTAs (the producer warp never takes part and keeps streaming).
 __device__ __forceinline__ void pk_grid_barrier(unsigned int* ctr, unsigned int& epoch, int tid) {
     pk_named_sync();
@@ -258,6 +242,8 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     int* s_flag = reinterpret_cast<int*>(lrun + 8);
     __shared__ __align__(8) uint64_t full[kPkMaxStages];
     __shared__ __align__(8) uint64_t empty[kPkMaxStages];
+    __shared__ int2 meta[kPkMaxStages];      // per stage: {first row of the block, column chunk | last-chunk flag | end-of-phase flag}
+    __shared__ int blk_rows[kPkMaxSlots];    // first rows of the blocks processed in the current phase
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, ncta = gridDim.x;
@@ -278,38 +264,43 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // =================================================================================================================
     if (warp == kPkConsumerWarps) {
         if (lane != 0) return;
-        // Two cursors over the same schedule: `ld` feeds the shared-memory ring, `pf` runs up to lookahead_bytes ahead of
-        // it issuing L2 prefetches so the ring refills at L2 latency after a compute gap.
-        unsigned int c = 0;   // running chunk counter -> stage = c % NS, use = c / NS
-        PkCursor ld, pf;
-        ld.init(a, cta, ncta);
-        pf.init(a, cta, ncta);
-        int ahead = 0;
+        unsigned int c = 0;   // running stage counter -> stage = c % NS, use = c / NS
         const uint64_t pol_first = l2_policy_evict_first();
-        while (ld.valid) {
-            while (pf.valid && ahead < a.lookahead_bytes) {
-                int row0, kb0;
-                pf.get(row0, kb0);
-                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(a.tmaps + pf.g), "r"(0), "r"(row0), "r"(kb0)
-                             : "memory");
-                ahead += kPkStageBytes;
-                pf.advance(a, cta, ncta);
+        const bool dynamic = a.tp == 1 && a.pool != nullptr;
+        for (int step = 0; step < a.nsteps; ++step) {
+            for (int g = 0; g <= 4 * a.L; ++g) {
+                const uint16_t* W;
+                int N, K;
+                pk_phase(a, g, W, N, K);
+                const PkSplit sp = pk_split(N, K, cta, ncta, dynamic, a.static_num);
+                auto fetch_block = [&](int blk) {
+                    for (int cc = 0; cc < sp.ncc; ++cc, ++c) {
+                        const int st = c % NS;
+                        mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
+                        meta[st] = make_int2(blk * kPkBlockRows, cc | (cc == sp.ncc - 1 ? 1 << 16 : 0));
+                        mbar_expect_tx(&full[st], kPkStageBytes);      // the whole box always arrives (out-of-range columns as zeros)
+                        // weights are dead once staged: evict_first keeps the L2 for the KV cache and the activations
+                        asm volatile(
+                            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                                smem_u32(ring + (size_t)st * kPkStageBytes)),
+                            "l"(a.tmaps + g), "r"(0), "r"(blk * kPkBlockRows), "r"(cc * (kPkChunkCols / 64)), "r"(smem_u32(&full[st])), "l"(pol_first)
+                            : "memory");
+                    }
+                };
+                for (int blk = sp.s0; blk < sp.s1; ++blk) fetch_block(blk);
+                // tickets are taken lazily, only when this CTA is ready to stream another block (taking them ahead of time hands
+                // the tail of the phase to CTAs that may turn out slow: measured slower); the ring hides the atomic's round trip
+                for (int taken = 0; sp.npool > 0 && taken < kPkPoolCap; ++taken) {
+                    const int t = (int)atomicAdd(a.pool + g, 1u);
+                    if (t >= sp.npool) break;
+                    fetch_block(sp.pool0 + t);
+                }
+                const int st = c % NS;          // end-of-phase message (no data)
+                mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
+                meta[st] = make_int2(0, kPkMetaEnd);
+                mbar_arrive(&full[st]);
+                ++c;
             }
-            int row0, kb0;
-            ld.get(row0, kb0);
-            if (a.flags & 8) { row0 = ld.s.row_begin; kb0 = 0; }   // DEV experiment: always this CTA's first chunk (L2-resident)
-            const int st = c % NS;
-            mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
-            mbar_expect_tx(&full[st], kPkStageBytes);      // the whole box always arrives (out-of-range parts as zeros)
-            // weights are dead once staged: evict_first keeps the L2 for the lookahead and the KV cache
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
-                    smem_u32(ring + (size_t)st * kPkStageBytes)),
-                "l"(a.tmaps + ld.g), "r"(0), "r"(row0), "r"(kb0), "r"(smem_u32(&full[st])), "l"(pol_first)
-                : "memory");
-            ahead -= kPkStageBytes;
-            ld.advance(a, cta, ncta);
-            ++c;
         }
         return;
     }
@@ -331,8 +322,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // sums land in partial[(row - row_begin) * 8 + warp] and are added up in the phase epilogue.
     long long dbg_wait = 0;
     int dbg_layer = -1, dbg_phase = 0;
-    auto consume = [&](int N, int K) -> PkSlice {
-        const PkSlice s = pk_slice(N, K, cta, ncta);
+    auto consume = [&](int K) -> int {      // -> number of 16-row blocks this CTA processed (their first rows in blk_rows[])
         dbg_wait = 0;
         // ldmatrix row addresses of this lane: A = weight tile rows (lane & 15), +8 columns for lanes 16-31;
         // B = [n = lane & 7][8 consecutive k]: n == 1 -> x_lo, every other n -> x_hi (columns 2-7 of D are never read, so those
@@ -345,46 +335,61 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         const int bn = lane & 7, bk = ((lane >> 3) & 1) * 8;
         const uint16_t* xrow = bn == 1 ? xl : xh;
         float acc[2][4];
-        int i = 0;
-        for (int blk = 0; blk < s.nblocks; ++blk) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = 0.f;
-            for (int cc = 0; cc < s.ncc; ++cc, ++i, ++c) {
-                const int st = c % NS;
-                const long long tw0 = a.dbg ? clock64() : 0;
-                mbar_wait(&full[st], (c / NS) & 1);
-                if (a.dbg) dbg_wait += clock64() - tw0;
-                const uint8_t* tile = ring + (size_t)st * kPkStageBytes + a_off;
-                const int col0 = cc * kPkChunkCols;
-                // all fragment loads of the chunk first (independent, in flight together), then the MMAs (two accumulator chains)
-                constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
-                const uint16_t* xcol = xrow + (col0 + bk + warp * 16);
-#pragma unroll
-                for (int h = 0; h < KPW; h += 4) {
-                    uint32_t af[4][4], bf[4][2];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        ldmatrix_x4(af[j], tile + (h + j) * 4096);
-                        ldmatrix_x2(bf[j], xcol + (h + j) * kPkConsumerWarps * 16);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j & 1], af[j], bf[j]);
-                }
+        int nslots = 0, nch = 0;
+        while (true) {
+            const int st = c % NS;
+            const long long tw0 = a.dbg ? clock64() : 0;
+            mbar_wait(&full[st], (c / NS) & 1);
+            if (a.dbg) dbg_wait += clock64() - tw0;
+            const int2 m = meta[st];
+            ++c;
+            if (m.y & kPkMetaEnd) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[st]);
+                break;
             }
-            if (tq == 0) {
-                float* pr = partial + (size_t)(blk * kPkBlockRows + g) * kPkConsumerWarps + warp;
-                pr[0] = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
-                pr[8 * kPkConsumerWarps] = (acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3]);
+            const int cc = m.y & 0xFFFF;
+            if (cc == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = 0.f;
+            }
+            const uint8_t* tile = ring + (size_t)st * kPkStageBytes + a_off;
+            const int col0 = cc * kPkChunkCols;
+            // all fragment loads of a half chunk first (independent, in flight together), then the MMAs (two accumulator chains)
+            constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
+            const uint16_t* xcol = xrow + (col0 + bk + warp * 16);
+#pragma unroll
+            for (int h = 0; h < KPW; h += 4) {
+                uint32_t af[4][4], bf[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ldmatrix_x4(af[j], tile + (h + j) * 4096);
+                    ldmatrix_x2(bf[j], xcol + (h + j) * kPkConsumerWarps * 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j & 1], af[j], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            ++nch;
+            if (m.y & (1 << 16)) {      // last column chunk of the block: the row sums are complete
+                if (tq == 0) {
+                    float* pr = partial + (size_t)(nslots * kPkBlockRows + g) * kPkConsumerWarps + warp;
+                    pr[0] = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
+                    pr[8 * kPkConsumerWarps] = (acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3]);
+                }
+                if (tid == 0) blk_rows[nslots] = m.x;
+                ++nslots;
             }
         }
-        if (a.dbg != nullptr && cta == 0 && tid == 0 && dbg_layer == a.L / 2) a.dbg[32 + (dbg_phase++ & 3)] = dbg_wait * 1000 + s.nchunks;
-        pk_named_sync();   // partial[] complete
-        return s;
+        if (a.dbg != nullptr && cta == 0 && tid == 0 && dbg_layer == a.L / 2) a.dbg[32 + (dbg_phase++ & 3)] = dbg_wait * 1000 + nch;
+        pk_named_sync();   // partial[] and blk_rows[] complete
+        return nslots;
     };
+    // local row (slot * 16 + r) of the blocks this CTA processed in the current phase -> row of the weight matrix
+    auto grow = [&](int local_row) { return blk_rows[local_row >> 4] + (local_row & 15); };
     // sum of the 8 per-warp partials of one row
-    auto row_sum = [&](const PkSlice& s, int local_row) {
+    auto row_sum = [&](int local_row) {
         const float* pr = partial + (size_t)local_row * kPkConsumerWarps;
         float v = pr[0];
 #pragma unroll
@@ -396,13 +401,13 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // (tp x ~100 bytes), publishes a per-CTA flag with release.sys, waits for the same CTA of every peer, then sums the tp
     // partials in rank order (identical on every rank, so the replicas stay bit-identical) and adds them to the residual.
     unsigned int ar_epoch = a.ar_epoch0;
-    auto allreduce_resid_add = [&](const PkSlice& s) {
+    auto allreduce_resid_add = [&](int nslots) {
         ar_epoch += 1;
         const int par = ar_epoch & 1;
-        const int npair = (s.row_end - s.row_begin) / 2;
+        const int npair = nslots * (kPkBlockRows / 2);
         for (int e = tid; e < npair; e += kPkConsumers) {
-            const float2 v = make_float2(row_sum(s, 2 * e), row_sum(s, 2 * e + 1));
-            const size_t off = (size_t)(par * a.tp + a.rank) * a.H + s.row_begin + 2 * e;
+            const float2 v = make_float2(row_sum(2 * e), row_sum(2 * e + 1));
+            const size_t off = (size_t)(par * a.tp + a.rank) * a.H + grow(2 * e);
             for (int r = 0; r < a.tp; ++r) *reinterpret_cast<float2*>(a.peer_part[r] + off) = v;
         }
         // no per-thread system fence: the CTA barrier orders every thread's pushes before the flag writers' st.release.sys,
@@ -415,10 +420,11 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         pk_named_sync();
         const float* mine = a.peer_part[a.rank];
         for (int e = tid; e < npair; e += kPkConsumers) {
-            float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
+            const int gr = grow(2 * e);
+            float2* p = reinterpret_cast<float2*>(a.resid + gr);
             float2 v = __ldcg(p);
             for (int r = 0; r < a.tp; ++r) {
-                const float2 y = __ldcg(reinterpret_cast<const float2*>(mine + (size_t)(par * a.tp + r) * a.H + s.row_begin + 2 * e));
+                const float2 y = __ldcg(reinterpret_cast<const float2*>(mine + (size_t)(par * a.tp + r) * a.H + gr));
                 v.x += y.x;
                 v.y += y.y;
             }
@@ -566,12 +572,12 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 load_x_rmsnorm(a.resid, false, nullptr, lw.ln1, a.H, nullptr);
             stamp(l);
             {
-                const PkSlice s = consume(a.nqkv, a.H);
+                const int nslots = consume(a.H);
                 stamp(l);
                 const int d = a.d, half = d >> 1;
-                for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                    const int ra = s.row_begin + 2 * e;
-                    float va = row_sum(s, 2 * e), vb = row_sum(s, 2 * e + 1);
+                for (int e = tid; e < nslots * (kPkBlockRows / 2); e += kPkConsumers) {
+                    const int ra = grow(2 * e);
+                    float va = row_sum(2 * e), vb = row_sum(2 * e + 1);
                     if (lw.bqkv) { va += lw.bqkv[ra]; vb += lw.bqkv[ra + 1]; }
                     const int hh = ra / d, j = (ra % d) >> 1;
                     if (hh < a.nh + a.nkv) {
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             }
             stamp(l);
             pk_grid_barrier(a.gbar, epoch, tid);
+            if (cta == 0 && tid == 0 && a.pool != nullptr) atomicExch(a.pool + (4 * l), 0u);      // every producer is past this phase: re-arm its pool
             stamp(l);
 
             // ---------------- P2: split-K attention over (kv head, split) items + last-arriver merge ----------------
@@ -767,75 +774,88 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             load_x_plain(a.xhl, nq);
             stamp(l);
             {
-                const PkSlice s = consume(a.H, nq);
+                const int nslots = consume(nq);
                 stamp(l);
                 if (a.tp > 1) {
-                    allreduce_resid_add(s);
+                    allreduce_resid_add(nslots);
                 } else {
-                    for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                        float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
+                    for (int e = tid; e < nslots * (kPkBlockRows / 2); e += kPkConsumers) {
+                        float2* p = reinterpret_cast<float2*>(a.resid + grow(2 * e));
                         float2 v = __ldcg(p);
-                        v.x += row_sum(s, 2 * e);
-                        v.y += row_sum(s, 2 * e + 1);
+                        v.x += row_sum(2 * e);
+                        v.y += row_sum(2 * e + 1);
                         *p = v;
                     }
                 }
             }
             stamp(l);
             pk_grid_barrier(a.gbar, epoch, tid);
+            if (cta == 0 && tid == 0 && a.pool != nullptr) atomicExch(a.pool + (4 * l + 1), 0u);      // every producer is past this phase: re-arm its pool
             stamp(l);
 
             // ---------------- P4: RMSNorm -> gate|up -> SiLU(gate) * up ----------------
             load_x_rmsnorm(a.resid, false, nullptr, lw.ln2, a.H, nullptr);
             stamp(l);
             {
-                const PkSlice s = consume(2 * a.I, a.H);
+                long long t0c = 0;
+                if (a.dbg != nullptr && tid == 0 && l == a.L / 2) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0c));
+                const int nslots = consume(a.H);
+                if (a.dbg != nullptr && tid == 0 && l == a.L / 2) {
+                    long long t1c;
+                    unsigned int smid;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1c));
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    a.dbg[64 + cta * 4] = t0c; a.dbg[64 + cta * 4 + 1] = t1c; a.dbg[64 + cta * 4 + 2] = smid; a.dbg[64 + cta * 4 + 3] = nslots;
+                }
                 stamp(l);
-                for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                    const float g = row_sum(s, 2 * e), u = row_sum(s, 2 * e + 1);
+                for (int e = tid; e < nslots * (kPkBlockRows / 2); e += kPkConsumers) {
+                    const float g = row_sum(2 * e), u = row_sum(2 * e + 1);
                     const float av = g / (1.f + expf(-g)) * u;
                     uint16_t ah, al;
                     split_hi_lo(av, ah, al);
-                    a.xhl[2 * nq + (s.row_begin >> 1) + e] = ah;
-                    a.xhl[2 * nq + a.I + (s.row_begin >> 1) + e] = al;
+                    const int aj = grow(2 * e) >> 1;
+                    a.xhl[2 * nq + aj] = ah;
+                    a.xhl[2 * nq + a.I + aj] = al;
                 }
             }
             stamp(l);
             pk_grid_barrier(a.gbar, epoch, tid);
+            if (cta == 0 && tid == 0 && a.pool != nullptr) atomicExch(a.pool + (4 * l + 2), 0u);      // every producer is past this phase: re-arm its pool
             stamp(l);
 
             // ---------------- P5: down_proj + residual add ----------------
             load_x_plain(a.xhl + 2 * nq, a.I);
             stamp(l);
             {
-                const PkSlice s = consume(a.H, a.I);
+                const int nslots = consume(a.I);
                 stamp(l);
                 if (a.tp > 1) {
-                    allreduce_resid_add(s);
+                    allreduce_resid_add(nslots);
                 } else {
-                    for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                        float2* p = reinterpret_cast<float2*>(a.resid + s.row_begin + 2 * e);
+                    for (int e = tid; e < nslots * (kPkBlockRows / 2); e += kPkConsumers) {
+                        float2* p = reinterpret_cast<float2*>(a.resid + grow(2 * e));
                         float2 v = __ldcg(p);
-                        v.x += row_sum(s, 2 * e);
-                        v.y += row_sum(s, 2 * e + 1);
+                        v.x += row_sum(2 * e);
+                        v.y += row_sum(2 * e + 1);
                         *p = v;
                     }
                 }
             }
             stamp(l);
             pk_grid_barrier(a.gbar, epoch, tid);
+            if (cta == 0 && tid == 0 && a.pool != nullptr) atomicExch(a.pool + (4 * l + 3), 0u);      // every producer is past this phase: re-arm its pool
             stamp(l);
         }
 
         // ---------------- final RMSNorm -> lm_head -> f32 logits + arg-max (last index wins ties) ----------------
         load_x_rmsnorm(a.resid, false, nullptr, a.final_norm, a.H, nullptr);
         {
-            const PkSlice s = consume(a.V, a.H);
+            const int nslots = consume(a.H);
             float bv = -INFINITY;
             int bi = -1;
-            for (int e = tid; e < (s.row_end - s.row_begin) / 2; e += kPkConsumers) {
-                const int ra = a.rank * a.V + s.row_begin + 2 * e;      // index in the FULL vocabulary (vocab-parallel head)
-                const float va = row_sum(s, 2 * e), vb = row_sum(s, 2 * e + 1);
+            for (int e = tid; e < nslots * (kPkBlockRows / 2); e += kPkConsumers) {
+                const int ra = a.rank * a.V + grow(2 * e);      // index in the FULL vocabulary (vocab-parallel head)
+                const float va = row_sum(2 * e), vb = row_sum(2 * e + 1);
                 if (a.tp > 1) {
                     for (int r = 0; r < a.tp; ++r) *reinterpret_cast<float2*>(a.peer_logits[r] + ra) = make_float2(va, vb);
                 } else {
@@ -864,6 +884,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             }
         }
         pk_grid_barrier(a.gbar, epoch, tid);
+        if (cta == 0 && tid == 0 && a.pool != nullptr) atomicExch(a.pool + (4 * a.L), 0u);      // every producer is past this phase: re-arm its pool
         if (a.tp > 1) ar_epoch += 1;      // the arg-max exchange below is exchange number 2L+1 of the step (uniform in every thread)
         if (cta == 0 && warp == 0) {
             float bv = -INFINITY;

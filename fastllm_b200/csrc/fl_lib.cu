@@ -583,15 +583,20 @@ static void plan_persistent(fl_cache& c) {
     if (!(w.d == 64 || w.d == 128)) return;
     if (w.H < 2048 || nq < 256 || w.I < 256) return;        // small models stay on the multi-kernel path
     // MMA weight stream: row slices in units of 8 rows, k-steps of 16 columns; the RMSNorm prologue keeps a row in registers
-    if (w.pk_tmaps.p == nullptr || w.nqkv % 8 || w.V % 8 || w.H > kPkMaxNormK) return;
+    // whole 16-row blocks in every phase; the RMSNorm prologue keeps a row in registers
+    if (w.pk_tmaps.p == nullptr || w.nqkv % 16 || w.H % 16 || (2 * w.I) % 16 || w.V % 16 || w.H > kPkMaxNormK) return;
     // x_hi / x_lo are zero-padded to whole 1024-column chunks (the weight tail of the last chunk is zero-filled by TMA)
     int kmax = (std::max(w.H, std::max(nq, w.I)) + kPkChunkCols - 1) / kPkChunkCols * kPkChunkCols;
     // attention scratch in the same region: [lane groups = 8 warps * 32/(d/8)][4 heads][d] + (m, l) pairs = 8192 + 512 floats,
     // and the split-merge weights [8][nsplit] + 8
     p.xs_floats = (int)align_up((size_t)std::max(std::max(kmax + 16, 8192 + 512), 8 * kNumSMs + 16), 4);
-    int rows = 0;
-    for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) rows = std::max(rows, 8 * ((N / 8 + kNumSMs - 1) / kNumSMs + 1));
-    p.partial_rows = (rows + kPkBlockRows - 1) / kPkBlockRows * kPkBlockRows;      // whole 16-row blocks
+    int slots = 0;      // blocks one CTA can process in a phase: its static share + the pool cap (see pk_split)
+    for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) {
+        const int nblk = N / kPkBlockRows;
+        slots = std::max(slots, w.tp == 1 ? nblk / kNumSMs + kPkPoolCap : (nblk + kNumSMs - 1) / kNumSMs + 1);
+    }
+    if (slots > kPkMaxSlots) return;
+    p.partial_rows = slots * kPkBlockRows;
     const size_t fixed = (size_t)p.xs_floats * 4 + (size_t)p.partial_rows * kPkConsumerWarps * 4 + (size_t)kAttnMaxRep * kKvPage * 4 + 64 * 4;
     const size_t avail = 232448 - 2048;   // 227 KB opt-in limit minus static shared memory and slack
     if (fixed + 2 * (size_t)kPkStageBytes > avail) return;
@@ -629,6 +634,12 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     a.xhl = c.pk_xhl.p;
     a.kcap = (std::max(w.H, std::max(w.nh * w.d, w.I)) + kPkChunkCols - 1) / kPkChunkCols * kPkChunkCols;
     a.tmaps = w.pk_tmaps.p;
+    if (c.pk_pool.p == nullptr) c.pk_pool.alloc(4 * (size_t)w.L + 1, true);
+    a.pool = c.pk_pool.p;
+    {
+        const char* sn = std::getenv("FL_PK_STATIC");      // dev knob: static share of the blocks in 32nds
+        a.static_num = sn ? std::max(0, std::min(32, std::atoi(sn))) : kPkStaticNum;
+    }
     a.tp = w.tp; a.rank = w.rank;
     if (w.tp > 1) {
         for (int r = 0; r < w.tp; ++r) {
@@ -650,7 +661,7 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     }
     static long long* dbg_buf = nullptr;
     const bool dbg = env_flag("FL_PK_DEBUG");
-    if (dbg && !dbg_buf) FL_CUDA(cudaMalloc(&dbg_buf, 64 * sizeof(long long)));
+    if (dbg && !dbg_buf) FL_CUDA(cudaMalloc(&dbg_buf, (64 + 4 * kNumSMs) * sizeof(long long)));
     a.dbg = dbg ? dbg_buf : nullptr;
     FL_CUDA(cudaMemsetAsync(c.gbar.p, 0, sizeof(unsigned int), c.stream));
     void* params[] = {&a};
@@ -683,6 +694,15 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
         fprintf(stderr, "[FL_PK_DEBUG] layer %d, CTA 0 phase times (us):", w.L / 2);
         for (int i = 0; i < 18; ++i) fprintf(stderr, " %s=%.2f;", names[i], (h[i + 1] - h[i]) / 1000.0);
         fprintf(stderr, " layer total=%.2f\n", (h[18] - h[0]) / 1000.0);
+        if (env_flag("FL_PK_DEBUG_CTAS")) {      // per-CTA start / end of the gate|up weight phase: who is the barrier waiting for?
+            std::vector<long long> pc(4 * kNumSMs);
+            FL_CUDA(cudaMemcpy(pc.data(), dbg_buf + 64, pc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            long long tmin = pc[0];
+            for (int i = 0; i < kNumSMs; ++i) tmin = std::min(tmin, pc[4 * i]);
+            for (int i = 0; i < kNumSMs; ++i)
+                fprintf(stderr, "[FL_PK_CTA] cta %d sm %lld chunks %lld start %.2f end %.2f\n", i, pc[4 * i + 2], pc[4 * i + 3], (pc[4 * i] - tmin) / 1000.0,
+                        (pc[4 * i + 1] - tmin) / 1000.0);
+        }
     }
 }
 

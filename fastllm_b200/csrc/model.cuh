@@ -126,6 +126,7 @@ struct fl_cache {
     fl::PkPlan pk;
     fl::DenseWs dw;
     fl::DevBuf<unsigned int> gbar;
+    fl::DevBuf<unsigned int> pk_pool;  // persistent decode kernel: ticket counters of the per-phase dynamic block pools
     fl::DevBuf<uint16_t> pk_xhl;    // persistent decode kernel: hi/lo bf16 hand-over of attn_out and the MLP activation
     fl::DevBuf<float> resid2;        // second residual buffer (tp > 1: the fused residual-add prologue ping-pongs)
     fl::DevBuf<float> tp_buf;        // [rows, H] partial o_proj / down_proj outputs awaiting the all-reduce (tp > 1)

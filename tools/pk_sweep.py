@@ -19,5 +19,5 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
 else:
     for spec in sys.argv[1:] or ["0", "128", "256", "384", "512", "768"]:
         la, _, flags = spec.partition(":")
-        env = dict(os.environ, FL_PK_LOOKAHEAD_KB=la, FL_PK_FLAGS=flags or "0")
+        env = dict(os.environ, FL_PK_LOOKAHEAD_KB=la, FL_PK_FLAGS=flags or "0", FL_PK_STATIC=os.environ.get("FL_PK_STATIC", "27"))
         subprocess.run([sys.executable, __file__, "child"], env=env)
