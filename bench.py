@@ -59,9 +59,9 @@ def peaks(kind="hbm"):
 
 def ncu_traffic_per_step():
     """DRAM bytes per decode step of decode_persistent_kernel from the committed `ncu --set full` capture
-    (profiles/r01_persistent_full_raw.csv: one launch of 3 steps, Mistral-7B b=1, KV 2048); None if unavailable."""
+    (profiles/r01_persistent_final_full_raw.csv: one launch of 8 steps, Mistral-7B b=1, KV 2048); None if unavailable."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01_persistent_full_raw.csv")
+    p = os.path.join(ROOT, "profiles", "r01_persistent_final_full_raw.csv")
     try:
         rows = list(csv.reader(open(p)))
         hdr, units, r = rows[0], rows[1], rows[2]
@@ -70,7 +70,7 @@ def ncu_traffic_per_step():
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             tot += float(r[i]) * scale[units[i]]
-        return tot / 3.0
+        return tot / 8.0
     except Exception:
         return None
 
