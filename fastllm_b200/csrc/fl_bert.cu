@@ -28,6 +28,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D bf16 tensor [rows, cols] row-major (row stride ld elements), box [box_rows, 64 cols], 128-byte swizzle.
+// Output-tile width of the encoder GEMMs.  With hidden = 384 every GEMM of the model has K-major operands of equal depth, so a
+// 128 x BN tile moves (128 + BN) * K * 2 bytes from L2 for 2 * 128 * BN * K FLOP: 64 FLOP/B at BN = 128 -- L2->SM bound
+// (~7 TB/s chip-wide => ~450 TFLOP/s) long before the tensor pipe.  BN = 192 divides all three widths (1152, 384, 1536), lifts
+// the intensity to 77 FLOP/B and still fits two TMEM accumulator stages (2 x 256 columns).
+constexpr int kBertBN = 192;
+
 CUtensorMap make_tmap_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     CUtensorMap m;
     const cuuint64_t dims[2] = {cols, rows};
@@ -60,7 +66,7 @@ CUtensorMap make_tmap_pk(const void* ptr, uint64_t N, uint64_t K) {
 
 template <int EPI>
 static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
-    constexpr int BN = 128;
+    constexpr int BN = kBertBN;
     const size_t smem = gemm_smem_bytes(BN, DUAL_NONE);
     static bool attr_set = false;
     if (!attr_set) {
@@ -213,10 +219,10 @@ void bert_finalize(BertModel& m) {
     FL_CHECK(!m.finalized, FL_ERR_STATE, "model already finalized");
     for (const std::string& n : bert_expected(m)) FL_CHECK(m.have.count(n), FL_ERR_STATE, "missing tensor: " + n);
     for (BertLayerW& w : m.layers) {   // weight-side TMA descriptors ([out, in] row-major == K-major B operand)
-        w.tm_wqkv = make_tmap_bf16(w.wqkv, 3 * m.H, m.H, m.H, 128);
-        w.tm_wo = make_tmap_bf16(w.wo, m.H, m.H, m.H, 128);
-        w.tm_wi = make_tmap_bf16(w.wi, m.I, m.H, m.H, 128);
-        w.tm_wo2 = make_tmap_bf16(w.wo2, m.H, m.I, m.I, 128);
+        w.tm_wqkv = make_tmap_bf16(w.wqkv, 3 * m.H, m.H, m.H, kBertBN);
+        w.tm_wo = make_tmap_bf16(w.wo, m.H, m.H, m.H, kBertBN);
+        w.tm_wi = make_tmap_bf16(w.wi, m.I, m.H, m.H, kBertBN);
+        w.tm_wo2 = make_tmap_bf16(w.wo2, m.H, m.I, m.I, kBertBN);
     }
     m.finalized = true;
 }

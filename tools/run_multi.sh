@@ -17,4 +17,4 @@ run mistral_b1 --steps 128 --warmup 8
 run qwen_prefill --workload qwen25_7b_prefill4k --steps 4
 run qwen_b1 --workload qwen25_7b_b1 --steps 128
 run mixtral_b32 --workload mixtral8x7b_b32 --steps 32 --warmup 4
-run minilm --workload minilm_256x128 --steps 20
+[ "$N" -lt 8 ] && run minilm --workload minilm_256x128 --steps 20
