@@ -3,11 +3,11 @@
 // Mistral-7B is five kernels of 5-36 us of HBM time each, and launch/ramp/tail costs as much as the streaming.
 //
 //   * grid = one CTA per SM (148), all resident (cooperative launch), 8 consumer warps + 1 producer warp.
-//   * WEIGHT STREAM: the producer thread walks the step's static schedule -- for every layer, for every GEMV phase, this
-//     CTA's contiguous row slice of the weight matrix, cut into <=32 KB row-aligned chunks -- and keeps a ring of
-//     shared-memory stages full with cp.async.bulk (TMA engine) + mbarrier.  The stream is decoupled from the compute
-//     phases: while consumers sit in a grid barrier, an epilogue or the attention phase, the ring is already filling with
-//     the NEXT phase's weights, so HBM keeps streaming across phase boundaries.
+//   * WEIGHT STREAM: the producer thread feeds a ring of shared-memory stages with the weight chunks this CTA will consume
+//     -- per phase its static share of 16-row blocks, then blocks drawn from the phase's ticketed pool -- one 3-D TMA
+//     request (32 KB, swizzled) per chunk, completion on the stage's mbarrier, plus a small per-stage message telling the
+//     consumers which block / chunk arrived.  The stream is decoupled from the compute phases: while consumers sit in a
+//     grid barrier, an epilogue or the attention phase, the ring is already filling with the NEXT phase's weights.
 //   * consumers: a chunk is a 16-row x 1024-column block of the weight matrix: ONE 3-D TMA request that lands as
 //     [column block][row][128 B] with the 128-byte swizzle keyed by the row (bank-conflict-free ldmatrix).  The 8 warps split its 64 k-steps; each k-step is ONE mma.sync m16n8k16: A = the bf16 weight tile
 //     straight from shared memory (ldmatrix, no unpack instructions), B = the activation vector split hi + lo into two bf16
@@ -102,8 +102,7 @@ struct PkArgs {
     float* peer_logits[8];           // rank r's full-vocabulary logits [Vfull]
     unsigned int ar_epoch0;          // exchanges completed on this communicator before this launch
     int* comm_err;                   // set to 1 when a peer did not show up within the spin budget
-    int flags;            // bit 0: prefetch this CTA's KV pages into L2 at the top of P1
-    int lookahead_bytes;  // how far (per CTA) the producer prefetches into L2 beyond the shared-memory ring
+    int flags;            // dev knob (FL_PK_FLAGS) bit 0: prefetch this CTA's KV pages into L2 at the top of P1
     long long* dbg;       // optional: CTA 0 writes %globaltimer at the phase boundaries of layer L/2 (FL_PK_DEBUG=1)
 };
 
@@ -154,34 +153,15 @@ __device__ __forceinline__ uint4 ldcg_u4(const void* p) {
     return r;
 }
 
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
-
-// L2 eviction-priority hints for the weight stream.  Weights are read exactly once per step, and the L2 lookahead cursor runs
-// ahead of the demand loads: under the default (LRU-like) policy the OLDEST lines in L2 are the prefetched-but-not-yet-consumed
-// ones, so a deep lookahead evicts exactly the lines it is about to need (measured: 512 KB/CTA lookahead = 1.5x the HBM traffic).
-// Demand loads therefore carry evict_first (the line is dead once it is in shared memory) and prefetches evict_last.
+// L2 eviction-priority hint of the weight stream: weights are read exactly once per step and are dead once they are in shared
+// memory, so the demand loads carry evict_first and leave the L2 to the KV cache and the activations.  (An L2 lookahead
+// cursor ahead of the ring was measured and removed: it cannot buy bandwidth -- the L2->SM delivery rate is the limit -- and
+// deep lookahead makes the prefetched-but-unused lines the oldest in an LRU-like L2: 512 KB/CTA = 1.13x the HBM traffic.)
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ void prefetch_l2_bulk_hint(const void* gsrc, uint32_t bytes, uint64_t policy) {
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(gsrc), "r"(bytes), "l"(policy) : "memory");
-}
-
 // Weight matrix of global phase g of a step: g = 4*layer + {0:qkv, 1:o, 2:gate|up, 3:down}, g = 4*L: lm_head.
 __device__ __forceinline__ void pk_phase(const PkArgs& a, int g, const uint16_t*& W, int& N, int& K) {
     if (g == 4 * a.L) { W = a.lm_head; N = a.V; K = a.H; return; }

@@ -654,8 +654,6 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
         g_peer.ar_epoch += (unsigned int)nsteps * (2u * (unsigned int)w.L + 1u);
     }
     {
-        const char* la = std::getenv("FL_PK_LOOKAHEAD_KB");
-        a.lookahead_bytes = (la ? std::atoi(la) : 128) * 1024;
         const char* fl = std::getenv("FL_PK_FLAGS");
         a.flags = fl ? std::atoi(fl) : 0;
     }

@@ -55,3 +55,25 @@ def test_tp2_matches_tp1(tmp_path):
     assert np.abs(np.array(one["logits"]) - np.array(two["logits"])).max() < 3e-3
     assert np.abs(np.array(one["synth_logits"]) - np.array(two["synth_logits"])).max() < 3e-3
     assert np.abs(np.array(one["batch3"]) - np.array(two["batch3"])).max() < 3e-3
+
+
+def test_head_layout_more_ranks_than_kv_heads():
+    """tp.head_layout (the Python statement of build_weights in csrc/fl_lib.cu): Qwen2.5-7B (28 q / 4 kv heads) at TP-8 replicates each
+    kv head on two ranks and deals its 7 query heads 4 + 3 (+1 zero head); every q head is owned exactly once; Mistral-7B at TP-8
+    is the plain split."""
+    from fastllm_b200 import tp
+    owned = []
+    for r in range(8):
+        q0, qn, nhl, k0, kn = tp.head_layout(28, 4, r, 8)
+        assert (nhl, kn, k0) == (4, 1, r // 2) and qn == (4 if r % 2 == 0 else 3)
+        assert all(h // 7 == k0 for h in range(q0, q0 + qn))          # a rank's q heads belong to its kv head's group
+        owned += list(range(q0, q0 + qn))
+    assert sorted(owned) == list(range(28))
+    assert [tp.head_layout(32, 8, r, 8) for r in range(8)] == [(4 * r, 4, 4, r, 1) for r in range(8)]
+    w = {"model.layers.0.self_attn.q_proj.weight": np.zeros((28 * 128, 64), np.float32),
+         "model.layers.0.self_attn.k_proj.weight": np.zeros((4 * 128, 64), np.float32),
+         "model.layers.0.self_attn.o_proj.weight": np.zeros((64, 28 * 128), np.float32)}
+    sh = tp.shard_weights(w, 28, 4, 3, 8)      # rank 3: kv head 1, q heads 11..13
+    assert sh["model.layers.0.self_attn.q_proj.weight"].shape == (3 * 128, 64)
+    assert sh["model.layers.0.self_attn.k_proj.weight"].shape == (128, 64)
+    assert sh["model.layers.0.self_attn.o_proj.weight"].shape == (64, 3 * 128)

@@ -1,4 +1,5 @@
-"""Dev tool: time the persistent decode kernel (Mistral-7B b=1, KV 2048) under different FL_PK_LOOKAHEAD_KB values."""
+"""Dev tool: time the persistent decode kernel (FL_MODEL, default Mistral-7B; b=1, KV FL_CTX) under different dev knobs.
+usage: pk_sweep.py [static_share_in_32nds[:flags]] ...   (FL_PK_STATIC / FL_PK_FLAGS)"""
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -15,9 +16,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         cache.fill_synthetic(1, ctx)
         _, ms = cache.decode_greedy_loop(first, ctx, 64)
         best = min(best, ms / 64)
-    print(f"lookahead={os.environ.get('FL_PK_LOOKAHEAD_KB')}KB flags={os.environ.get('FL_PK_FLAGS')}  ms/step={best:.4f}  tok/s={1000/best:.1f}")
+    print(f"static={os.environ.get('FL_PK_STATIC')}/32 flags={os.environ.get('FL_PK_FLAGS')}  ms/step={best:.4f}  tok/s={1000/best:.1f}")
 else:
-    for spec in sys.argv[1:] or ["0", "128", "256", "384", "512", "768"]:
-        la, _, flags = spec.partition(":")
-        env = dict(os.environ, FL_PK_LOOKAHEAD_KB=la, FL_PK_FLAGS=flags or "0", FL_PK_STATIC=os.environ.get("FL_PK_STATIC", "27"))
+    for spec in sys.argv[1:] or ["30"]:
+        st, _, flags = spec.partition(":")
+        env = dict(os.environ, FL_PK_STATIC=st, FL_PK_FLAGS=flags or "0")
         subprocess.run([sys.executable, __file__, "child"], env=env)
