@@ -235,12 +235,12 @@ static __global__ void moe_accum_kernel(const float* __restrict__ y, int nsl, lo
 
 // arg-max over the vocabulary, one CTA per row, last index wins ties (candle LogitsProcessor::sample_argmax)
 // (also folds the split-K slices of the lm_head GEMM into the f32 logits buffer the caller reads)
-static __global__ void __launch_bounds__(256) dense_argmax_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int V,
+static __global__ void __launch_bounds__(1024) dense_argmax_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int V,
                                                                   float* __restrict__ logits, uint32_t* __restrict__ next_ids) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float sv[8];
-    __shared__ int si[8];
+    __shared__ float sv[32];
+    __shared__ int si[32];
     float* l = logits + (size_t)blockIdx.x * V;
     float v = -INFINITY;
     int idx = -1;
@@ -259,7 +259,7 @@ static __global__ void __launch_bounds__(256) dense_argmax_kernel(const float* _
     if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
             if (sv[w] > v || (sv[w] == v && si[w] > idx)) { v = sv[w]; idx = si[w]; }
         next_ids[blockIdx.x] = (uint32_t)idx;
     }

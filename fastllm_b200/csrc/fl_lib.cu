@@ -888,7 +888,7 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
     if (w.tp > 1) {   // gather the vocab slices of every rank, lay them out as [b, Vfull], arg-max (last index wins ties)
         tp_allgather(lc, c.tp_local.p, c.tp_gather.p, (size_t)b * w.V);
         launch(lc, "tp_logits", 0, tp_logits_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)c.tp_gather.p, w.tp, b, w.V, c.logits.p);
-        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)c.logits.p, 1, (long long)0, w.Vfull,
+        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(1024), 0, (const float*)c.logits.p, 1, (long long)0, w.Vfull,
                c.logits.p, c.next_ids.p);
     }
     launch(lc, "advance_state", 0, advance_state_kernel, dim3(1), dim3(kMaxBatch), 0, c.state.p, b, t, loop_mode ? 1 : 0, c.ids.p,
@@ -1073,9 +1073,12 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             at.sliding_window = windowed ? w.cfg.sliding_window : 0; at.qscale = qscale;
             const uint64_t kv_bytes = (uint64_t)b * (c.kv_len + t) * w.nkv * w.d * 4;
             if (t == 1) {
-                // ~4 waves of 3 resident CTAs per SM; a split streams at least one 64-token page
+                // 3 CTAs are resident per SM.  Few (sequence, kv head) pairs: ONE wave, as many splits as fit (every CTA pays the
+                // same load -> softmax -> merge latency chain once; a second, mostly empty wave would double it).  Many pairs:
+                // ~4 waves so the tail is short.  A split streams at least one 64-token page.
                 const int npages = (c.kv_len + t + kKvPage - 1) / kKvPage;
-                const int want = (12 * kNumSMs + b * w.nkv - 1) / (b * w.nkv);
+                const int pairs = b * w.nkv, slots = 3 * kNumSMs;
+                const int want = pairs <= slots ? slots / pairs : (4 * slots + pairs - 1) / pairs;
                 const int nsp = std::max(1, std::min(std::min(c.nsplit, npages), want));
                 launch_attn_mma(lc, w.d, true, dim3(nsp, w.nkv, b), kv_bytes, at);
             } else {
@@ -1166,10 +1169,10 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                c.tp_local.p);
         tp_allgather(lc, c.tp_local.p, c.tp_gather.p, (size_t)b * w.V);
         launch(lc, "tp_logits", 0, tp_logits_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)c.tp_gather.p, w.tp, b, w.V, c.logits.p);
-        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)c.logits.p, 1, (long long)0, w.Vfull, c.logits.p,
+        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(1024), 0, (const float*)c.logits.p, 1, (long long)0, w.Vfull, c.logits.p,
                c.next_ids.p);
     } else {
-        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(256), 0, (const float*)d.y.p, ksh, (long long)b * w.V, w.V, c.logits.p,
+        launch(lc, "dense_argmax", 0, dense_argmax_kernel, dim3(b), dim3(1024), 0, (const float*)d.y.p, ksh, (long long)b * w.V, w.V, c.logits.p,
                c.next_ids.p);
     }
     launch(lc, "advance_state", 0, advance_state_kernel, dim3(1), dim3(kMaxBatch), 0, c.state.p, b, t, loop_mode ? 1 : 0, c.ids.p,
