@@ -662,6 +662,7 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     if (dbg && !dbg_buf) FL_CUDA(cudaMalloc(&dbg_buf, (64 + 4 * kNumSMs) * sizeof(long long)));
     a.dbg = dbg ? dbg_buf : nullptr;
     FL_CUDA(cudaMemsetAsync(c.gbar.p, 0, sizeof(unsigned int), c.stream));
+    FL_CUDA(cudaMemsetAsync(c.pk_pool.p, 0, (4 * (size_t)w.L + 1) * sizeof(unsigned int), c.stream));   // the kernel re-arms them itself; this covers an aborted launch
     void* params[] = {&a};
     const void* fn = (w.d == 64) ? (const void*)decode_persistent_kernel<64> : (const void*)decode_persistent_kernel<128>;
     ProfEntry pe;
@@ -929,7 +930,7 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
         for (size_t r = 1; r <= std::min<size_t>(R, kMaxBatch); ++r) consider(r, w.V, w.H);     // the lm_head runs on one row per sequence
         d.y.alloc(need);
     }
-    d.resid.alloc(R * w.H); d.q.alloc(R * nq); d.attn.alloc(R * nq);
+    d.resid.alloc(R * w.H); d.q.alloc(R * nq);      // the attention output goes straight into xhi / xlo (hi/lo operand of o_proj)
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
     if (w.cfg.arch != FL_ARCH_MIXTRAL && R > 128) { d.xhi2.alloc(R * (size_t)w.I); d.xlo2.alloc(R * (size_t)w.I); }
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {

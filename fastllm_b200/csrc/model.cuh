@@ -75,7 +75,7 @@ struct DenseWs {
     int chunk = 0;              // attention rows per launch
     DevBuf<uint16_t> xhi, xlo;  // [rows, Kmax] hi/lo bf16 split of the activations fed to the next GEMM
     DevBuf<float> y;            // [rows, Nmax] GEMM output
-    DevBuf<float> resid, q, attn;
+    DevBuf<float> resid, q;
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
     DevBuf<float> moe_out, route_w;
