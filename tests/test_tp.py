@@ -21,7 +21,8 @@ def _run(mode, nproc, out, port):
 
 def test_tp_sharding_scheme_gloo_world2(tmp_path):
     """Column-parallel gate/up + row-parallel down with an all-reduce, vocab-parallel head with an all-gather, q/k/v split by
-    head: same numbers as the unsharded oracle (numpy over gloo, 2 processes)."""
+    head (incl. replicated kv head + padded query heads), and the Mixtral expert-parallel dispatch / combine data flow with
+    data-parallel rows: same numbers as the unsharded oracle (numpy over gloo, 2 processes)."""
     assert _run("cpu", 2, str(tmp_path / "cpu.json"), 29631)["ok"]
 
 

@@ -151,6 +151,40 @@ def cpu_main(out_path):
     part_a = torch.from_numpy(attn_block(qs, qn, kn))
     dist.all_reduce(part_a)
     ok = ok and bool(np.abs(part_a.numpy() - attn_block(qw, nh, nkv)).max() < 1e-4)
+    # Mixtral expert parallelism with data-parallel attention (fl_config.ep_dp_attention): every rank owns a slice of the rows and
+    # E / world experts.  DISPATCH: the rows (+ their routing weights) travel to every expert rank; every rank runs its experts over
+    # ALL rows with the masked routing weight (zero when the expert was not selected); COMBINE: the partial outputs of rank p's rows
+    # travel back to rank p, which sums them in rank order.  Must equal the oracle's sparse-MoE block on the owner's rows.
+    from oracle import mixtral as omix
+    mcfg, mw, _ = golden_weights("mixtral")
+    E, topk = mcfg.num_local_experts, mcfg.num_experts_per_tok
+    pm = "model.layers.0.block_sparse_moe."
+    xm = np.random.default_rng(2).standard_normal((4 * world, mcfg.hidden_size)).astype(np.float32)
+    per = xm.shape[0] // world
+    mine = xm[rank * per:(rank + 1) * per]
+    idx, wts = omix.route_top_k(ops.linear(mine, mw[pm + "gate.weight"]), topk)
+    route = np.zeros((per, E), dtype=np.float32)
+    for r_ in range(per):
+        route[r_, idx[r_]] = wts[r_]
+    g_rows = [torch.empty(per, mcfg.hidden_size) for _ in range(world)]
+    g_route = [torch.empty(per, E) for _ in range(world)]
+    dist.all_gather(g_rows, torch.from_numpy(np.ascontiguousarray(mine)))          # dispatch (every rank receives every block)
+    dist.all_gather(g_route, torch.from_numpy(route))
+    rows_all = np.concatenate([t.numpy() for t in g_rows]); route_all = np.concatenate([t.numpy() for t in g_route])
+    e_local = E // world
+    part = np.zeros_like(rows_all)
+    for e in range(rank * e_local, (rank + 1) * e_local):
+        w1, w2, w3 = (mw[pm + f"experts.{e}.{n}.weight"] for n in ("w1", "w2", "w3"))
+        y = ops.linear(ops.silu(ops.linear(rows_all, w1)) * ops.linear(rows_all, w3), w2)
+        part += route_all[:, e:e + 1] * y
+    back = [torch.empty(world * per, mcfg.hidden_size) for _ in range(world)]
+    dist.all_gather(back, torch.from_numpy(part))                                   # combine: keep block `rank` of every source
+    combined = np.zeros((per, mcfg.hidden_size), dtype=np.float32)
+    for src in range(world):                                                        # fixed rank order
+        combined += back[src].numpy()[rank * per:(rank + 1) * per]
+    experts = [(mw[pm + f"experts.{e}.w1.weight"], mw[pm + f"experts.{e}.w2.weight"], mw[pm + f"experts.{e}.w3.weight"]) for e in range(E)]
+    want = omix.sparse_moe_block(mine[None], mw[pm + "gate.weight"], experts, topk)[0]
+    ok = ok and bool(np.abs(combined - want).max() < 1e-4)
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:
