@@ -52,6 +52,11 @@ SYMBOLS = {
     "fl_forward": (_I, [_VP, _VP, _VP, _I, _I, _SZ, _VP]),
     "fl_forward_greedy": (_I, [_VP, _VP, _VP, _I, _I, _SZ, _VP]),
     "fl_decode_greedy_loop": (_I, [_VP, _VP, _VP, _I, _SZ, _I, _VP, C.POINTER(C.c_float)]),
+    "fl_sampler_create": (_I, [_U64, C.c_double, C.POINTER(_VP)]),
+    "fl_sampler_sample": (_I, [_VP, _VP, _SZ, C.POINTER(C.c_uint32)]),
+    "fl_sampler_next_u32": (_I, [_VP, C.POINTER(C.c_uint32)]),
+    "fl_sampler_destroy": (_I, [_VP]),
+    "fl_forward_sample": (_I, [_VP, _VP, _VP, _I, _I, _SZ, _VP, C.POINTER(C.c_uint32)]),
     "fl_embed": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
     "fl_embed_timed": (_I, [_VP, _VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_float)]),
     "fl_comm_unique_id": (_I, [_VP]),

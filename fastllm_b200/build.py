@@ -18,7 +18,7 @@ def _newest_source_mtime() -> float:
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for dp, _, fs in os.walk(root):
             for f in fs:
-                if f.endswith((".cu", ".cuh", ".h")):
+                if f.endswith((".cu", ".cuh", ".h", ".hpp")):
                     m = max(m, os.path.getmtime(os.path.join(dp, f)))
     return m
 

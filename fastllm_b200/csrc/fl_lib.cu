@@ -12,6 +12,7 @@
 #include "elementwise.cuh"
 #include "gemv.cuh"
 #include "model.cuh"
+#include "sampler.hpp"
 #include "synth.cuh"
 
 namespace fl {
@@ -1538,6 +1539,69 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
         cudaEventDestroy(e1);
         if (elapsed_ms) *elapsed_ms = ms;
         if (out_ids) FL_CUDA(cudaMemcpy(out_ids, c->trace.p, (size_t)steps * b * 4, cudaMemcpyDeviceToHost));
+    } catch (const fl::Error& e) {
+        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        throw;
+    }
+    FL_API_END
+}
+
+// ---- sampling (host code; the reference samples on the host from the logits of every forward, models/mod.rs:425-428) ----
+struct fl_sampler {
+    fl::LogitsProcessor lp;
+    fl_sampler(uint64_t seed, double temperature) : lp(seed, temperature) {}
+};
+
+FL_EXPORT int fl_sampler_create(uint64_t seed, double temperature, fl_sampler** out) {
+    FL_API_BEGIN
+    FL_CHECK(out, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(!std::isnan(temperature), FL_ERR_INVALID, "temperature is NaN");
+    *out = new fl_sampler(seed, temperature);
+    FL_API_END
+}
+
+FL_EXPORT int fl_sampler_sample(fl_sampler* s, const float* logits_host, size_t n, uint32_t* token) {
+    FL_API_BEGIN
+    FL_CHECK(s && logits_host && token, FL_ERR_INVALID, "NULL argument");
+    try {
+        *token = s->lp.sample(logits_host, n);
+    } catch (const fl::SamplerError& e) {
+        throw fl::Error(FL_ERR_INVALID, e.what());
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_sampler_next_u32(fl_sampler* s, uint32_t* out) {
+    FL_API_BEGIN
+    FL_CHECK(s && out, FL_ERR_INVALID, "NULL argument");
+    *out = s->lp.next_u32();
+    FL_API_END
+}
+
+FL_EXPORT int fl_sampler_destroy(fl_sampler* s) {
+    FL_API_BEGIN
+    delete s;
+    FL_API_END
+}
+
+FL_EXPORT int fl_forward_sample(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, fl_sampler* s,
+                                uint32_t* next_id) {
+    FL_API_BEGIN
+    FL_CHECK(m && c && s && next_id, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w != nullptr && m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    use_device();
+    try {
+        run_forward(*c, ids, b, t, rope_offset);
+        // only row 0 is sampled (logits.get(0)?.flatten_all()?, models/mod.rs:421): one V*4-byte read-back into the pinned staging row
+        const size_t n = c->w->Vfull;
+        FL_CUDA(cudaMemcpyAsync(c->h_logits.p, c->logits.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        FL_CUDA(cudaStreamSynchronize(c->stream));
+        check_peer_error();
+        try {
+            *next_id = s->lp.sample(c->h_logits.p, n);
+        } catch (const fl::SamplerError& e) {
+            throw fl::Error(FL_ERR_INVALID, e.what());
+        }
     } catch (const fl::Error& e) {
         if (e.code == FL_ERR_CUDA) c->poisoned = true;
         throw;

@@ -11,7 +11,7 @@ Reference interfaces mirrored (paths under /root/reference/src/models):
   LlamaWithConfig / LlamaCache                                       llama.rs:52-149
   MistralWithConfig / MistralCache                                   mistral.rs:16-236
   QwenWithConfig / QwenCache                                         qwen.rs:12-151
-  Model::generate (greedy path)                                      mod.rs:363-463
+  Model::generate + candle LogitsProcessor (arg-max / temperature)   mod.rs:363-463
 """
 from __future__ import annotations
 
@@ -120,6 +120,17 @@ class DeviceCache:
         _lib.check(self.lib.fl_forward_greedy(self.model.h, self.h, ids.ctypes.data_as(C.c_void_p), b, t, rope_offset,
                                               out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def forward_sample(self, ids: np.ndarray, rope_offset: int, logits_processor: "LogitsProcessor") -> int:
+        """fl_forward + LogitsProcessor::sample of row 0 in one call (one V*4-byte read-back, no logits array on this side)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if ids.ndim != 2:
+            raise FastllmError(-1, f"input must be [batch, seq], got shape {ids.shape}")
+        b, t = ids.shape
+        tok = C.c_uint32()
+        _lib.check(self.lib.fl_forward_sample(self.model.h, self.h, ids.ctypes.data_as(C.c_void_p), b, t, rope_offset,
+                                              logits_processor.h, C.byref(tok)))
+        return tok.value
 
     def decode_greedy_loop(self, first_ids: np.ndarray, rope_offset: int, steps: int):
         first = np.ascontiguousarray(first_ids, dtype=np.uint32).reshape(-1)
@@ -374,10 +385,47 @@ class MixtralWithConfig(MistralWithConfig):
         return _fl_config("mixtral", cf, 32768, cf.sliding_window if cf.sliding_window is not None else 4096, False)
 
 
+class LogitsProcessor:
+    """candle's LogitsProcessor as the reference builds it: LogitsProcessor::new(Default::default(), Some(temperature as f64),
+    None) (mod.rs:157-158, 373-374).  Temperature < 1e-7 => arg-max (IEEE total order, LAST index among equal maxima);
+    otherwise soft-max + WeightedIndex over StdRng::seed_from_u64(seed).  The arithmetic is the library's (fl_sampler_*,
+    csrc/sampler.hpp): host code, because the reference samples on the host from the logits every forward returns."""
+
+    def __init__(self, seed: int = 0, temperature: float | None = None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.fl_sampler_create(seed, -1.0 if temperature is None else float(temperature), C.byref(h)))
+        self.h = h
+
+    def sample(self, logits: np.ndarray) -> int:
+        v = np.ascontiguousarray(logits, dtype=np.float32).reshape(-1)       # logits.to_dtype(F32)
+        tok = C.c_uint32()
+        _lib.check(self.lib.fl_sampler_sample(self.h, v.ctypes.data_as(C.c_void_p), v.size, C.byref(tok)))
+        return tok.value
+
+    def next_u32(self) -> int:
+        w = C.c_uint32()
+        _lib.check(self.lib.fl_sampler_next_u32(self.h, C.byref(w)))
+        return w.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.fl_sampler_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 def sample_argmax(logits: np.ndarray) -> int:
     """LogitsProcessor::sample with temperature None/<1e-7: arg-max, LAST index among equal maxima (mod.rs:425-428)."""
-    v = np.asarray(logits, dtype=np.float32).reshape(-1)
-    return int(np.flatnonzero(v == v.max())[-1])
+    global _greedy
+    if _greedy is None:
+        _greedy = LogitsProcessor(0, None)      # arg-max never touches the generator: one shared instance
+    return _greedy.sample(logits)
+
+
+_greedy = None
 
 
 class Model:
@@ -387,9 +435,9 @@ class Model:
         self.model, self.cache, self.eos_token_id = model, cache, eos_token_id
 
     def generate(self, prompt_ids, max_tokens: int, temperature: float = 0.0, return_logits: bool = False):
-        if temperature >= 1e-7:
-            raise FastllmError(-5, "temperature sampling (candle WeightedIndex/StdRng) is SURVEY.md section 8f item 1, not built")
         self.cache = self.model.initialize_cache()                       # mod.rs:370
+        # mod.rs:373-374: seed Default::default() = 0, `temperature as f64` of the API's f32 (chat.rs:24-25 defaults it to 0.0)
+        logits_processor = LogitsProcessor(0, float(np.float32(temperature)))
         ids = np.asarray(prompt_ids, dtype=np.uint32).reshape(1, -1)    # mod.rs:386-394
         pos = 0
         logits = self.model.forward(ids, pos, self.cache)               # mod.rs:402-405
@@ -399,7 +447,7 @@ class Model:
             last = np.asarray(logits)[0].reshape(-1)                     # logits.get(0)?.flatten_all()?
             if return_logits:
                 trace.append(last.copy())
-            tok = sample_argmax(last)
+            tok = logits_processor.sample(last)                          # mod.rs:425-428
             if self.eos_token_id is not None and tok == self.eos_token_id:
                 break                                                    # EOS: break before emitting (mod.rs:431-436)
             out.append(tok)

@@ -7,7 +7,7 @@
 //   LlamaWithConfig / LlamaCache           src/models/llama.rs:52-160
 //   MistralWithConfig / MistralCache       src/models/mistral.rs:16-248
 //   QwenWithConfig / QwenCache             src/models/qwen.rs:12-186
-//   Model<M>::generate (greedy)            src/models/mod.rs:342-464
+//   Model<M>::generate + LogitsProcessor   src/models/mod.rs:342-464
 // INTEGRATION.md shows the Rust shim (a transliteration of this file) a maintainer would add.
 #pragma once
 #include <cstdint>
@@ -167,28 +167,37 @@ struct OffsetAdapter {
 using MistralWithConfig = OffsetAdapter<FL_ARCH_MISTRAL, MistralCache>;
 using QwenWithConfig = OffsetAdapter<FL_ARCH_QWEN2, QwenCache>;
 
-// LogitsProcessor::sample_argmax: max_by(total_cmp) => LAST index among equal maxima
-inline uint32_t sample_argmax(const float* v, int n) {
-    int best = 0;
-    for (int i = 1; i < n; ++i)
-        if (v[i] >= v[best]) best = i;
-    return (uint32_t)best;
-}
+// candle's LogitsProcessor as the generate loops build it (mod.rs:157-158, 373-374): LogitsProcessor::new(seed, Some(temperature),
+// None).  The arithmetic (arg-max in IEEE total order with the LAST maximum winning; soft-max + WeightedIndex over
+// StdRng::seed_from_u64) is the library's fl_sampler_*: host code, as in the reference.
+struct LogitsProcessor {
+    fl_sampler* h = nullptr;
+    LogitsProcessor(uint64_t seed, std::optional<double> temperature) { check(fl_sampler_create(seed, temperature.value_or(-1.0), &h)); }
+    ~LogitsProcessor() { if (h) fl_sampler_destroy(h); }
+    LogitsProcessor(const LogitsProcessor&) = delete;
+    LogitsProcessor& operator=(const LogitsProcessor&) = delete;
+    uint32_t sample(const float* logits, size_t n) {
+        uint32_t tok = 0;
+        check(fl_sampler_sample(h, logits, n, &tok));
+        return tok;
+    }
+};
 
-// ---- Model<M>::generate, temperature 0 (mod.rs:363-463), prompts already tokenised -------------------------------------
+// ---- Model<M>::generate (mod.rs:363-463), prompts already tokenised ----------------------------------------------------
 template <typename M>
 struct Model {
     M model;
     typename M::Cache cache;
     std::optional<uint32_t> eos_token_id = 2;   // tokenizer.token_to_id("</s>")
-    std::vector<uint32_t> generate(const std::vector<uint32_t>& prompt, int max_tokens) {
+    std::vector<uint32_t> generate(const std::vector<uint32_t>& prompt, int max_tokens, float temperature = 0.0f) {
         cache = M::initialize_cache(0);                                           // mod.rs:370
+        LogitsProcessor logits_processor(0, (double)temperature);                 // mod.rs:373-374
         size_t pos = 0;
         Logits logits = model.forward(prompt.data(), 1, (int)prompt.size(), pos, cache);   // mod.rs:402-405
         pos += prompt.size();
         std::vector<uint32_t> out;
         for (int i = 0; i < max_tokens; ++i) {                                    // mod.rs:411-453
-            const uint32_t tok = sample_argmax(logits.row(0), logits.vocab);
+            const uint32_t tok = logits_processor.sample(logits.row(0), (size_t)logits.vocab);   // logits.get(0)?.flatten_all()?
             if (eos_token_id && tok == *eos_token_id) break;                      // break BEFORE emitting
             out.push_back(tok);
             logits = model.forward(&tok, 1, 1, pos, cache);

@@ -1,5 +1,7 @@
 // Self-test of the C++ host mirror: builds a tiny synthetic Llama through the reference-shaped interface, runs
 // Model::generate, prints the greedy ids as JSON.  tests/test_host_cpp_gpu.py compares them with the oracle.
+// `host_selftest --sampler seed temperature vocab logits.bin` needs no GPU: it runs the mirror's LogitsProcessor over the f32 rows
+// of logits.bin and prints the sampled ids (tests/test_sampling_cpu.py compares them with the oracle).
 // Build: g++ -std=c++17 -O2 host/host_selftest.cpp -o host/_build/host_selftest -Lfastllm_b200 -lfastllm_b200 -Wl,-rpath,...
 #include <cstdio>
 #include <cstdlib>
@@ -8,6 +10,25 @@
 #include "fastllm_host.hpp"
 
 int main(int argc, char** argv) {
+    if (argc == 6 && std::strcmp(argv[1], "--sampler") == 0) {
+        try {
+            const uint64_t seed = std::strtoull(argv[2], nullptr, 10);
+            const double temperature = std::atof(argv[3]);
+            const size_t vocab = (size_t)std::strtoull(argv[4], nullptr, 10);
+            FILE* lf = std::fopen(argv[5], "rb");
+            if (!lf || vocab == 0) throw std::runtime_error("cannot open logits");
+            fastllm::LogitsProcessor lp(seed, temperature < 0 ? std::nullopt : std::optional<double>(temperature));
+            std::vector<float> row(vocab);
+            std::printf("[");
+            for (int i = 0; std::fread(row.data(), 4, vocab, lf) == vocab; ++i) std::printf("%s%u", i ? "," : "", lp.sample(row.data(), vocab));
+            std::printf("]\n");
+            std::fclose(lf);
+            return 0;
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "host_selftest --sampler failed: %s\n", e.what());
+            return 1;
+        }
+    }
     // argv: weights.bin (concatenated f32 tensors in manifest order), manifest.txt (name ndim dims...), prompt ids...
     if (argc < 4) { std::fprintf(stderr, "usage: host_selftest manifest.txt weights.bin max_tokens id...\n"); return 2; }
     try {

@@ -22,6 +22,12 @@
  *                                qwen.rs:123-145); returns the last-position logits as f32 [b, V]
  *   fl_forward_greedy         <- forward + LogitsProcessor arg-max of models/mod.rs:421-428 fused on device
  *                                (ties resolve to the LAST index, as candle's max_by(total_cmp) does)
+ *   fl_sampler_* / fl_forward_sample
+ *                             <- candle's LogitsProcessor as the generate loops build and call it:
+ *                                LogitsProcessor::new(Default::default(), Some(temperature as f64), None)
+ *                                models/mod.rs:157-158,373-374 and logits_processor.sample(&last_logits)
+ *                                models/mod.rs:308-310,425-428 (arg-max below 1e-7, else soft-max + WeightedIndex
+ *                                over rand 0.8's StdRng seeded with seed_from_u64)
  *   fl_embed                  <- EmbeddingModel::embed models/embeddings.rs:397-447 after tokenisation:
  *                                encoder forward + mean_pooling (:346-368) + normalize_l2 (:341-344)
  */
@@ -43,6 +49,7 @@ extern "C" {
 
 typedef struct fl_model fl_model;
 typedef struct fl_cache fl_cache;
+typedef struct fl_sampler fl_sampler;
 
 typedef enum fl_status {
     FL_OK = 0,
@@ -126,6 +133,19 @@ FL_EXPORT int fl_forward_greedy(fl_model* m, fl_cache* c, const uint32_t* ids, i
  * [steps, b] or NULL.  elapsed_ms: CUDA-event time of the whole loop on the cache's stream, or NULL. */
 FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* first_ids, int b, size_t rope_offset, int steps,
                           uint32_t* out_ids, float* elapsed_ms);
+
+/* ---- sampling (host arithmetic: the reference samples on the host from every forward's logits) --- */
+/* LogitsProcessor::new(seed, Some(temperature), None): temperature < 1e-7 => arg-max (IEEE total order, LAST index among
+ * equal maxima); otherwise softmax(logits * (1/T as f32)) with a sequential f32 denominator, then
+ * WeightedIndex<f32>::sample over StdRng::seed_from_u64(seed) (ChaCha12).  The reference always passes seed 0. */
+FL_EXPORT int fl_sampler_create(uint64_t seed, double temperature, fl_sampler** out);
+FL_EXPORT int fl_sampler_sample(fl_sampler* s, const float* logits_host, size_t n, uint32_t* token);
+FL_EXPORT int fl_sampler_next_u32(fl_sampler* s, uint32_t* out);  /* the generator's next raw word (known-answer tests) */
+FL_EXPORT int fl_sampler_destroy(fl_sampler* s);
+/* fl_forward, then sample row 0 of the logits (the generate loop only looks at logits.get(0), models/mod.rs:421); one
+ * vocab*4-byte read-back, no caller-side logits buffer.  next_id: host u32 [1]. */
+FL_EXPORT int fl_forward_sample(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, fl_sampler* s,
+                                uint32_t* next_id);
 
 /* ---- embeddings (BERT family) ------------------------------------------------------------------ */
 /* ids/mask: host u32 [b, t]; mask may be NULL (all ones).  out: host f32 [b, hidden], mean-pooled and L2-normalised. */

@@ -273,9 +273,12 @@ def sample_argmax(logits: np.ndarray) -> int:
     return int(np.flatnonzero(v == m)[-1])
 
 
-def generate(adapter, prompt_ids, max_tokens: int, eos_id: int | None = 2, return_logits: bool = False):
-    """Model::generate (mod.rs:363-463) with temperature 0 (arg-max): fresh cache, prefill [1, N] at pos 0, then
-    per step: logits.get(0).flatten_all -> arg-max -> break on EOS *before* emitting -> forward([1,1], pos); pos += 1."""
+def generate(adapter, prompt_ids, max_tokens: int, eos_id: int | None = 2, return_logits: bool = False, temperature: float = 0.0):
+    """Model::generate (mod.rs:363-463): fresh cache, LogitsProcessor::new(0, Some(temperature as f64), None) (arg-max below
+    1e-7, the API default), prefill [1, N] at pos 0, then per step: logits.get(0).flatten_all -> sample -> break on EOS
+    *before* emitting -> forward([1,1], pos); pos += 1."""
+    from .sampling import LogitsProcessor
+    logits_processor = LogitsProcessor(0, float(np.float32(temperature)))
     cache = adapter.initialize_cache()
     ids = np.asarray(prompt_ids, dtype=np.uint32).reshape(1, -1)
     pos = 0
@@ -285,7 +288,7 @@ def generate(adapter, prompt_ids, max_tokens: int, eos_id: int | None = 2, retur
     for _ in range(max_tokens):
         last = np.asarray(logits)[0].reshape(-1)
         all_logits.append(last.copy())
-        tok = sample_argmax(last)
+        tok = logits_processor.sample(last)
         if eos_id is not None and tok == eos_id:
             break
         out.append(tok)
