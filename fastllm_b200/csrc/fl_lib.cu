@@ -1307,8 +1307,8 @@ FL_EXPORT int fl_device_synchronize(void) {
 FL_EXPORT int fl_model_create(const fl_config* cfg, fl_model** out) {
     FL_API_BEGIN
     FL_CHECK(cfg != nullptr && out != nullptr, FL_ERR_INVALID, "NULL argument");
+    validate_config(*cfg);   // host logic first: the reference panics on a bad config before anything touches the device (mistral.rs:109-127)
     use_device();
-    validate_config(*cfg);
     if (cfg->arch == FL_ARCH_BERT) {
         auto bm = std::make_shared<BertModel>();
         bm->cfg = *cfg;
