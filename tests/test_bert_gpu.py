@@ -3,6 +3,8 @@
 Tolerance (north_star): cosine >= 0.999 per embedding; the path runs bf16 tensor-core inputs with f32 accumulation, so
 max-abs on the unit-norm embedding components is also held to 2e-2.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -90,3 +92,29 @@ def test_bert_errors():
         m.embed_ids(np.ones((1, 129), dtype=np.uint32))               # > 128 tokens: not built in this round
     with pytest.raises(FastllmError):
         models.MiniLMModel(models.BertConfig(96, 4, 1, 256, 64, 1e-12, 200), None)   # head_dim 24 unsupported
+
+
+# The reference's one numeric test (models/embeddings.rs:473-511).  It needs the real all-MiniLM-L6-v2 checkpoint, which the reference
+# downloads and this image cannot: opt-in through FASTLLM_MINILM_DIR = a directory holding model.safetensors, tokenizer.json
+# (+ config.json) of sentence-transformers/all-MiniLM-L6-v2.  Sentences and bands are the reference's, verbatim.
+SIMILARITY_BANDS = [
+    ("I really enjoyed the movie. It was a great film.", "The movie was excellent and I had a good time watching it.", 0.8, None),
+    ("I enjoy programming in Python because it's easy to read.", "Java is a popular programming language for enterprise applications.",
+     0.4, 0.8),
+    ("The recipe calls for two cups of flour and one cup of sugar.", "The Hubble telescope has captured stunning images of distant galaxies.",
+     None, 0.4),
+]
+
+
+@pytest.mark.skipif(not os.environ.get("FASTLLM_MINILM_DIR"), reason="opt-in: set FASTLLM_MINILM_DIR to a local all-MiniLM-L6-v2 checkout")
+def test_embedding_similarities():
+    from tokenizers import Tokenizer
+    from fastllm_b200 import models, safetensors_io
+    d = os.environ["FASTLLM_MINILM_DIR"]
+    tok = Tokenizer.from_file(os.path.join(d, "tokenizer.json"))
+    tensors = {n.removeprefix("bert."): a for n, a in safetensors_io.iter_tensors(d)}
+    m = models.MiniLMModel(models.BertConfig(vocab_size=tok.get_vocab_size(False)), tensors)      # embeddings.rs:301-306
+    ids = lambda s: np.asarray(tok.encode(s.lower(), add_special_tokens=True).ids, dtype=np.uint32)   # do_lower_case (:398-403)
+    for a, b, lo, hi in SIMILARITY_BANDS:
+        sim = m.compute_similarity(ids(a), ids(b))
+        assert (lo is None or sim > lo) and (hi is None or sim < hi), (a, b, sim)
