@@ -170,6 +170,7 @@ static std::vector<std::string> bert_expected(const BertModel& m) {
 static uint16_t h_bf16(float f) {
     uint32_t b;
     std::memcpy(&b, &f, 4);
+    if ((b & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((b >> 16) | 0x40u);   // NaN stays NaN (quiet), as half::bf16::from_f32 does
     return (uint16_t)((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
 }
 

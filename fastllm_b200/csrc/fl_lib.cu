@@ -29,6 +29,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static uint16_t host_f32_to_bf16(float f) {
     uint32_t b;
     std::memcpy(&b, &f, 4);
+    if ((b & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((b >> 16) | 0x40u);   // NaN stays NaN (quiet), as half::bf16::from_f32 does
     return (uint16_t)((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
 }
 static float host_f16_to_f32(uint16_t h) {
@@ -640,6 +641,13 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     {
         const char* sn = std::getenv("FL_PK_STATIC");      // dev knob: static share of the blocks in 32nds
         a.static_num = sn ? std::max(0, std::min(32, std::atoi(sn))) : kPkStaticNum;
+        // every pool block needs a taker: a CTA takes at most kPkPoolCap tickets per phase, so a share that leaves more than
+        // kNumSMs * kPkPoolCap blocks in some phase's pool (only reachable through the knob) falls back to the all-static split
+        for (int N : {w.nqkv, w.H, 2 * w.I, w.V}) {
+            const int nblk = N / kPkBlockRows;
+            const int S = (int)((long long)nblk * a.static_num / 32) / kNumSMs;
+            if (nblk - kNumSMs * S > kNumSMs * kPkPoolCap) a.static_num = 32;
+        }
     }
     a.tp = w.tp; a.rank = w.rank;
     if (w.tp > 1) {
