@@ -1023,6 +1023,8 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         const int bn = R <= 16 ? 16 : (R <= 32 ? 32 : (R <= 64 ? 64 : 128));
         const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, bn), lo = make_tmap_bf16(xlo, R, K, K, bn);
         GemmArgs g{N, R, K, nullptr, nullptr, 0, out, N, ks, (long long)R * N};     // M = weight rows, N = activation rows
+        static const bool w_prefetch = env_flag("FL_GEMM_WPREFETCH");     // experimental: not yet measured on a GPU
+        g.w_prefetch = (w_prefetch && pdl) ? 1 : 0;
         switch (bn) {
             case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
             case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;

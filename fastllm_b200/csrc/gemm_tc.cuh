@@ -36,6 +36,7 @@ struct GemmArgs {
     int ksplit;                 // >1: K is cut into ksplit ranges handled by different work items (GEPI_F32 / GEPI_ATOMIC_F32)
     long long split_stride;     // GEPI_F32 with ksplit > 1: split s writes its partial sums to out + s * split_stride (deterministic)
     void* out2 = nullptr;       // GEPI_SILU_HL: the lo half ([M, ldo] bf16, like `out` = the hi half)
+    int w_prefetch = 0;         // DUAL_B: request the first ring-full of WEIGHT tiles before griddepcontrol.wait (see the producer)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -180,6 +181,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            // Swap-AB decode GEMMs are short (one work item per CTA, 5-40 us) and sit in a chain GEMM -> element-wise -> GEMM, so the
+            // ~2 us between the dependency wait and the first landed weight tile is a fixed tax on every one of them.  The WEIGHT
+            // operand does not depend on the previous kernel (it is constant after upload), so with w_prefetch the first ring-full of
+            // weight tiles is requested BEFORE griddepcontrol.wait: the CTA becomes resident as soon as the previous GEMM's CTA on
+            // this SM exits (every kernel of the chain calls launch_dependents at entry) and fills its ring while the element-wise
+            // kernel in between runs.  The stage barrier still expects the whole stage; the activation tiles that complete it are
+            // requested after the wait.  (The first pass over the ring needs no empty-slot wait: the slots have never been used.)
+            uint32_t pre = 0;
+            if (DUAL == DUAL_B && g.w_prefetch) {
+                for (int item = blockIdx.x; item < ntiles && pre < (uint32_t)kStages; item += gridDim.x) {
+                    const int tile = item / ksplit, ks = item % ksplit;
+                    const int m0 = (tile / nt) * kGemmBM;
+                    const int kb1 = min((ks + 1) * nkps, nk);
+                    for (int kb = ks * nkps; kb < kb1 && pre < (uint32_t)kStages; ++kb, ++pre) {
+                        mbar_expect_tx(&full[pre], kStageBytes);
+                        tma_load_2d(gsm + (size_t)pre * kStageBytes, &tmA, kb * kGemmBK, m0, &full[pre]);
+                    }
+                }
+            }
             pdl_wait();
             asm volatile("fence.proxy.async;" ::: "memory");      // the previous kernel's generic-proxy stores -> TMA reads
             uint32_t c = 0;
@@ -189,8 +209,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb1 = min((ks + 1) * nkps, nk);
                 for (int kb = ks * nkps; kb < kb1; ++kb, ++c) {
                     const int st = c % kStages;
-                    mbar_wait(&empty[st], ((c / kStages) & 1) ^ 1);
                     uint8_t* sa = gsm + (size_t)st * kStageBytes;
+                    if (DUAL == DUAL_B && c < pre) {       // weight tile already on its way; complete the stage with the activations
+                        tma_load_2d(sa + kBOff, &tmA2, kb * kGemmBK, n0, &full[st]);
+                        tma_load_2d(sa + kBOff + kBBytes, &tmB, kb * kGemmBK, n0, &full[st]);
+                        continue;
+                    }
+                    mbar_wait(&empty[st], ((c / kStages) & 1) ^ 1);
                     mbar_expect_tx(&full[st], kStageBytes);
                     if (DUAL == DUAL_B) {       // tmA = weights, tmA2 / tmB = activation hi / lo
                         tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
