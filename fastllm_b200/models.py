@@ -344,8 +344,8 @@ class MistralWithConfig(_CausalBase):
         ids = np.asarray(input)
         if ids.ndim != 2:
             raise FastllmError(-1, f"input must be [batch, seq], got shape {ids.shape}")
-        if self._kv is None:
-            self._kv = DeviceCache(self.dev, max(self.MAX_BATCH, ids.shape[0]), self._capacity())
+        if self._kv is None or (cache.get_offset() == 0 and self._kv.max_batch < ids.shape[0]):
+            self._kv = DeviceCache(self.dev, max(self.MAX_BATCH, ids.shape[0]), self._capacity())   # a wider batch starts a new KV
         if cache.get_offset() == 0:
             self.clear_kv_cache()
         out = self._kv.forward(ids, cache.get_offset())
@@ -455,6 +455,53 @@ class Model:
             pos += 1
         return (out, trace) if return_logits else out
 
+    def generate_batch(self, prompts, max_tokens: int, temperature: float = 0.0, max_batch: int = 64):
+        """Request batching at the API boundary (the reference serialises requests at batch 1 under a
+        mutex, chat.rs:206-208).  Exact by construction: only prompts of EQUAL token length share a batch, so the sequences of
+        a group advance in lock-step through one [b, t] forward per step (no padding, one KV length), every sequence has its
+        own LogitsProcessor seeded 0 like every request of the reference, and a sequence that hit EOS keeps its row (fed its
+        last token, output ignored) until the group is done.  Same arithmetic per sequence as generate(p); the batch-b decode
+        step runs on the dense path and batch-1 on the persistent path, so logits agree to the kernel tolerance (3e-3), not
+        bitwise.  Returns one id list per prompt, in request order."""
+        out = [None] * len(prompts)
+        groups: dict = {}
+        for i, p in enumerate(prompts):
+            groups.setdefault(len(p), []).append(i)
+        for idxs in groups.values():
+            for k in range(0, len(idxs), max_batch):
+                chunk = idxs[k:k + max_batch]
+                for i, toks in zip(chunk, self._generate_group([prompts[i] for i in chunk], max_tokens, temperature)):
+                    out[i] = toks
+        return out
+
+    def _generate_group(self, prompts, max_tokens: int, temperature: float):
+        b = len(prompts)
+        self.cache = self.model.initialize_cache()
+        processors = [LogitsProcessor(0, float(np.float32(temperature))) for _ in range(b)]
+        ids = np.asarray(prompts, dtype=np.uint32).reshape(b, -1)
+        pos = 0
+        logits = self.model.forward(ids, pos, self.cache)
+        pos += ids.shape[1]
+        outs = [[] for _ in range(b)]
+        done = [False] * b
+        nxt = np.ascontiguousarray(ids[:, -1:])
+        for _ in range(max_tokens):
+            rows = np.asarray(logits).reshape(b, -1)
+            for i in range(b):
+                if done[i]:
+                    continue
+                tok = processors[i].sample(rows[i])
+                if self.eos_token_id is not None and tok == self.eos_token_id:
+                    done[i] = True                                       # break before emitting, for this sequence only
+                    continue
+                outs[i].append(tok)
+                nxt[i, 0] = tok
+            if all(done):
+                break
+            logits = self.model.forward(nxt, pos, self.cache)
+            pos += 1
+        return outs
+
 
 # --------------------------------------------------------------------------------------------------------------------
 # EmbeddingModel (models/embeddings.rs:17-38) -- BERT / MiniLM sentence encoder
@@ -520,6 +567,21 @@ class MiniLMModel:
             mask = np.ascontiguousarray(mask, dtype=np.uint32).reshape(b, t)
             mptr = mask.ctypes.data_as(C.c_void_p)
         _lib.check(self.dev.lib.fl_embed(self.dev.h, ids.ctypes.data_as(C.c_void_p), mptr, b, t, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def embed_many(self, sentences, max_batch: int = 256) -> np.ndarray:
+        """`input: [String]` batching (the reference takes one string per request, api/embeddings.rs:11-15).
+        Exact by construction: the reference's attention applies NO mask (embeddings.rs:155-159) and a lone sentence has an
+        all-ones mask, so padding would change results; sentences of EQUAL token length are therefore grouped into one [b, t]
+        call each (no padding) and the rows scattered back in request order.  Returns f32 [len(sentences), hidden]."""
+        out = np.empty((len(sentences), self.config.hidden_size), dtype=np.float32)
+        groups: dict = {}
+        for i, s in enumerate(sentences):
+            groups.setdefault(len(s), []).append(i)
+        for idxs in groups.values():
+            for k in range(0, len(idxs), max_batch):
+                chunk = idxs[k:k + max_batch]
+                out[chunk] = self.embed_ids(np.asarray([sentences[i] for i in chunk], dtype=np.uint32))
         return out
 
     def embed_ids_timed(self, ids: np.ndarray, repeats: int):
