@@ -87,12 +87,14 @@ inline int32_t total_order_key(float f) {
 
 // LogitsProcessor::sample_argmax: iter().enumerate().max_by(|(_, u), (_, v)| u.total_cmp(v)) -- max_by keeps the LAST maximum
 inline uint32_t sample_argmax(const float* v, size_t n) {
-    size_t best = 0;
+    // two passes: a branch-free max reduction over the order keys (vectorised by the compiler), then the LAST index holding it
     int32_t kb = total_order_key(v[0]);
     for (size_t i = 1; i < n; ++i) {
         const int32_t k = total_order_key(v[i]);
-        if (k >= kb) { kb = k; best = i; }
+        kb = k > kb ? k : kb;
     }
+    size_t best = n - 1;
+    while (total_order_key(v[best]) != kb) --best;
     return (uint32_t)best;
 }
 

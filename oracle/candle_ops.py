@@ -81,7 +81,7 @@ def rope_tables(head_dim: int, max_pos: int, theta: float, theta_pow_f64: bool):
     Then freqs = positions(f32) outer inv_freq (f32 matmul), cos/sin in f32."""
     i = np.arange(0, head_dim, 2)
     # libm powf / cosf / sinf are (almost always) correctly rounded; model them as f64 evaluation rounded to f32,
-    # which is also what fastllm_b200/csrc/model.cu does on the host, so both sides hold identical tables.
+    # which is also what the library does on the host (finalize() in fastllm_b200/csrc/fl_lib.cu), so both sides hold identical tables.
     if theta_pow_f64:
         p = np.power(np.float64(theta), i.astype(np.float64) / np.float64(head_dim)).astype(F32)
     else:
