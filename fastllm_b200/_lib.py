@@ -54,6 +54,7 @@ SYMBOLS = {
     "fl_decode_greedy_loop": (_I, [_VP, _VP, _VP, _I, _SZ, _I, _VP, C.POINTER(C.c_float)]),
     "fl_sampler_create": (_I, [_U64, C.c_double, C.POINTER(_VP)]),
     "fl_sampler_sample": (_I, [_VP, _VP, _SZ, C.POINTER(C.c_uint32)]),
+    "fl_argmax_rows": (_I, [_VP, _I, _SZ, _VP]),
     "fl_sampler_next_u32": (_I, [_VP, C.POINTER(C.c_uint32)]),
     "fl_sampler_destroy": (_I, [_VP]),
     "fl_forward_sample": (_I, [_VP, _VP, _VP, _I, _I, _SZ, _VP, C.POINTER(C.c_uint32)]),

@@ -2,6 +2,7 @@
 // See include/fastllm_b200.h for the reference interface each entry point replaces.
 #include <cmath>
 #include <sstream>
+#include <thread>
 
 #include "attn_decode.cuh"
 #include "attn_mma.cuh"
@@ -1577,6 +1578,25 @@ FL_EXPORT int fl_sampler_sample(fl_sampler* s, const float* logits_host, size_t 
         *token = s->lp.sample(logits_host, n);
     } catch (const fl::SamplerError& e) {
         throw fl::Error(FL_ERR_INVALID, e.what());
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_argmax_rows(const float* logits_host, int rows, size_t n, uint32_t* tokens) {
+    FL_API_BEGIN
+    FL_CHECK(logits_host && tokens && rows >= 0 && n > 0, FL_ERR_INVALID, "bad argument");
+    // a batch of rows is a memory-bound scan of rows * n * 4 bytes: fan it out over a few host threads
+    const int nthr = (size_t)rows * n >= ((size_t)1 << 20) ? std::min(rows, 8) : 1;
+    auto scan = [&](int r0, int r1) {
+        for (int r = r0; r < r1; ++r) tokens[r] = fl::sample_argmax(logits_host + (size_t)r * n, n);
+    };
+    if (nthr <= 1) {
+        scan(0, rows);
+    } else {
+        std::vector<std::thread> pool;
+        for (int i = 1; i < nthr; ++i) pool.emplace_back(scan, (int)((long long)rows * i / nthr), (int)((long long)rows * (i + 1) / nthr));
+        scan(0, rows / nthr);
+        for (std::thread& th : pool) th.join();
     }
     FL_API_END
 }

@@ -85,14 +85,29 @@ inline int32_t total_order_key(float f) {
     return b ^ (int32_t)((uint32_t)(b >> 31) >> 1);
 }
 
+// largest order key of v[0..n): a branch-free max reduction the compiler vectorises; the AVX2 clone is picked at run time
+#define FL_MAX_KEY_BODY                                  \
+    int32_t kb = total_order_key(v[0]);                  \
+    for (size_t i = 1; i < n; ++i) {                     \
+        const int32_t k = total_order_key(v[i]);         \
+        kb = k > kb ? k : kb;                            \
+    }                                                    \
+    return kb;
+static inline int32_t max_key_generic(const float* v, size_t n) { FL_MAX_KEY_BODY }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static inline int32_t max_key_avx2(const float* v, size_t n) { FL_MAX_KEY_BODY }
+static inline int32_t max_key(const float* v, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    return avx2 ? max_key_avx2(v, n) : max_key_generic(v, n);
+}
+#else
+static inline int32_t max_key(const float* v, size_t n) { return max_key_generic(v, n); }
+#endif
+#undef FL_MAX_KEY_BODY
+
 // LogitsProcessor::sample_argmax: iter().enumerate().max_by(|(_, u), (_, v)| u.total_cmp(v)) -- max_by keeps the LAST maximum
 inline uint32_t sample_argmax(const float* v, size_t n) {
-    // two passes: a branch-free max reduction over the order keys (vectorised by the compiler), then the LAST index holding it
-    int32_t kb = total_order_key(v[0]);
-    for (size_t i = 1; i < n; ++i) {
-        const int32_t k = total_order_key(v[i]);
-        kb = k > kb ? k : kb;
-    }
+    const int32_t kb = max_key(v, n);
     size_t best = n - 1;
     while (total_order_key(v[best]) != kb) --best;
     return (uint32_t)best;

@@ -428,6 +428,15 @@ def sample_argmax(logits: np.ndarray) -> int:
 _greedy = None
 
 
+def sample_argmax_rows(logits: np.ndarray) -> np.ndarray:
+    """sample_argmax for every row of [b, V] logits (a batch of greedy requests) in one library call -> u32 [b]."""
+    v = np.ascontiguousarray(logits, dtype=np.float32)
+    v = v.reshape(v.shape[0], -1)
+    out = np.empty((v.shape[0],), dtype=np.uint32)
+    _lib.check(_lib.load().fl_argmax_rows(v.ctypes.data_as(C.c_void_p), v.shape[0], v.shape[1], out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 class Model:
     """Model<M> (mod.rs:342-464) without the tokenizer: prompts are already token ids."""
 

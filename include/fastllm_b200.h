@@ -140,6 +140,8 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
  * WeightedIndex<f32>::sample over StdRng::seed_from_u64(seed) (ChaCha12).  The reference always passes seed 0. */
 FL_EXPORT int fl_sampler_create(uint64_t seed, double temperature, fl_sampler** out);
 FL_EXPORT int fl_sampler_sample(fl_sampler* s, const float* logits_host, size_t n, uint32_t* token);
+/* The arg-max rule above for every row of a host f32 [rows, n] matrix (a batch of greedy requests); tokens: host u32 [rows]. */
+FL_EXPORT int fl_argmax_rows(const float* logits_host, int rows, size_t n, uint32_t* tokens);
 FL_EXPORT int fl_sampler_next_u32(fl_sampler* s, uint32_t* out);  /* the generator's next raw word (known-answer tests) */
 FL_EXPORT int fl_sampler_destroy(fl_sampler* s);
 /* fl_forward, then sample row 0 of the logits (the generate loop only looks at logits.get(0), models/mod.rs:421); one

@@ -190,3 +190,17 @@ def test_generate_loop_with_temperature_matches_oracle(three_d):
     assert got == want and len(got) == 6                           # EOS breaks before emitting
     assert [p for _, p in ad.calls] == [0, 3, 4, 5, 6, 7, 8]       # pos: 0, then prompt length + i
     assert ad.calls[0][0].shape == (1, 3) and all(c.shape == (1, 1) for c, _ in ad.calls[1:])
+
+
+def test_argmax_rows_equals_row_by_row():
+    """fl_argmax_rows (a batch of greedy requests, threaded over rows above 1 Mi elements) == the single-row rule, ties and all."""
+    rs = np.random.RandomState(9)
+    for b, v in [(1, 7), (5, 1000), (64, 32000)]:
+        x = rs.standard_normal((b, v)).astype(np.float32)
+        x[b // 2, [0, v // 3, v - 1]] = 9.0                    # a three-way tie: the LAST index wins
+        x[0, v // 2] = np.inf
+        got = models.sample_argmax_rows(x)
+        assert got.dtype == np.uint32 and got.shape == (b,)
+        assert list(got) == [osamp.sample_argmax(r) for r in x]
+    assert int(models.sample_argmax_rows(x)[b // 2]) == v - 1
+    assert models.sample_argmax_rows(x[:, None, :]).shape == (b,)       # [b, 1, V] logits of the Mistral / Qwen2 adapters
