@@ -8,8 +8,11 @@
 //   MistralWithConfig / MistralCache       src/models/mistral.rs:16-248
 //   QwenWithConfig / QwenCache             src/models/qwen.rs:12-186
 //   Model<M>::generate + LogitsProcessor   src/models/mod.rs:342-464
+//   EmbeddingModel / MiniLMModel           src/models/embeddings.rs:17-38, 245-447
 // INTEGRATION.md shows the Rust shim (a transliteration of this file) a maintainer would add.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -203,6 +206,60 @@ struct Model {
             logits = model.forward(&tok, 1, 1, pos, cache);
             pos += 1;
         }
+        return out;
+    }
+};
+
+// ---- EmbeddingModel (models/embeddings.rs:17-38) / MiniLMModel (:245-447) after tokenisation -------------------------------------
+struct BertConfig {   // models/embeddings.rs:46-54 (+ the vocabulary size the reference takes from the tokenizer, :301-306)
+    int hidden_size = 384, num_attention_heads = 12, num_hidden_layers = 6, intermediate_size = 1536, max_position_embeddings = 512;
+    double layer_norm_eps = 1e-12;
+    int vocab_size = 30522;
+};
+struct MiniLMModel {
+    std::shared_ptr<DeviceModel> dev;
+    std::string id = "sentence-transformers/all-MiniLM-L6-v2";
+    static const char* get_family() { return "bert"; }
+    static bool supports_architecture(const std::string& a) { return a == "BertModel" || a == "RobertaModel" || a == "DebertaModel"; }
+    static MiniLMModel create(const BertConfig& cfg, const TensorMap& tensors, int device) {   // MiniLMModel::new (:257-339)
+        check(fl_init(device));
+        fl_config c{};
+        c.arch = FL_ARCH_BERT;
+        c.hidden_size = cfg.hidden_size; c.intermediate_size = cfg.intermediate_size; c.vocab_size = cfg.vocab_size;
+        c.num_hidden_layers = cfg.num_hidden_layers; c.num_attention_heads = cfg.num_attention_heads; c.num_key_value_heads = cfg.num_attention_heads;
+        c.max_position_embeddings = cfg.max_position_embeddings; c.norm_eps = (float)cfg.layer_norm_eps; c.tp_size = 1;
+        return MiniLMModel{upload(c, tensors)};
+    }
+    const std::string& model_id() const { return id; }
+    size_t embedding_size() const { return (size_t)dev->cfg.hidden_size; }   // the reference hard-codes 384 (:453-455)
+    // EmbeddingModel::embed after tokenisation: ids (and the tokenizer's attention mask, or nullptr = all ones) [b, t] -> f32 [b, hidden]
+    std::vector<float> embed_ids(const uint32_t* ids, const uint32_t* mask, int b, int t) const {
+        std::vector<float> out((size_t)b * dev->cfg.hidden_size);
+        check(fl_embed(dev->h, ids, mask, b, t, out.data()));
+        return out;
+    }
+    // default impl of EmbeddingModel::compute_similarity (:22-37): cosine of the two embeddings
+    float compute_similarity(const std::vector<uint32_t>& a, const std::vector<uint32_t>& b) const {
+        const std::vector<float> va = embed_ids(a.data(), nullptr, 1, (int)a.size()), vb = embed_ids(b.data(), nullptr, 1, (int)b.size());
+        double dot = 0, na = 0, nb = 0;
+        for (size_t i = 0; i < va.size(); ++i) { dot += (double)va[i] * vb[i]; na += (double)va[i] * va[i]; nb += (double)vb[i] * vb[i]; }
+        return (float)(dot / (std::sqrt(na) * std::sqrt(nb)));
+    }
+    // `input: [String]` batching, exact: only sentences of EQUAL token length share a [b, t] call (the
+    // reference's attention has no mask, so padding would change results); rows come back in request order
+    std::vector<std::vector<float>> embed_many(const std::vector<std::vector<uint32_t>>& sentences, int max_batch = 256) const {
+        std::vector<std::vector<float>> out(sentences.size());
+        std::map<size_t, std::vector<size_t>> groups;
+        for (size_t i = 0; i < sentences.size(); ++i) groups[sentences[i].size()].push_back(i);
+        const size_t H = embedding_size();
+        for (const auto& kv : groups)
+            for (size_t k = 0; k < kv.second.size(); k += (size_t)max_batch) {
+                const size_t n = std::min(kv.second.size() - k, (size_t)max_batch);
+                std::vector<uint32_t> ids;
+                for (size_t j = 0; j < n; ++j) ids.insert(ids.end(), sentences[kv.second[k + j]].begin(), sentences[kv.second[k + j]].end());
+                const std::vector<float> e = embed_ids(ids.data(), nullptr, (int)n, (int)kv.first);
+                for (size_t j = 0; j < n; ++j) out[kv.second[k + j]].assign(e.begin() + j * H, e.begin() + (j + 1) * H);
+            }
         return out;
     }
 };
