@@ -10,7 +10,8 @@
 //     (row, kv_head) -- elected with an atomic ticket -- merges the splits and writes the normalised output, so no
 //     separate combine launch is needed;
 //   * rows of a multi-token call (prefill chunks) are causal: row r sees kv_base + i_rel + 1 keys, and the
-//     Mistral/Qwen2 sliding-window prefill rule (key j banned when j + sw < i, new tokens only) is applied.
+//     Mistral/Qwen2 sliding-window prefill rule (key j banned when j + sw < i, among the NEW tokens only: cached keys stay
+//     visible, as candle concatenates zeros for the cached columns of its mask) is applied.
 #pragma once
 #include "common.cuh"
 #include "gemv.cuh"
@@ -71,8 +72,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
     const int seq = rg / a.t, irel = rg % a.t;
     const int kv_base = a.state->kv_base[seq];
     const int len = kv_base + irel + 1;
+    // candle's Mistral/Qwen2 mask is [t, t] over the NEW tokens (key j banned when j + sw < i) with ZEROS concatenated for the
+    // cached columns: every cached key (< kv_base) stays visible, the window only thins out the new tokens
     const int start = (a.sliding_window > 0 && irel - a.sliding_window > 0) ? kv_base + irel - a.sliding_window : 0;
-    const int first_page = start / kKvPage;
+    const int first_page = kv_base > 0 ? 0 : start / kKvPage;
     const int npages = (len + kKvPage - 1) / kKvPage;
     const int per = (npages - first_page + nsplit - 1) / nsplit;
     const int p0 = first_page + split * per;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
             const float kf[8] = {bf16lo(kw.x), bf16hi(kw.x), bf16lo(kw.y), bf16hi(kw.y),
                                  bf16lo(kw.z), bf16hi(kw.z), bf16lo(kw.w), bf16hi(kw.w)};
             const int tok_abs = p * kKvPage + tok;
-            const bool valid = tok_abs >= start && tok_abs < len;
+            const bool valid = (tok_abs >= start || tok_abs < kv_base) && tok_abs < len;
 #pragma unroll
             for (int h = 0; h < kAttnMaxRep; ++h) {
                 if (h < n_rep) {

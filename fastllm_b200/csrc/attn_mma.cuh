@@ -14,7 +14,7 @@
 // multiplied against the same K / V fragments (as the dense GEMMs do with their activations), K/V are bf16 in the cache
 // already, accumulation is f32: results stay inside the kernel tolerance of the f32 oracle.
 // Semantics: scores * 1/sqrt(d) after the matmul, causal rows for multi-token calls,
-// Mistral/Qwen2 sliding-window rule inside the prefill only (key j banned when j + sw < i), softmax max-subtract/exp/sum/div.
+// Mistral/Qwen2 sliding-window rule inside the prefill only (key j banned when j + sw < i, new tokens only; cached keys stay visible), softmax max-subtract/exp/sum/div.
 #pragma once
 #include "attn_decode.cuh"
 #include "dense_ops.cuh"
@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_prefill_kernel(const Att
     // key range of the whole tile
     const int ilast = min(i0 + kPrefillBM, a.t) - 1;
     const int len_tile = kv_base + ilast + 1;
-    const int start_tile = (sw > 0 && i0 - sw > 0) ? kv_base + i0 - sw : 0;
+    // the window thins out the NEW tokens only: candle concatenates zeros for the cached columns of its [t, t] mask, so every
+    // cached key (< kv_base) stays visible and a call on a non-empty cache walks all pages
+    const int start_tile = (sw > 0 && i0 - sw > 0 && kv_base == 0) ? i0 - sw : 0;
     const int p0 = start_tile / kKvPage, p1 = (len_tile + kKvPage - 1) / kKvPage;
 
     auto load = [&](int p, int st) {
@@ -372,10 +374,10 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_prefill_kernel(const Att
                 for (int e = 0; e < 4; ++e) {
                     const int key = key0 + nt * 8 + tq * 2 + (e & 1);
                     if (e < 2) {
-                        s[nt][e] = (key >= st0 && key < len0) ? s[nt][e] * a.qscale : -INFINITY;
+                        s[nt][e] = ((key >= st0 || key < kv_base) && key < len0) ? s[nt][e] * a.qscale : -INFINITY;
                         mx0 = fmaxf(mx0, s[nt][e]);
                     } else {
-                        s[nt][e] = (key >= st1 && key < len1) ? s[nt][e] * a.qscale : -INFINITY;
+                        s[nt][e] = ((key >= st1 || key < kv_base) && key < len1) ? s[nt][e] * a.qscale : -INFINITY;
                         mx1 = fmaxf(mx1, s[nt][e]);
                     }
                 }

@@ -155,13 +155,15 @@ static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
 }
 
 // act = silu(gate) * up from the interleaved gate|up GEMM output, written directly as the hi/lo split the down GEMM reads
+// (grouped expert GEMMs: rows are blocks of `grp_cap` per expert, of which grp_cnt[block] are valid; the rest is skipped)
 static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int I, uint16_t* __restrict__ xhi,
-                                               uint16_t* __restrict__ xlo) {
+                                               uint16_t* __restrict__ xlo, const int* __restrict__ grp_cnt = nullptr, int grp_cap = 0) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= I) return;
+    if (grp_cnt != nullptr && (row % grp_cap) >= grp_cnt[row / grp_cap]) return;
     float2 gu = make_float2(0.f, 0.f);
     for (int s = 0; s < nsl; ++s) {
         const float2 p = *reinterpret_cast<const float2*>(y + (size_t)s * sl_stride + (size_t)row * 2 * I + 2 * j);
@@ -177,22 +179,29 @@ static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int 
 
 // ---- Mixtral sparse-MoE (candle-transformers models::mixtral::SparseMoeBlock) ----------------
 // router: logits = x . W_gate^T, softmax over ALL experts (f32), stable descending sort (ties keep the LOWER expert index),
-// take top_k, renormalise by their sum; route_w[row][e] = weight or 0.  One CTA per row.
+// take top_k, renormalise by their sum; route_w[row][e] = weight or 0.  One CTA per row, one WARP per expert (128-bit loads,
+// one shuffle reduction each): the eight dot products of a Mixtral row run side by side instead of as eight block reductions.
 static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* __restrict__ xhi, const uint16_t* __restrict__ xlo, int H,
                                                                 const float* __restrict__ wgate, int E, int top_k, float* __restrict__ route_w) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float red[8];
     __shared__ float logit[64];
-    const int row = blockIdx.x;
-    for (int e = 0; e < E; ++e) {
+    const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint2* h4 = reinterpret_cast<const uint2*>(xhi + (size_t)row * H);      // 4 bf16 per load (H % 8 == 0 on the dense path)
+    const uint2* l4 = reinterpret_cast<const uint2*>(xlo + (size_t)row * H);
+    for (int e = warp; e < E; e += 8) {
+        const float4* wg = reinterpret_cast<const float4*>(wgate + (size_t)e * H);
         float acc = 0.f;
-        for (int i = threadIdx.x; i < H; i += blockDim.x) {
-            const float x = __uint_as_float((uint32_t)xhi[(size_t)row * H + i] << 16) + __uint_as_float((uint32_t)xlo[(size_t)row * H + i] << 16);
-            acc = fmaf(x, wgate[(size_t)e * H + i], acc);
+        for (int i = lane; i < H / 4; i += 32) {
+            const uint2 a = h4[i], b = l4[i];
+            const float4 w = wg[i];
+            acc = fmaf(bf16lo(a.x) + bf16lo(b.x), w.x, acc);
+            acc = fmaf(bf16hi(a.x) + bf16hi(b.x), w.y, acc);
+            acc = fmaf(bf16lo(a.y) + bf16lo(b.y), w.z, acc);
+            acc = fmaf(bf16hi(a.y) + bf16hi(b.y), w.w, acc);
         }
-        const float tot = block_sum_256(acc, red);
-        if (threadIdx.x == 0) logit[e] = tot;
+        acc = warp_sum(acc);
+        if (lane == 0) logit[e] = acc;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -216,6 +225,80 @@ static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* 
         }
         for (int k = 0; k < top_k; ++k) rw[picked[k]] = logit[picked[k]] / picked_sum;
     }
+}
+
+// Grouped expert GEMMs (decode batches): the rows routed to each LOCAL expert are gathered into that expert's block of a
+// stacked activation buffer (candle: index_select of the rows per expert), in ascending row order.
+//   gx_hi / gx_lo [E_local * cap, H] : block j holds the hi / lo halves of the rows routed to expert e0 + j
+//   cnt [E_local]                    : rows in block j (read by the grouped GEMM, the SiLU kernel and nobody else)
+//   pos [Rm, E_local]                : slot (j * cap + p) of row r in block j, or -1: the combine kernel's scatter map
+// grid (E_local, copy CTAs), 256 threads; every CTA of an expert rebuilds the (<= 256-entry) list, then copies its share of rows.
+struct MoeGatherArgs {
+    const uint16_t* xhi;
+    const uint16_t* xlo;
+    const float* route;      // [Rm, E]
+    int Rm, H, E, e0, E_local, cap;
+    uint16_t* gx_hi;
+    uint16_t* gx_lo;
+    int* cnt;
+    int* pos;
+};
+static __global__ void __launch_bounds__(256) moe_gather_kernel(const MoeGatherArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ int s_list[256];
+    __shared__ int s_cnt;
+    const int j = blockIdx.x, e = a.e0 + j, tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        int n = 0;
+        for (int r0 = 0; r0 < a.Rm; r0 += 32) {
+            const int r = r0 + lane;
+            const bool sel = r < a.Rm && a.route[(size_t)r * a.E + e] != 0.f;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
+            if (sel) s_list[n + __popc(m & ((1u << lane) - 1u))] = r;
+            n += __popc(m);
+        }
+        if (lane == 0) s_cnt = n;
+    }
+    __syncthreads();
+    const int n = s_cnt;
+    if (blockIdx.y == 0) {
+        if (tid == 0) a.cnt[j] = n;
+        for (int r = tid; r < a.Rm; r += blockDim.x) a.pos[(size_t)r * a.E_local + j] = -1;
+        __syncthreads();
+        for (int p = tid; p < n; p += blockDim.x) a.pos[(size_t)s_list[p] * a.E_local + j] = j * a.cap + p;
+    }
+    const int H8 = a.H / 8;
+    for (int p = blockIdx.y; p < n; p += gridDim.y) {
+        const uint4* sh = reinterpret_cast<const uint4*>(a.xhi + (size_t)s_list[p] * a.H);
+        const uint4* sl = reinterpret_cast<const uint4*>(a.xlo + (size_t)s_list[p] * a.H);
+        uint4* dh = reinterpret_cast<uint4*>(a.gx_hi + ((size_t)j * a.cap + p) * a.H);
+        uint4* dl = reinterpret_cast<uint4*>(a.gx_lo + ((size_t)j * a.cap + p) * a.H);
+        for (int i = tid; i < H8; i += blockDim.x) {
+            dh[i] = sh[i];
+            dl[i] = sl[i];
+        }
+    }
+}
+
+// index_add of the weighted expert outputs: moe_out[row] = sum over this rank's experts j (ascending: a fixed order) that
+// selected the row of route[row][e0 + j] * (sum over split-K slices of y[slot of the row in block j])
+static __global__ void moe_combine_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int H, const float* __restrict__ route, int E,
+                                          int e0, int E_local, const int* __restrict__ pos, float* __restrict__ moe_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H) return;
+    float v = 0.f;
+    for (int j = 0; j < E_local; ++j) {
+        const int p = pos[(size_t)row * E_local + j];
+        if (p < 0) continue;
+        float s = 0.f;
+        for (int k = 0; k < nsl; ++k) s += y[(size_t)k * sl_stride + (size_t)p * H + i];
+        v += route[(size_t)row * E + e0 + j] * s;
+    }
+    moe_out[(size_t)row * H + i] = v;
 }
 
 // moe_out[row] (=|+=) route_w[row][e] * sum over split-K slices of y[row]   (index_add of the weighted expert output)

@@ -1,6 +1,7 @@
 // BERT / MiniLM sentence-encoder path behind fl_embed (host orchestration), sm_100a.
 // Reference: MiniLMModel::{new, embed_tokens, forward, mean_pooling, normalize_l2, embed} src/models/embeddings.rs:245-447.
 #include <cmath>
+#include <memory>
 
 #include "bert.cuh"
 #include "bert_model.cuh"
@@ -177,10 +178,11 @@ static uint16_t h_bf16(float f) {
 void bert_put_tensor(BertModel& m, const char* name, int dtype, const int64_t* shape, int rank, const void* host) {
     FL_CHECK(!m.finalized, FL_ERR_STATE, "model already finalized");
     const std::string n(name);
-    // tensors the reference never reads (pooler, token-type embeddings, position_ids buffer): accept and ignore
-    if (n.compare(0, 7, "pooler.") == 0 || n == "embeddings.token_type_embeddings.weight" || n == "embeddings.position_ids") return;
+    // tensors the reference never reads (pooler, token-type embeddings, position_ids buffer, anything else in the checkpoint):
+    // accepted and ignored, as VarBuilder ignores the extra entries of the loaded HashMap (embeddings.rs:290-298); a MISSING tensor
+    // is still an error at finalize
     BertRoute r;
-    FL_CHECK(bert_route(m, n, r), FL_ERR_INVALID, "unknown tensor name: " + n);
+    if (!bert_route(m, n, r)) return;
     FL_CHECK(dtype == FL_DTYPE_F32, FL_ERR_UNSUPPORTED, "BERT tensors must be f32 (the reference loads MiniLM as F32, embeddings.rs:298)");
     const bool ok = r.mat ? (rank == 2 && shape[0] == r.rows && shape[1] == r.cols) : (rank == 1 && shape[0] == r.rows);
     FL_CHECK(ok, FL_ERR_INVALID, "shape mismatch for " + n);
@@ -289,40 +291,31 @@ void bert_embed(BertModel& m, const uint32_t* ids, const uint32_t* mask, int b, 
         std::memcpy(m.h_ids.p + T, mask, T * 4);
         FL_CUDA(cudaMemcpyAsync(m.mask.p, m.h_ids.p + T, T * 4, cudaMemcpyHostToDevice, m.stream));
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::unique_ptr<EventPair> ev;
     if (device_ms) {
-        FL_CUDA(cudaEventCreate(&e0));
-        FL_CUDA(cudaEventCreate(&e1));
-        FL_CUDA(cudaEventRecord(e0, m.stream));
+        ev.reset(new EventPair);
+        FL_CUDA(cudaEventRecord(ev->e0, m.stream));
     }
     bert_enqueue(m, b, t, mask != nullptr);
-    if (device_ms) FL_CUDA(cudaEventRecord(e1, m.stream));
+    if (device_ms) FL_CUDA(cudaEventRecord(ev->e1, m.stream));
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(m.h_out.p, m.out.p, (size_t)b * m.H * 4, cudaMemcpyDeviceToHost, m.stream));
     FL_CUDA(cudaStreamSynchronize(m.stream));
     std::memcpy(out, m.h_out.p, (size_t)b * m.H * 4);
-    if (device_ms) {
-        FL_CUDA(cudaEventElapsedTime(device_ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-    }
+    if (device_ms) FL_CUDA(cudaEventElapsedTime(device_ms, ev->e0, ev->e1));
 }
 
 // Device-resident repeat of the encoder on the ids already uploaded by the last bert_embed (benchmark `value`).
 void bert_repeat(BertModel& m, int b, int t, int iters, float* elapsed_ms) {
     std::lock_guard<std::mutex> lock(m.mu);
     FL_CHECK((size_t)b * t <= m.cap_tokens, FL_ERR_STATE, "call fl_embed with this shape first");
-    cudaEvent_t e0, e1;
-    FL_CUDA(cudaEventCreate(&e0));
-    FL_CUDA(cudaEventCreate(&e1));
-    FL_CUDA(cudaEventRecord(e0, m.stream));
+    EventPair ev;
+    FL_CUDA(cudaEventRecord(ev.e0, m.stream));
     for (int i = 0; i < iters; ++i) bert_enqueue(m, b, t, false);
-    FL_CUDA(cudaEventRecord(e1, m.stream));
+    FL_CUDA(cudaEventRecord(ev.e1, m.stream));
     FL_CUDA(cudaStreamSynchronize(m.stream));
     FL_CUDA(cudaGetLastError());
-    FL_CUDA(cudaEventElapsedTime(elapsed_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    FL_CUDA(cudaEventElapsedTime(elapsed_ms, ev.e0, ev.e1));
 }
 
 BertModel::~BertModel() {

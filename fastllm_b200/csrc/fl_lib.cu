@@ -222,9 +222,12 @@ static void build_weights(Weights& w) {
         lo[l].wo = take(H * nq * 2);
         if (moe) {
             lo[l].wgate = take((size_t)w.E * H * 4);
+            // a layer's w1|w3 matrices back to back, then its w2 matrices back to back: each set is also ONE stacked matrix
+            // ([E_local * 2I, H] / [E_local * H, I]), the A operand of the grouped expert GEMMs
+            const size_t gu0 = take((size_t)w.E_local * 2 * I * H * 2), dn0 = take((size_t)w.E_local * H * I * 2);
             for (int e = 0; e < w.E_local; ++e) {
-                lo[l].ewgu.push_back(take(2 * I * H * 2));
-                lo[l].ewdown.push_back(take(H * I * 2));
+                lo[l].ewgu.push_back(gu0 + (size_t)e * 2 * I * H * 2);
+                lo[l].ewdown.push_back(dn0 + (size_t)e * H * I * 2);
             }
             lo[l].wgu = lo[l].wdown = 0;
         } else {
@@ -381,7 +384,10 @@ static std::vector<std::string> expected_tensors(const Weights& w) {
 static void put_tensor(Weights& w, const char* name, int dtype, const int64_t* shape, int rank, const void* host) {
     FL_CHECK(!w.finalized, FL_ERR_STATE, "model already finalized");
     TensorRoute r;
-    FL_CHECK(route_tensor(w, name, r), FL_ERR_INVALID, std::string("unknown tensor name: ") + name);
+    // Names the model does not read are skipped, as candle's VarBuilder ignores the extra entries of the HashMap the loader hands
+    // over (huggingface.rs:81-130 loads EVERY tensor of the checkpoint: `self_attn.rotary_emb.inv_freq` in older Llama exports,
+    // `visual.*` in Qwen2_5_VLForConditionalGeneration, ...).  finalize() stays the strict gate: a MISSING tensor is an error.
+    if (!route_tensor(w, name, r)) { w.ignored++; return; }
     if (r.base == nullptr) return;       // an expert that lives on another expert-parallel rank
     int64_t numel = 1;
     for (int i = 0; i < rank; ++i) numel *= shape[i];
@@ -500,6 +506,8 @@ static void finalize(Weights& w) {
                     lw.tm_ewgu.push_back(make_tmap_bf16(lw.ewgu[e], 2 * (uint64_t)w.I, w.H, w.H, 128));
                     lw.tm_ewdown.push_back(make_tmap_bf16(lw.ewdown[e], w.H, w.I, w.I, 128));
                 }
+                lw.tm_ewgu_all = make_tmap_bf16(lw.ewgu[0], (uint64_t)w.E_local * 2 * w.I, w.H, w.H, 128);
+                lw.tm_ewdown_all = make_tmap_bf16(lw.ewdown[0], (uint64_t)w.E_local * w.H, w.I, w.I, 128);
             } else {
                 lw.tm_wgu = make_tmap_bf16(lw.wgu, 2 * (uint64_t)w.I, w.H, w.H, 128);
                 lw.tm_wdown = make_tmap_bf16(lw.wdown, w.H, w.I, w.I, 128);
@@ -914,6 +922,8 @@ static void enqueue_forward(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_
 constexpr int kDenseMaxSplit = 16;    // upper bound on the split-K slices of a decode GEMM (see pick_ksplit)
 
 static int pick_ksplit(int tiles, int nk, int R);
+// rows per expert block of the grouped expert GEMMs = their N tile: the smallest of 16 / 32 / 64 / 128 that holds every row
+static int moe_group_cap(int Rm) { return Rm <= 16 ? 16 : (Rm <= 32 ? 32 : (Rm <= 64 ? 64 : 128)); }
 
 static void ensure_dense_ws(fl_cache& c, int rows) {
     DenseWs& d = c.dw;
@@ -937,6 +947,16 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
         };
         consider(R, w.nqkv, w.H); consider(R, w.H, nq); consider(R, w.V, w.H);
         consider(Rm, 2 * (size_t)w.I, w.H); consider(Rm, w.H, w.I);
+        if (w.cfg.arch == FL_ARCH_MIXTRAL) {      // grouped expert GEMMs: E_local stacked matrices x one block of `cap` rows each
+            for (size_t cap = 16; cap <= (size_t)moe_group_cap((int)std::min<size_t>(Rm, 128)); cap *= 2) {
+                const size_t Rg = (size_t)w.E_local * cap;
+                for (size_t NK : {(size_t)0, (size_t)1}) {
+                    const size_t N = NK == 0 ? 2 * (size_t)w.I : w.H, K = NK == 0 ? w.H : w.I;
+                    const int ksg = pick_ksplit((int)(w.E_local * ((N + 127) / 128)), (int)((K + kGemmBK - 1) / kGemmBK), (int)cap);
+                    need = std::max(need, Rg * N * (size_t)ksg);
+                }
+            }
+        }
         for (size_t r = 1; r <= std::min<size_t>(R, kMaxBatch); ++r) consider(r, w.V, w.H);     // the lm_head runs on one row per sequence
         d.y.alloc(need);
     }
@@ -944,7 +964,12 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
     if (w.cfg.arch != FL_ARCH_MIXTRAL && R > 128) { d.xhi2.alloc(R * (size_t)w.I); d.xlo2.alloc(R * (size_t)w.I); }
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {
-        d.xhi2.alloc(Rm * kmax); d.xlo2.alloc(Rm * kmax);
+        // grouped path (calls with <= 128 expert rows): E_local blocks of up to grp_cap rows; masked path (prefill): Rm rows
+        d.grp_cap = moe_group_cap((int)std::min<size_t>(Rm, 128));
+        const size_t Rg = (size_t)w.E_local * d.grp_cap;
+        d.xhi2.alloc(std::max(Rm, Rg) * kmax); d.xlo2.alloc(std::max(Rm, Rg) * kmax);
+        d.gx_hi.alloc(Rg * w.H, true); d.gx_lo.alloc(Rg * w.H, true);
+        d.grp_cnt.alloc(w.E_local, true); d.grp_pos.alloc(Rm * w.E_local);
         d.moe_out.alloc(Rm * w.H); d.route_w.alloc(R * w.E);
         if (w.ep_dp) {
             d.g_xhi.alloc(Rm * w.H); d.g_xlo.alloc(Rm * w.H); d.g_route.alloc(Rm * w.E);
@@ -1050,6 +1075,41 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
     return ks;
 }
 
+// Grouped swap-AB GEMM over this rank's experts (decode batches): group j multiplies ITS gathered rows (block j of xhi / xlo,
+// `cap` rows, cnt[j] valid) with ITS matrix (block j of the stacked weights, Ne rows): out[ks][j * cap + n][Ne].  ONE launch over
+// (expert, weight tile, k slice) work items; an expert without rows costs nothing.  Returns the split-K factor.
+static int dense_gemm_grouped(fl_cache& c, LaunchCtx& lc, const char* tag, int groups, int cap, int Ne, int K, const CUtensorMap& tmWall,
+                              float* out, const uint16_t* xhi, const uint16_t* xlo, const int* cnt) {
+    const int nk = (K + kGemmBK - 1) / kGemmBK;
+    const int tiles = groups * ((Ne + kGemmBM - 1) / kGemmBM);
+    const int ks = pick_ksplit(tiles, nk, cap);
+    const bool prof = g_prof.on && !lc.capturing;
+    const bool pdl = lc.pdl && !prof;
+    ProfEntry pe;
+    if (prof) {
+        pe.tag = tag;
+        pe.bytes = (uint64_t)groups * Ne * K * 2;
+        FL_CUDA(cudaEventCreate(&pe.e0));
+        FL_CUDA(cudaEventCreate(&pe.e1));
+        FL_CUDA(cudaEventRecord(pe.e0, lc.stream));
+    }
+    const CUtensorMap hi = make_tmap_bf16(xhi, (uint64_t)groups * cap, K, K, cap), lo = make_tmap_bf16(xlo, (uint64_t)groups * cap, K, K, cap);
+    GemmArgs g{groups * Ne, cap, K, nullptr, nullptr, 0, out, Ne, ks, (long long)groups * cap * Ne};
+    g.grp_m = Ne; g.grp_cap = cap; g.grp_cnt = cnt;
+    switch (cap) {
+        case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+        case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+        case 64: launch_gemm_tc<64, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+        default: launch_gemm_tc<128, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+    }
+    if (prof) {
+        FL_CUDA(cudaEventRecord(pe.e1, lc.stream));
+        g_prof.entries.push_back(pe);
+    }
+    if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
+    return ks;
+}
+
 static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode) {
     const Weights& w = *c.w;
     DenseWs& d = c.dw;
@@ -1089,10 +1149,13 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 // 3 CTAs are resident per SM.  Few (sequence, kv head) pairs: ONE wave, as many splits as fit (every CTA pays the
                 // same load -> softmax -> merge latency chain once; a second, mostly empty wave would double it).  Many pairs:
                 // ~4 waves so the tail is short.  A split streams at least one 64-token page.
-                const int npages = (c.kv_len + t + kKvPage - 1) / kKvPage;
+                // The grid must NOT depend on the current KV length: this launch is captured into the step's CUDA graph, which is
+                // keyed by (batch, loop mode) only and replayed as the context grows (a serve flow captures at a one-page prompt
+                // and then decodes to thousands of tokens).  Splits beyond the last page are empty (p0 >= p1) and the merge skips
+                // them, so a fixed split count is correct at every length.
                 const int pairs = b * w.nkv, slots = 3 * kNumSMs;
                 const int want = pairs <= slots ? slots / pairs : (4 * slots + pairs - 1) / pairs;
-                const int nsp = std::max(1, std::min(std::min(c.nsplit, npages), want));
+                const int nsp = std::max(1, std::min(c.nsplit, want));
                 launch_attn_mma(lc, w.d, true, dim3(nsp, w.nkv, b), kv_bytes, at);
             } else {
                 launch_attn_mma(lc, w.d, false, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
@@ -1115,9 +1178,9 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             prep("dense_resid_rmsnorm", pa, R);
         }
         if (w.cfg.arch == FL_ARCH_MIXTRAL) {
-            // sparse MoE: route, then stream EVERY local expert once over all rows (weights of unselected experts are zero in
-            // route_w, so no host sync, no gather/scatter and a fixed summation order); at decode batch sizes the block is
-            // HBM-bound on the expert weights either way.
+            // sparse MoE: route, then (decode batches) gather each local expert's rows and run ONE grouped GEMM pair over all
+            // experts, or (prefill, > 128 rows) stream every local expert over all rows with the routing weight as a mask (zero
+            // when not selected).  No host sync either way, and a fixed summation order (experts ascending).
             launch(lc, "moe_router", 0, moe_router_kernel, dim3(R), dim3(256), 0, (const uint16_t*)d.xhi.p, (const uint16_t*)d.xlo.p, w.H,
                    (const float*)lw.wgate, w.E, w.top_k, d.route_w.p);
             // expert parallelism with data-parallel attention: DISPATCH -- this rank's rows (hi/lo halves + routing weights)
@@ -1132,11 +1195,24 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 ep_alltoall(lc, segs, 3);
                 ex_hi = d.g_xhi.p; ex_lo = d.g_xlo.p; ex_route = d.g_route.p;
             }
+            if (Rm <= 128 && !env_flag("FL_MOE_MASKED")) {
+                // decode batches: per-expert row lists + ONE grouped GEMM pair over (expert, weight tile, k slice) work items
+                const int cap = moe_group_cap(Rm), Rg = w.E_local * cap, e0 = w.rank * w.E_local;
+                MoeGatherArgs ga{ex_hi, ex_lo, ex_route, Rm, w.H, w.E, e0, w.E_local, cap, d.gx_hi.p, d.gx_lo.p, d.grp_cnt.p, d.grp_pos.p};
+                launch(lc, "moe_gather", 0, moe_gather_kernel, dim3(w.E_local, std::max(1, std::min(Rm, 2 * kNumSMs / w.E_local))), dim3(256), 0, ga);
+                int ke = dense_gemm_grouped(c, lc, "gemm_tc_moe_w13", w.E_local, cap, 2 * w.I, w.H, lw.tm_ewgu_all, d.y.p, d.gx_hi.p, d.gx_lo.p,
+                                            d.grp_cnt.p);
+                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, Rg), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)Rg * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p, (const int*)d.grp_cnt.p, cap);
+                ke = dense_gemm_grouped(c, lc, "gemm_tc_moe_w2", w.E_local, cap, w.H, w.I, lw.tm_ewdown_all, d.y.p, d.xhi2.p, d.xlo2.p, d.grp_cnt.p);
+                launch(lc, "moe_combine", 0, moe_combine_kernel, dim3((w.H + 255) / 256, Rm), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)Rg * w.H, w.H, ex_route, w.E, e0, w.E_local, (const int*)d.grp_pos.p, d.moe_out.p);
+            } else
             for (int j = 0; j < w.E_local; ++j) {
                 const int e = w.rank * w.E_local + j;
                 int ke = dense_gemm(c, lc, "gemm_tc_moe_w13", Rm, 2 * w.I, w.H, lw.tm_ewgu[j], d.y.p, ex_hi, ex_lo);
                 launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, Rm), dim3(256), 0, (const float*)d.y.p, ke,
-                       (long long)Rm * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p);
+                       (long long)Rm * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p, (const int*)nullptr, 0);
                 ke = dense_gemm(c, lc, "gemm_tc_moe_w2", Rm, w.H, w.I, lw.tm_ewdown[j], d.y.p, d.xhi2.p, d.xlo2.p);
                 launch(lc, "moe_accum", 0, moe_accum_kernel, dim3((w.H + 255) / 256, Rm), dim3(256), 0, (const float*)d.y.p, ke,
                        (long long)Rm * w.H, w.H, ex_route, w.E, e, j == 0 ? 1 : 0, d.moe_out.p);
@@ -1160,7 +1236,7 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             } else {
                 ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
                 launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
-                       (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p);
+                       (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p, (const int*)nullptr, 0);
                 ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
             }
             delta = d.y.p;
@@ -1303,6 +1379,10 @@ FL_EXPORT int fl_init(int device) {
     FL_CUDA(cudaGetDeviceProperties(&prop, device));
     FL_CHECK(prop.major == 10, FL_ERR_UNSUPPORTED,
              std::string("fastllm_b200 is built for sm_100a (B200) only; found ") + prop.name);
+    // one process drives ONE GPU (a process per GPU); per-process state -- the opt-in shared-memory
+    // attributes of the kernels, the exchange area, the communicator -- is bound to the first device
+    const int cur = g_device.load();
+    FL_CHECK(cur < 0 || cur == device, FL_ERR_STATE, "fl_init: this process is already bound to device " + std::to_string(cur));
     FL_CUDA(cudaSetDevice(device));
     g_device.store(device);
     FL_API_END
@@ -1474,7 +1554,7 @@ FL_EXPORT int fl_forward(fl_model* m, fl_cache* c, const uint32_t* ids, int b, i
         check_peer_error();
         std::memcpy(logits_host, c->h_logits.p, n * 4);
     } catch (const fl::Error& e) {
-        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;   // a missed peer leaves kv_len / exchange epochs out of step
         throw;
     }
     FL_API_END
@@ -1492,7 +1572,7 @@ FL_EXPORT int fl_forward_greedy(fl_model* m, fl_cache* c, const uint32_t* ids, i
         check_peer_error();
         std::memcpy(next_ids, c->h_ids.p, (size_t)b * 4);
     } catch (const fl::Error& e) {
-        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;   // a missed peer leaves kv_len / exchange epochs out of step
         throw;
     }
     FL_API_END
@@ -1521,10 +1601,8 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
         const bool persistent = (b == 1) && c->pk.ok;
         const bool use_graph = !persistent && !g_prof.on && !env_flag("FL_NO_GRAPH");
         GraphEntry* g = use_graph ? &get_graph(*c, b, true) : nullptr;
-        cudaEvent_t e0, e1;
-        FL_CUDA(cudaEventCreate(&e0));
-        FL_CUDA(cudaEventCreate(&e1));
-        FL_CUDA(cudaEventRecord(e0, c->stream));
+        EventPair ev;
+        FL_CUDA(cudaEventRecord(ev.e0, c->stream));
         if (persistent) {
             launch_persistent(*c, steps, true);   // all steps inside one cooperative launch
             c->kv_len += steps;
@@ -1541,17 +1619,15 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
             }
             c->kv_len += 1;
         }
-        FL_CUDA(cudaEventRecord(e1, c->stream));
+        FL_CUDA(cudaEventRecord(ev.e1, c->stream));
         FL_CUDA(cudaStreamSynchronize(c->stream));
         check_peer_error();
         float ms = 0.f;
-        FL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
+        FL_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
         if (elapsed_ms) *elapsed_ms = ms;
         if (out_ids) FL_CUDA(cudaMemcpy(out_ids, c->trace.p, (size_t)steps * b * 4, cudaMemcpyDeviceToHost));
     } catch (const fl::Error& e) {
-        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;   // a missed peer leaves kv_len / exchange epochs out of step
         throw;
     }
     FL_API_END
@@ -1633,7 +1709,7 @@ FL_EXPORT int fl_forward_sample(fl_model* m, fl_cache* c, const uint32_t* ids, i
             throw fl::Error(FL_ERR_INVALID, e.what());
         }
     } catch (const fl::Error& e) {
-        if (e.code == FL_ERR_CUDA) c->poisoned = true;
+        if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;   // a missed peer leaves kv_len / exchange epochs out of step
         throw;
     }
     FL_API_END

@@ -37,6 +37,14 @@ struct GemmArgs {
     long long split_stride;     // GEPI_F32 with ksplit > 1: split s writes its partial sums to out + s * split_stride (deterministic)
     void* out2 = nullptr;       // GEPI_SILU_HL: the lo half ([M, ldo] bf16, like `out` = the hi half)
     int w_prefetch = 0;         // DUAL_B: request the first ring-full of WEIGHT tiles before griddepcontrol.wait (see the producer)
+    // GROUPED swap-AB GEMM (DUAL_B + GEPI_F32_T; the Mixtral experts): A stacks `M / grp_m` weight matrices of grp_m rows each,
+    // B stacks one block of grp_cap (<= BN) activation rows per group -- the rows routed to that expert, gathered -- and group j
+    // multiplies ITS rows with ITS matrix: out[slice][j * grp_cap + n][row within the group].  grp_cnt[j] (device memory, written
+    // by the gather kernel) is the number of valid rows: a group without rows is skipped entirely (no weight traffic), columns
+    // past the count are not stored.
+    int grp_m = 0;
+    int grp_cap = 0;
+    const int* grp_cnt = nullptr;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -150,8 +158,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (g.K + kGemmBK - 1) / kGemmBK;
-    const int mt = (g.M + kGemmBM - 1) / kGemmBM, nt = (g.N + BN - 1) / BN;
+    const bool grouped = (DUAL == DUAL_B) && g.grp_m > 0;
+    const int mt_e = grouped ? (g.grp_m + kGemmBM - 1) / kGemmBM : 0;      // m tiles per group
+    const int mt = grouped ? (g.M / g.grp_m) * mt_e : (g.M + kGemmBM - 1) / kGemmBM, nt = grouped ? 1 : (g.N + BN - 1) / BN;
     const int ksplit = g.ksplit > 1 ? g.ksplit : 1;
+    // tile -> (first row of the A box, first row of the B box, group, first row inside the group)
+    auto coords = [&](int tile, int& m0, int& n0, int& grp, int& mrow0) {
+        if (grouped) {
+            grp = tile / mt_e;
+            mrow0 = (tile % mt_e) * kGemmBM;
+            m0 = grp * g.grp_m + mrow0;
+            n0 = grp * g.grp_cap;
+        } else {
+            grp = 0;
+            m0 = mrow0 = (tile / nt) * kGemmBM;
+            n0 = (tile % nt) * BN;
+        }
+    };
     const int nkps = (nk + ksplit - 1) / ksplit;          // k-blocks per split
     const int ntiles = mt * nt * ksplit;                  // work items: (m tile, n tile, k split), k split fastest
 
@@ -205,7 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t c = 0;
             for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
                 const int tile = item / ksplit, ks = item % ksplit;
-                const int m0 = (tile / nt) * kGemmBM, n0 = (tile % nt) * BN;
+                int m0, n0, grp, mrow0;
+                coords(tile, m0, n0, grp, mrow0);
+                if (grouped && g.grp_cnt[grp] == 0) continue;      // no row was routed to this expert: its weights are not read
                 const int kb1 = min((ks + 1) * nkps, nk);
                 for (int kb = ks * nkps; kb < kb1; ++kb, ++c) {
                     const int st = c % kStages;
@@ -234,11 +259,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
             uint32_t c = 0, ti = 0;
-            for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++ti) {
+            if (grouped) pdl_wait();      // grp_cnt is written by the preceding kernel
+            for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
+                if (grouped && g.grp_cnt[(item / ksplit) / mt_e] == 0) continue;
+                const uint32_t ti_now = ti++;
                 const int ks = item % ksplit;
                 const int kb0 = ks * nkps, kb1 = min((ks + 1) * nkps, nk);
-                const uint32_t as = ti & 1;
-                mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator stage
+                const uint32_t as = ti_now & 1;
+                mbar_wait(&acc_empty[as], ((ti_now >> 1) & 1) ^ 1);     // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * kAccCols;
                 for (int kb = kb0; kb < kb1; ++kb, ++c) {
@@ -269,18 +297,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int cslice = (warp - 2) >> 2;
         uint32_t ti = 0;
-        for (int item = blockIdx.x; item < ntiles; item += gridDim.x, ++ti) {
+        if (grouped) pdl_wait();          // grp_cnt is written by the preceding kernel
+        for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
             const int tile = item / ksplit, ksi = item % ksplit;
-            const int m0 = (tile / nt) * kGemmBM, n0 = (tile % nt) * BN;
-            const uint32_t as = ti & 1;
-            const int row = m0 + q * 32 + lane;
-            mbar_wait(&acc_full[as], (ti >> 1) & 1);
+            int m0, n0, grp, mrow0;
+            coords(tile, m0, n0, grp, mrow0);
+            const int gcnt = grouped ? g.grp_cnt[grp] : 0;
+            if (grouped && gcnt == 0) continue;
+            const uint32_t ti_now = ti++;
+            const uint32_t as = ti_now & 1;
+            // grouped: `row` counts inside the group's matrix and the columns are the group's block of the stacked output
+            const int row = mrow0 + q * 32 + lane;
+            const int row_lim = grouped ? g.grp_m : g.M, col_lim = grouped ? gcnt : g.N;
+            if (grouped) n0 = 0;
+            mbar_wait(&acc_full[as], (ti_now >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = cslice * 32; c0 < BN; c0 += 128) {      // 32-column chunks dealt round-robin to the 4 warps of a lane quarter
                 uint32_t r[32];
                 tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                if (row < g.M) {
+                if (row < row_lim) {
                     const int col = n0 + c0;
                     if (EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16) {
                         uint16_t* o = reinterpret_cast<uint16_t*>(g.out) + (size_t)row * g.ldo + col;
@@ -325,10 +361,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (EPI == GEPI_F32_T) {
                         // transposed store: D[row = weight row, col = activation row] -> out[slice][col, row]; for a fixed col the
                         // 32 lanes of the warp write 32 consecutive floats
-                        float* o = reinterpret_cast<float*>(g.out) + (size_t)ksi * (size_t)g.split_stride + row;
+                        float* o = reinterpret_cast<float*>(g.out) + (size_t)ksi * (size_t)g.split_stride + (size_t)grp * g.grp_cap * g.ldo + row;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (col + j < g.N) o[(size_t)(col + j) * g.ldo] = __uint_as_float(r[j]);
+                            if (col + j < col_lim) o[(size_t)(col + j) * g.ldo] = __uint_as_float(r[j]);
                     } else if (EPI == GEPI_ATOMIC_F32) {
                         // split-K partial sums meet in a pre-zeroed f32 buffer (vector red.global.add, sm_90+)
                         float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;

@@ -27,6 +27,9 @@ struct LayerW {
     float* wgate = nullptr;                         // [E, H] f32 (bf16-rounded values)
     std::vector<uint16_t*> ewgu, ewdown;
     std::vector<CUtensorMap> tm_ewgu, tm_ewdown;
+    // the same expert matrices as ONE stacked tensor each (they are allocated back to back): [E_local * 2I, H] and
+    // [E_local * H, I], the A operands of the grouped expert GEMMs
+    CUtensorMap tm_ewgu_all, tm_ewdown_all;
 };
 
 // Immutable after finalize; shared (ref-counted) between fl_model clones and their caches.
@@ -54,6 +57,7 @@ struct Weights {
     float* rope_cos = nullptr;  // [max_pos, d/2]
     float* rope_sin = nullptr;
     std::set<std::string> have; // tensor names that arrived
+    int ignored = 0;            // tensors handed over that the architecture does not read (skipped like VarBuilder does)
     bool lm_head_loaded = false;
     bool finalized = false;
     uint64_t streamed_bytes = 0;
@@ -79,6 +83,10 @@ struct DenseWs {
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
     DevBuf<float> moe_out, route_w;
+    // grouped expert GEMMs (decode batches): per-expert blocks of gathered rows, their counts, and the row -> slot map
+    int grp_cap = 0;                 // rows per expert block (the GEMM's N tile: 16 / 32 / 64 / 128)
+    DevBuf<uint16_t> gx_hi, gx_lo;   // [E_local * grp_cap, H]
+    DevBuf<int> grp_cnt, grp_pos;    // [E_local], [moe_rows, E_local]
     // expert parallelism with data-parallel attention: dispatch / combine staging (all rows of all ranks, rank-major)
     size_t moe_rows = 0;         // rows the expert GEMMs see (rows, or rows * ep)
     DevBuf<uint16_t> g_xhi, g_xlo;   // [ep * rows, H] gathered block inputs

@@ -75,6 +75,24 @@ inline void launch(LaunchCtx& lc, const char* tag, uint64_t bytes, void (*kern)(
         g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
+// a start / stop event pair that cannot leak when something between create and destroy throws
+struct EventPair {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    EventPair() {
+        FL_CUDA(cudaEventCreate(&e0));
+        if (cudaEventCreate(&e1) != cudaSuccess) {
+            cudaEventDestroy(e0);
+            throw Error(-2, "cudaEventCreate failed");
+        }
+    }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+    ~EventPair() {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;

@@ -19,11 +19,12 @@ def test_workloads_cover_baseline_configs():
 
 
 def test_ncu_traffic_matches_algorithmic_bytes():
-    """profiles/r01_persistent_final_full_raw.csv: DRAM bytes per decode step of the persistent kernel == weights once + KV once
-    (Mistral-7B b=1, KV 2048: 14.490 GB) within 1 %."""
+    """profiles/rNN_persistent*_full_raw.csv (newest round): DRAM bytes per decode step of the persistent kernel == weights once +
+    KV once (Mistral-7B b=1, KV 2048: 14.490 GB) within 1 %, and the line names the file it comes from."""
     import bench
-    t = bench.ncu_traffic_per_step()
+    t, src = bench.ncu_traffic_per_step()
     assert t is not None and abs(t / 14.490e9 - 1.0) < 0.01, t
+    assert "profiles/" in src
 
 
 def test_reference_arm_answers_for_workloads_without_a_cpu_leg():
@@ -39,3 +40,24 @@ def test_peaks_come_from_measured_file_or_documented_fallback():
     hbm, src = bench.peaks("hbm")
     tf, _ = bench.peaks("tensor")
     assert 5000 < hbm < 9000 and 1000 < tf < 2500 and ("measured" in src or "fallback" in src)
+
+
+def test_reference_arm_times_whole_steps_with_every_core_under_a_launcher_that_pins_one_thread():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm (rank 0 alone) must still use every host core, and when the
+    model fits the host it times WHOLE decode steps (TinyLlama: 4.1 GB f32), so ms_per_step x steps is time actually spent."""
+    import time
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    t0 = time.time()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tinyllama_b1", "--gpus", "2",
+                        "--steps", "6", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    wall = time.time() - t0
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["extrapolated"] is False and line["cpu_baseline"]["extrapolated"] is False
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) or (os.cpu_count() or 1) == 1
+    assert line["steps"] * line["ms_per_step"] / 1e3 < wall       # the claimed steps fit inside the run
+    # the other ranks of the launch exit without work and without output
+    env["RANK"] = "1"
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tinyllama_b1", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""

@@ -265,3 +265,38 @@ def test_tensor_core_attention_long_context(name, b, t, steps):
         errs.append(float(np.abs(want - got).max()))
     print(f"{name} b={b} t={t}: max-abs logits err per call {['%.2e' % e for e in errs]}")
     assert max(errs) <= KERNEL_TOL
+
+
+def test_mixtral_masked_prefill_and_grouped_decode_agree(monkeypatch):
+    """The MoE block has two execution plans: calls with more than 128 expert rows (prefill) stream every expert over all rows
+    with the routing weight as a mask; decode batches gather per-expert row lists and run ONE grouped GEMM pair.  A 150-row
+    prefill (masked), batch-3 decode steps (grouped, experts with 0..3 rows), and the same decode steps forced onto the masked
+    plan: all against the oracle."""
+    from dataclasses import replace
+    from fastllm_b200 import models
+    cfg = replace(TINY["mixtral"], max_position_embeddings=256)
+    w = ocl.synth_weights(cfg, 17, 0.08)
+    model, _ = product_model(cfg, w)
+    prompts = synth.token_ids(33, cfg.vocab_size, (3, 50))
+
+    def run(masked):
+        if masked:
+            monkeypatch.setenv("FL_MOE_MASKED", "1")
+        else:
+            monkeypatch.delenv("FL_MOE_MASKED", raising=False)
+        oracle = ocl.CausalLM(cfg, w, kv_dtype="bf16")
+        cache = models.DeviceCache(model.dev, 3, 128)
+        want, got = oracle.forward(prompts, 0), cache.forward(prompts, 0)
+        outs, errs = [got], [float(np.abs(want - got).max())]
+        for s in range(4):
+            nxt = np.array([[models.sample_argmax(r)] for r in got], dtype=np.uint32)
+            want, got = oracle.forward(nxt, 50 + s), cache.forward(nxt, 50 + s)
+            outs.append(got)
+            errs.append(float(np.abs(want - got).max()))
+        return np.stack(outs), max(errs)
+
+    grouped, e_g = run(False)
+    masked, e_m = run(True)
+    print(f"mixtral tiny: grouped-plan err {e_g:.2e}, masked-plan err {e_m:.2e}, plans differ by {np.abs(grouped - masked).max():.2e}")
+    assert e_g <= KERNEL_TOL and e_m <= KERNEL_TOL
+    assert np.array_equal(grouped[0], masked[0])          # the prefill runs the masked plan either way
