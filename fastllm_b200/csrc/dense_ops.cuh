@@ -243,7 +243,7 @@ struct MoeGatherArgs {
     int* cnt;
     int* pos;
 };
-static __global__ void __launch_bounds__(256) moe_gather_kernel(const MoeGatherArgs a) {
+static __global__ void moe_gather_kernel(const MoeGatherArgs a) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ int s_list[256];
