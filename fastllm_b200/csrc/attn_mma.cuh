@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_gqa_decode_kernel(const 
     pdl_launch_dependents();
     pdl_wait();
 
-    const int len = a.state->kv_base[seq] + 1;
+    const int cslot = st_slot(a.state, seq);          // ragged batches: every sequence has its own cache slot and length
+    const int len = a.state->kv_base[cslot] + 1;
     const int npages = (len + kKvPage - 1) / kKvPage;
     const int per = (npages + nsplit - 1) / nsplit;
     const int p0 = split * per, p1 = min(p0 + per, npages);
-    const int* pt = a.page_table + (size_t)seq * a.pt_stride;
+    const int* pt = a.page_table + (size_t)cslot * a.pt_stride;
 
     auto load = [&](int p, int st) {
         const size_t off = ((size_t)pt[p] * a.nkv + kvh) * (size_t)TILE;
@@ -298,9 +299,10 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_prefill_kernel(const Att
     pdl_launch_dependents();
     pdl_wait();
     const int i0 = qt * kPrefillBM;
-    const int kv_base = a.state->kv_base[seq];
+    const int cslot = st_slot(a.state, seq);
+    const int kv_base = a.state->kv_base[cslot];
     const int sw = a.sliding_window;
-    const int* pt = a.page_table + (size_t)seq * a.pt_stride;
+    const int* pt = a.page_table + (size_t)cslot * a.pt_stride;
 
     // key range of the whole tile
     const int ilast = min(i0 + kPrefillBM, a.t) - 1;

@@ -1,7 +1,8 @@
 // BERT / MiniLM encoder glue kernels around the tcgen05 GEMM (gemm_tc.cuh), sm_100a.
 // Semantics follow the reference's hand-written encoder line by line (src/models/embeddings.rs):
 //   embed_ln_kernel   : word + position embedding gather, add, LayerNorm eps = 1e-12 literal, NO token-type (:370-378, :315-318)
-//   bert_attn_kernel  : per (sentence, head): softmax(Q K^T / sqrt(d)) V, NO attention / padding mask (:130-166)
+//   bert_attn_kernel  : per (sentence, head): softmax(Q K^T / sqrt(d)) V, NO attention / padding mask (:130-166); sentences of
+//                       more than 128 tokens go through bert_attn_long_kernel (key tiles + online softmax)
 //   layernorm_kernel  : post-LN over (x + f(x)), eps = config.layer_norm_eps (:185-190, :236-241); one-pass var = E[x^2]-mean^2
 //   pool_l2_kernel    : masked mean pooling (divisor = mask_count * hidden [sic], :346-368) + L2 normalise (:341-344)
 #pragma once
@@ -77,7 +78,7 @@ static __global__ void layernorm_kernel(const float* __restrict__ x, const float
 }
 
 // ---- fused small-head attention (t <= 128, d = 32) on mma.sync m16n8k16 bf16 ------------------------------------------
-constexpr int kBertS = 128;      // max tokens per sentence handled by the fused kernel
+constexpr int kBertS = 128;      // query / key rows per tile (a sentence of <= 128 tokens is ONE tile: bert_attn_kernel)
 constexpr int kBertD = 32;       // head dim
 constexpr int kBertLd = 40;      // padded smem row (80 bytes): conflict-free ldmatrix
 
@@ -174,6 +175,128 @@ static __global__ void __launch_bounds__(128) bert_attn_kernel(const uint16_t* _
             const int c = head * kBertD + dt * 8 + tq * 2;
             if (r0 < t) *reinterpret_cast<uint32_t*>(ctx + (row0 + r0) * H + c) = pack_bf16(o[dt][0] * i0, o[dt][1] * i0);
             if (r1 < t) *reinterpret_cast<uint32_t*>(ctx + (row0 + r1) * H + c) = pack_bf16(o[dt][2] * i1, o[dt][3] * i1);
+        }
+    }
+}
+
+// Sentences longer than one 128-row tile (up to max_position_embeddings, 512 for MiniLM: the reference enforces no limit,
+// embeddings.rs:285-286): the same attention, FlashAttention-style.  grid (heads, sentences, ceil(t / 128) query tiles), 128 threads;
+// a CTA stages its 128 query rows once and walks the sentence's keys in 128-row tiles with an online softmax (running max / sum per
+// row, accumulator rescaled when the max moves) -- algebraically the reference's max-subtract / exp / sum / div over all keys.
+static __global__ void __launch_bounds__(128) bert_attn_long_kernel(const uint16_t* __restrict__ qkv, int t, int H, float scale,
+                                                                    uint16_t* __restrict__ ctx) {
+    __shared__ __align__(16) uint16_t sq[kBertS * kBertLd], sk[kBertS * kBertLd], sv[kBertS * kBertLd];
+    const int head = blockIdx.x, sent = blockIdx.y, q0 = blockIdx.z * kBertS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t row0 = (size_t)sent * t;
+    const int ld = 3 * H;
+    for (int i = tid; i < kBertS * 4; i += 128) {
+        const int r = i >> 2, c = (i & 3) * 8;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (q0 + r < t) q = *reinterpret_cast<const uint4*>(qkv + (row0 + q0 + r) * ld + head * kBertD + c);
+        *reinterpret_cast<uint4*>(sq + r * kBertLd + c) = q;
+    }
+    __syncthreads();
+    const int g = lane >> 2, tq = lane & 3;
+    const float inv_scale = 1.f / scale;
+    uint32_t qa[2][2][4];
+    float o[2][4][4], mrun[2][2], lrun[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[mt][ks], sq + (warp * 32 + mt * 16 + (lane & 15)) * kBertLd + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) o[mt][dt][0] = o[mt][dt][1] = o[mt][dt][2] = o[mt][dt][3] = 0.f;
+        mrun[mt][0] = mrun[mt][1] = -INFINITY;
+        lrun[mt][0] = lrun[mt][1] = 0.f;
+    }
+    for (int k0 = 0; k0 < t; k0 += kBertS) {
+        __syncthreads();      // the previous key tile is no longer being read
+        for (int i = tid; i < kBertS * 4; i += 128) {
+            const int r = i >> 2, c = (i & 3) * 8;
+            uint4 k = make_uint4(0, 0, 0, 0), v = k;
+            if (k0 + r < t) {
+                const uint16_t* src = qkv + (row0 + k0 + r) * ld + head * kBertD + c;
+                k = *reinterpret_cast<const uint4*>(src + H);
+                v = *reinterpret_cast<const uint4*>(src + 2 * H);
+            }
+            *reinterpret_cast<uint4*>(sk + r * kBertLd + c) = k;
+            *reinterpret_cast<uint4*>(sv + r * kBertLd + c) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            if (q0 + warp * 32 + mt * 16 >= t) continue;
+            float s[16][4];
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t kb[2];
+                    ldmatrix_x2(kb, sk + (nt * 8 + (lane & 7)) * kBertLd + ks * 16 + ((lane >> 3) & 1) * 8);
+                    mma_bf16_16816(s[nt], qa[mt][ks], kb);
+                }
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int key = k0 + nt * 8 + tq * 2 + (e & 1);
+                    s[nt][e] = key < t ? s[nt][e] * inv_scale : -INFINITY;
+                }
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
+            const float mn0 = fmaxf(mrun[mt][0], mx0), mn1 = fmaxf(mrun[mt][1], mx1);      // finite: the tile holds key k0 < t
+            const float al0 = __expf(mrun[mt][0] - mn0), al1 = __expf(mrun[mt][1] - mn1);
+            mrun[mt][0] = mn0; mrun[mt][1] = mn1;
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                s[nt][0] = __expf(s[nt][0] - mn0); s[nt][1] = __expf(s[nt][1] - mn0);
+                s[nt][2] = __expf(s[nt][2] - mn1); s[nt][3] = __expf(s[nt][3] - mn1);
+                ps0 += s[nt][0] + s[nt][1];
+                ps1 += s[nt][2] + s[nt][3];
+            }
+            lrun[mt][0] = lrun[mt][0] * al0 + ps0;      // per-thread partial row sums; the quad is reduced once at the end
+            lrun[mt][1] = lrun[mt][1] * al1 + ps1;
+#pragma unroll
+            for (int dt = 0; dt < 4; ++dt) {
+                o[mt][dt][0] *= al0; o[mt][dt][1] *= al0; o[mt][dt][2] *= al1; o[mt][dt][3] *= al1;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t pa[4];
+                pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+                pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+                pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+                pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+                for (int dt = 0; dt < 4; ++dt) {
+                    uint32_t vb[2];
+                    ldmatrix_x2_trans(vb, sv + (ks * 16 + (lane & 15)) * kBertLd + dt * 8);
+                    mma_bf16_16816(o[mt][dt], pa, vb);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int m0 = q0 + warp * 32 + mt * 16;
+        if (m0 >= t) continue;
+        float l0 = lrun[mt][0], l1 = lrun[mt][1];
+        l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 1); l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 2);
+        l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 1); l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        const int r0 = m0 + g, r1 = m0 + g + 8;
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) {
+            const int c = head * kBertD + dt * 8 + tq * 2;
+            if (r0 < t) *reinterpret_cast<uint32_t*>(ctx + (row0 + r0) * H + c) = pack_bf16(o[mt][dt][0] * i0, o[mt][dt][1] * i0);
+            if (r1 < t) *reinterpret_cast<uint32_t*>(ctx + (row0 + r1) * H + c) = pack_bf16(o[mt][dt][2] * i1, o[mt][dt][3] * i1);
         }
     }
 }

@@ -132,10 +132,11 @@ static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
     }
     if (a.bias) { va += a.bias[ra]; vb += a.bias[ra + 1]; }
     const int seq = row / a.t, irel = row % a.t;
-    const int slot = a.state->kv_base[seq] + irel;
-    const int page = a.page_table[seq * a.pt_stride + slot / kKvPage];
+    const int cslot = st_slot(a.state, seq);                    // cache slot of this sequence (its own index unless the call is ragged)
+    const int slot = a.state->kv_base[cslot] + irel;
+    const int page = a.page_table[cslot * a.pt_stride + slot / kKvPage];
     if (hh < a.nh + a.nkv) {
-        int pos = a.state->rope_pos + irel;
+        int pos = st_rope(a.state, seq) + irel;
         pos = pos < a.max_pos ? pos : a.max_pos - 1;
         const float cs = a.rope_cos[(size_t)pos * half + j], sn = a.rope_sin[(size_t)pos * half + j];
         const float o1 = va * cs - vb * sn, o2 = va * sn + vb * cs;

@@ -65,13 +65,14 @@ static __global__ void advance_state_kernel(StepState* st, int b, int t, int rop
     pdl_wait();
     const int i = threadIdx.x;
     if (i < b) {
-        st->kv_base[i] += t;
+        st->kv_base[st_slot(st, i)] += t;       // distinct slots per row (checked on the host)
         if (feedback) ids[i] = next_ids[i];
         if (trace != nullptr) trace[(size_t)(*trace_pos) * b + i] = next_ids[i];
     }
     __syncthreads();
     if (i == 0) {
         st->rope_pos += rope_inc;
+        st->ragged = 0;                         // the slot / position tables are valid for ONE call
         if (trace != nullptr) *trace_pos += 1;
     }
 }
@@ -104,10 +105,81 @@ static __global__ void tp_logits_kernel(const float* __restrict__ g, int tp, int
     }
 }
 
+// ---- opt-in device-side temperature sampling (fl_forward_sample_device; the parity path stays the host sampler) --------------
+// candle's LogitsProcessor with a temperature: prs = softmax(logits / T); WeightedIndex::new(prs).sample(rng) = the first index
+// whose cumulative weight exceeds x = u * total, u being ONE draw of the request's StdRng.  The host sampler object keeps the
+// generator and hands over u (so the random stream of a request is the same as on the host path); the soft-max weights, their
+// prefix sums and the search run here, on the logits row that is already in HBM: 4 bytes travel back instead of vocab * 4.
+// Difference to the host path: the prefix sums are built by a block scan (1024 partial sums) instead of one sequential f32 loop,
+// so a draw that lands within rounding distance (~1e-6 relative) of a boundary between two tokens may pick the neighbour.
+static __global__ void __launch_bounds__(1024) sample_softmax_kernel(const float* __restrict__ logits, int V, float mul, float u01,
+                                                                    uint32_t* __restrict__ out) {
+    __shared__ float red[32];
+    __shared__ float wtot[32];
+    __shared__ int s_pick;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (V + 1023) / 1024, i0 = min(tid * per, V), i1 = min(i0 + per, V);
+    float mx = -INFINITY;
+    for (int i = i0; i < i1; ++i) mx = fmaxf(mx, logits[i] * mul);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    if (tid == 0) s_pick = -1;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < 32; ++w) mx = fmaxf(mx, red[w]);
+    float sum = 0.f;
+    for (int i = i0; i < i1; ++i) sum += expf(logits[i] * mul - mx);
+    float inc = sum;                                   // inclusive scan over the 1024 chunk sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        float v = wtot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += t;
+        }
+        wtot[lane] = v;
+    }
+    __syncthreads();
+    const float base = warp ? wtot[warp - 1] : 0.f;
+    float excl = __shfl_up_sync(0xFFFFFFFFu, inc, 1);  // the intervals [excl, inc) of consecutive threads tile [0, total) exactly
+    excl = (lane ? excl : 0.f) + base;
+    inc += base;
+    const float chosen = u01 * wtot[31];
+    if (i0 < i1 && excl <= chosen && chosen < inc) {
+        float run = excl;
+        int pick = -1, last = i0;
+        for (int i = i0; i < i1 && pick < 0; ++i) {
+            const float wgt = expf(logits[i] * mul - mx);
+            if (wgt > 0.f) last = i;
+            run += wgt;
+            if (run > chosen) pick = i;
+        }
+        s_pick = pick >= 0 ? pick : last;
+    }
+    __syncthreads();
+    if (tid == 0) out[0] = (uint32_t)(s_pick >= 0 ? s_pick : V - 1);
+}
+
 static __global__ void set_state_kernel(StepState* st, int rope_pos) { st->rope_pos = rope_pos; }
 static __global__ void reset_state_kernel(StepState* st, int kv_len) {
     for (int i = threadIdx.x; i < kMaxBatch; i += blockDim.x) st->kv_base[i] = kv_len;
-    if (threadIdx.x == 0) st->rope_pos = 0;
+    if (threadIdx.x == 0) { st->rope_pos = 0; st->ragged = 0; }
 }
+// fl_forward_slots: batch row i runs on cache slot tab[i] at RoPE position tab[n + i]
+static __global__ void set_slots_kernel(StepState* st, const int* __restrict__ tab, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        st->slot[i] = tab[i];
+        st->rope_seq[i] = tab[n + i];
+    }
+    if (threadIdx.x == 0) st->ragged = 1;
+}
+static __global__ void reset_slot_kernel(StepState* st, int slot) { st->kv_base[slot] = 0; }
 
 }  // namespace fl

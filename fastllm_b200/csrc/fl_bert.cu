@@ -259,7 +259,10 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
         // B2: fused q|k|v projection + bias -> bf16 [T, 3H]
         launch_gemm<GEPI_BIAS_BF16>(st, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
         // B3+B4: per (sentence, head) softmax(QK^T / sqrt(d)) V, no mask
-        bert_attn_kernel<<<dim3(m.nh, b), 128, 0, st>>>(m.qkv.p, t, H, scale, m.ctx.p);
+        if (t <= kBertS)
+            bert_attn_kernel<<<dim3(m.nh, b), 128, 0, st>>>(m.qkv.p, t, H, scale, m.ctx.p);
+        else
+            bert_attn_long_kernel<<<dim3(m.nh, b, (t + kBertS - 1) / kBertS), 128, 0, st>>>(m.qkv.p, t, H, scale, m.ctx.p);
         g_launches.fetch_add(1);
         // B5: attention output dense + bias + residual -> f32, then LayerNorm -> bf16
         launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
@@ -280,7 +283,9 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
 void bert_embed(BertModel& m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out, float* device_ms) {
     FL_CHECK(m.finalized, FL_ERR_STATE, "model not finalized");
     FL_CHECK(ids && out && b >= 1 && t >= 1, FL_ERR_INVALID, "bad arguments");
-    FL_CHECK(t <= kBertS, FL_ERR_UNSUPPORTED, "BERT path handles at most 128 tokens per sentence in this round");
+    // the reference enforces no max_seq_length (embeddings.rs:285-286); what bounds a sentence is its position table: position ids
+    // 0..n index a [max_position_embeddings, H] embedding (embeddings.rs:416, 370-378), and candle's index_select fails past it
+    FL_CHECK(t <= m.maxpos, FL_ERR_INVALID, "sentence longer than max_position_embeddings (the position-embedding lookup fails in the reference too)");
     for (int i = 0; i < b * t; ++i) FL_CHECK(ids[i] < (uint32_t)m.V, FL_ERR_INVALID, "token id out of range");
     std::lock_guard<std::mutex> lock(m.mu);      // embed(&self) may be called from several threads: one workspace
     bert_reserve(m, b, t);

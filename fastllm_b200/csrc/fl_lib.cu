@@ -766,6 +766,10 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     c.amax_idx.alloc((size_t)kPassRows * c.amax_parts);
     c.h_ids.alloc((size_t)max_batch * max_seq);
     c.h_logits.alloc((size_t)max_batch * w.Vfull);
+    c.slot_len.assign(max_batch, 0);
+    c.slot_tab.alloc(2 * (size_t)max_batch);
+    c.h_slot_tab.alloc(2 * (size_t)max_batch);
+    c.sample_out.alloc(1, true);
     plan_persistent(c);
     const size_t smem = attn_smem_bytes(w.d, w.nh / w.nkv);
     switch (w.d) {
@@ -1270,8 +1274,11 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
     lc.pdl = saved_pdl;
 }
 
-static GraphEntry& get_graph(fl_cache& c, int b, bool loop_mode) {
-    const GraphKey key{b, loop_mode ? 1 : 0};
+// mode 0: one decode step of a uniform batch; 1: the same inside the device-resident greedy loop; 2: one decode step of a ragged
+// batch (fl_forward_slots: always the dense path, whatever the row count)
+static GraphEntry& get_graph(fl_cache& c, int b, int mode) {
+    const bool loop_mode = mode == 1;
+    const GraphKey key{b, mode};
     auto it = c.graphs.find(key);
     if (it != c.graphs.end()) return it->second;
     LaunchCtx lc;
@@ -1281,7 +1288,8 @@ static GraphEntry& get_graph(fl_cache& c, int b, bool loop_mode) {
     cudaGraph_t graph = nullptr;
     FL_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
     try {
-        enqueue_forward(c, lc, b, 1, loop_mode);
+        if (mode == 2) enqueue_forward_dense(c, lc, b, 1, false);
+        else enqueue_forward(c, lc, b, 1, loop_mode);
     } catch (...) {
         cudaStreamEndCapture(c.stream, &graph);
         if (graph) cudaGraphDestroy(graph);
@@ -1298,6 +1306,7 @@ static GraphEntry& get_graph(fl_cache& c, int b, bool loop_mode) {
 static void check_call(fl_cache& c, const uint32_t* ids, int b, int t, size_t rope_offset, int extra_steps) {
     const Weights& w = *c.w;
     FL_CHECK(!c.poisoned, FL_ERR_CUDA, "cache poisoned by an earlier CUDA error");
+    FL_CHECK(!c.slots_used, FL_ERR_STATE, "this cache is driven by sequence slots (fl_forward_slots): call fl_cache_reset before a uniform call");
     FL_CHECK(ids != nullptr, FL_ERR_INVALID, "ids is NULL");
     FL_CHECK(b >= 1 && b <= c.max_batch && t >= 1, FL_ERR_INVALID, "bad batch / sequence length");
     FL_CHECK(c.kv_len + t + extra_steps <= c.max_seq, FL_ERR_STATE, "KV cache full (kv_len + t > max_seq)");
@@ -1319,7 +1328,7 @@ static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t r
     if (b == 1 && t == 1 && c.pk.ok) {
         launch_persistent(c, 1, false);
     } else if (use_graph) {
-        GraphEntry& g = get_graph(c, b, false);
+        GraphEntry& g = get_graph(c, b, 0);
         FL_CUDA(cudaGraphLaunch(g.exec, c.stream));
         g_launches.fetch_add(g.kernels);
     } else {
@@ -1329,6 +1338,52 @@ static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t r
         enqueue_forward(c, lc, b, t, false);
     }
     c.kv_len += t;
+}
+
+// Ragged forward (continuous batching): batch row i is the sequence in cache slot slots[i], which holds slot_len[slots[i]]
+// tokens and is fed t new ones at RoPE position rope_offsets[i].  Every kernel of the dense path reads the per-row slot / position
+// from the step state, so sequences of different lengths share one step; the call always takes the dense (tcgen05) path.
+static void run_forward_slots(fl_cache& c, const int* slots, const uint32_t* ids, int n, int t, const size_t* rope_offsets) {
+    const Weights& w = *c.w;
+    FL_CHECK(!c.poisoned, FL_ERR_CUDA, "cache poisoned by an earlier CUDA error");
+    FL_CHECK(slots && ids && rope_offsets, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(n >= 1 && n <= c.max_batch && t >= 1, FL_ERR_INVALID, "bad batch / sequence length");
+    FL_CHECK(w.dense_ok, FL_ERR_UNSUPPORTED, "ragged batches run on the dense path: shapes must be multiples of 8");
+    FL_CHECK(c.slots_used || c.kv_len == 0, FL_ERR_STATE, "the cache holds tokens of uniform calls: fl_cache_reset before driving it by slots");
+    std::vector<char> seen(c.max_batch, 0);
+    for (int i = 0; i < n; ++i) {
+        const int sl = slots[i];
+        FL_CHECK(sl >= 0 && sl < c.max_batch, FL_ERR_INVALID, "slot index out of range");
+        FL_CHECK(!seen[sl], FL_ERR_INVALID, "a slot appears twice in one call");
+        seen[sl] = 1;
+        FL_CHECK(c.slot_len[sl] + t <= c.max_seq, FL_ERR_STATE, "KV cache full (slot length + t > max_seq)");
+        FL_CHECK((int64_t)rope_offsets[i] + t <= w.max_pos, FL_ERR_INVALID, "RoPE position beyond max_position_embeddings");
+        FL_CHECK(!(w.cfg.arch == FL_ARCH_LLAMA && t > 1 && c.slot_len[sl] != 0), FL_ERR_INVALID,
+                 "Llama: multi-token forward needs an empty cache (candle builds a t x t mask)");
+    }
+    for (int i = 0; i < n * t; ++i) FL_CHECK(ids[i] < (uint32_t)w.Vfull, FL_ERR_INVALID, "token id out of range");
+    ensure_dense_ws(c, n * t);
+    c.slots_used = true;
+    std::memcpy(c.h_ids.p, ids, (size_t)n * t * 4);
+    for (int i = 0; i < n; ++i) {
+        c.h_slot_tab.p[i] = slots[i];
+        c.h_slot_tab.p[n + i] = (int)rope_offsets[i];
+    }
+    FL_CUDA(cudaMemcpyAsync(c.ids.p, c.h_ids.p, (size_t)n * t * 4, cudaMemcpyHostToDevice, c.stream));
+    FL_CUDA(cudaMemcpyAsync(c.slot_tab.p, c.h_slot_tab.p, (size_t)2 * n * 4, cudaMemcpyHostToDevice, c.stream));
+    set_slots_kernel<<<1, 256, 0, c.stream>>>(c.state.p, c.slot_tab.p, n);
+    g_launches.fetch_add(1);
+    if (t == 1 && !g_prof.on && !env_flag("FL_NO_GRAPH")) {
+        GraphEntry& g = get_graph(c, n, 2);
+        FL_CUDA(cudaGraphLaunch(g.exec, c.stream));
+        g_launches.fetch_add(g.kernels);
+    } else {
+        LaunchCtx lc;
+        lc.stream = c.stream;
+        lc.pdl = !env_flag("FL_NO_PDL");
+        enqueue_forward_dense(c, lc, n, t, false);
+    }
+    for (int i = 0; i < n; ++i) c.slot_len[slots[i]] += t;
 }
 
 }  // namespace fl
@@ -1504,6 +1559,27 @@ FL_EXPORT int fl_cache_reset(fl_cache* c) {
     g_launches.fetch_add(1);
     FL_CUDA(cudaStreamSynchronize(c->stream));
     c->kv_len = 0;
+    c->slots_used = false;
+    std::fill(c->slot_len.begin(), c->slot_len.end(), 0);
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_slot_reset(fl_cache* c, int slot) {
+    FL_API_BEGIN
+    FL_CHECK(c, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(slot >= 0 && slot < c->max_batch, FL_ERR_INVALID, "slot index out of range");
+    use_device();
+    reset_slot_kernel<<<1, 1, 0, c->stream>>>(c->state.p, slot);
+    g_launches.fetch_add(1);
+    c->slot_len[slot] = 0;
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_slot_len(fl_cache* c, int slot, int* out) {
+    FL_API_BEGIN
+    FL_CHECK(c && out, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(slot >= 0 && slot < c->max_batch, FL_ERR_INVALID, "slot index out of range");
+    *out = c->slot_len[slot];
     FL_API_END
 }
 
@@ -1600,7 +1676,7 @@ FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* fi
         g_launches.fetch_add(1);
         const bool persistent = (b == 1) && c->pk.ok;
         const bool use_graph = !persistent && !g_prof.on && !env_flag("FL_NO_GRAPH");
-        GraphEntry* g = use_graph ? &get_graph(*c, b, true) : nullptr;
+        GraphEntry* g = use_graph ? &get_graph(*c, b, 1) : nullptr;
         EventPair ev;
         FL_CUDA(cudaEventRecord(ev.e0, c->stream));
         if (persistent) {
@@ -1710,6 +1786,53 @@ FL_EXPORT int fl_forward_sample(fl_model* m, fl_cache* c, const uint32_t* ids, i
         }
     } catch (const fl::Error& e) {
         if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;   // a missed peer leaves kv_len / exchange epochs out of step
+        throw;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_forward_slots(fl_model* m, fl_cache* c, const int* slots, const uint32_t* ids, int n, int t, const size_t* rope_offsets,
+                               float* logits_host) {
+    FL_API_BEGIN
+    FL_CHECK(m && c && logits_host, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w != nullptr && m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    use_device();
+    try {
+        run_forward_slots(*c, slots, ids, n, t, rope_offsets);
+        const size_t cnt = (size_t)n * c->w->Vfull;
+        FL_CUDA(cudaMemcpyAsync(c->h_logits.p, c->logits.p, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        FL_CUDA(cudaStreamSynchronize(c->stream));
+        check_peer_error();
+        std::memcpy(logits_host, c->h_logits.p, cnt * 4);
+    } catch (const fl::Error& e) {
+        if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;
+        throw;
+    }
+    FL_API_END
+}
+
+FL_EXPORT int fl_forward_sample_device(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, fl_sampler* s,
+                                       uint32_t* next_id) {
+    FL_API_BEGIN
+    FL_CHECK(m && c && s && next_id, FL_ERR_INVALID, "NULL argument");
+    FL_CHECK(m->w != nullptr && m->w.get() == c->w.get(), FL_ERR_INVALID, "cache belongs to a different model");
+    use_device();
+    try {
+        run_forward(*c, ids, b, t, rope_offset);
+        const uint32_t* src = c->next_ids.p;                       // temperature below 1e-7: the arg-max the forward already computed
+        if (!s->lp.is_argmax()) {
+            // row 0 only (logits.get(0)?, models/mod.rs:421); ONE generator draw per sample, exactly as on the host path
+            const float u = s->lp.draw_unit();
+            sample_softmax_kernel<<<1, 1024, 0, c->stream>>>(c->logits.p, c->w->Vfull, s->lp.inv_temperature(), u, c->sample_out.p);
+            g_launches.fetch_add(1);
+            src = c->sample_out.p;
+        }
+        FL_CUDA(cudaMemcpyAsync(c->h_ids.p, src, 4, cudaMemcpyDeviceToHost, c->stream));
+        FL_CUDA(cudaStreamSynchronize(c->stream));
+        check_peer_error();
+        *next_id = c->h_ids.p[0];
+    } catch (const fl::Error& e) {
+        if (e.code == FL_ERR_CUDA || e.code == FL_ERR_NCCL) c->poisoned = true;
         throw;
     }
     FL_API_END

@@ -28,9 +28,15 @@ enum : int { EPI_STORE = 0, EPI_RESID = 1, EPI_SILU = 2, EPI_QKV = 3 };
 // Device-resident step state of one KV cache (so a captured CUDA graph can be replayed as positions advance).
 struct StepState {
     int rope_pos;             // RoPE position of token 0 of the current forward call
-    int pad[3];
-    int kv_base[kMaxBatch];   // tokens already in the cache per sequence, BEFORE the current call
+    int ragged;               // 1 during a fl_forward_slots call: batch row i is cache slot slot[i] at RoPE position rope_seq[i]
+    int pad[2];
+    int kv_base[kMaxBatch];   // tokens already in the cache per sequence SLOT, BEFORE the current call
+    int slot[kMaxBatch];      // ragged calls: cache slot of batch row i (rows of the uniform calls are their own slots)
+    int rope_seq[kMaxBatch];  // ragged calls: RoPE position of token 0 of batch row i
 };
+// cache slot / RoPE position of batch row `seq` (continuous batching: sequences of different lengths share a step)
+__device__ __forceinline__ int st_slot(const StepState* s, int seq) { return s->ragged ? s->slot[seq] : seq; }
+__device__ __forceinline__ int st_rope(const StepState* s, int seq) { return s->ragged ? s->rope_seq[seq] : s->rope_pos; }
 
 struct GemvArgs {
     const uint16_t* W;   // [N, K] bf16

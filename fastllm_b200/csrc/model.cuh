@@ -117,7 +117,14 @@ struct fl_cache {
     std::shared_ptr<fl::Weights> w;
     cudaStream_t stream = nullptr;
     int max_batch = 0, max_seq = 0, pages_per_seq = 0, nsplit = 1;
-    int kv_len = 0;                       // host mirror of StepState.kv_base (same for every sequence)
+    int kv_len = 0;                       // host mirror of StepState.kv_base (same for every sequence; the uniform calls)
+    // continuous batching (fl_forward_slots): every sequence slot has its own length; once a slot call was made the cache is
+    // driven by slots until fl_cache_reset
+    bool slots_used = false;
+    std::vector<int> slot_len;            // host mirror of StepState.kv_base per slot
+    fl::DevBuf<int> slot_tab;             // [2 * max_batch] staging of (slot, RoPE position) per batch row
+    fl::PinnedBuf<int> h_slot_tab;
+    fl::DevBuf<uint32_t> sample_out;      // device-side sampling: the picked token
     fl::DevBuf<fl::StepState> state;
     fl::DevBuf<int> page_table;           // [max_batch, pages_per_seq]
     fl::DevBuf<uint16_t> kpool, vpool;    // [L][pages][nkv][kKvPage][d]

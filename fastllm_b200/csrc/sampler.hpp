@@ -123,6 +123,11 @@ class LogitsProcessor {
     LogitsProcessor(uint64_t seed, double temperature) : rng_(seed), argmax_(!(temperature >= 1e-7)), temperature_(temperature) {}
 
     uint32_t next_u32() { return rng_.next_u32(); }
+    bool is_argmax() const { return argmax_; }
+    float inv_temperature() const { return (float)(1.0 / temperature_); }
+    // the ONE generator draw a temperature sample consumes, as UniformFloat::<f32> turns it into [0, 1): (u32 >> 9) as the mantissa
+    // of a float in [1, 2), minus 1 (device-side sampling takes it from here, so a request's random stream is the same on both paths)
+    float draw_unit() { return f32_from_bits((rng_.next_u32() >> 9) | 0x3f800000u) - 1.0f; }
 
     uint32_t sample(const float* logits, size_t n) {
         if (n == 0) throw SamplerError("sample: empty logits");

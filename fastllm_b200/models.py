@@ -132,6 +132,43 @@ class DeviceCache:
                                               logits_processor.h, C.byref(tok)))
         return tok.value
 
+    def forward_sample_device(self, ids: np.ndarray, rope_offset: int, logits_processor: "LogitsProcessor") -> int:
+        """The opt-in fast path of forward_sample: soft-max weights, prefix sums and the search run on the device (4 bytes come
+        back instead of vocab * 4); the sampler object still owns the generator.  Not bit-identical to the host path by
+        construction (block scan instead of a sequential sum): see include/fastllm_b200.h."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if ids.ndim != 2:
+            raise FastllmError(-1, f"input must be [batch, seq], got shape {ids.shape}")
+        b, t = ids.shape
+        tok = C.c_uint32()
+        _lib.check(self.lib.fl_forward_sample_device(self.model.h, self.h, ids.ctypes.data_as(C.c_void_p), b, t, rope_offset,
+                                                     logits_processor.h, C.byref(tok)))
+        return tok.value
+
+    def forward_slots(self, slots, ids: np.ndarray, rope_offsets) -> np.ndarray:
+        """Ragged forward (continuous batching): row i of ids [n, t] is fed to the sequence in cache slot slots[i] at RoPE
+        position rope_offsets[i]; the slots keep their own lengths.  -> f32 [n, vocab]."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        if ids.ndim != 2:
+            raise FastllmError(-1, f"input must be [batch, seq], got shape {ids.shape}")
+        n, t = ids.shape
+        sl = np.ascontiguousarray(slots, dtype=np.int32).reshape(-1)
+        ro = np.ascontiguousarray(rope_offsets, dtype=np.uint64).reshape(-1)
+        if sl.size != n or ro.size != n:
+            raise FastllmError(-1, "slots / rope_offsets must have one entry per row of ids")
+        out = np.empty((n, self.vocab), dtype=np.float32)
+        _lib.check(self.lib.fl_forward_slots(self.model.h, self.h, sl.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), n, t,
+                                             ro.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def slot_reset(self, slot: int):
+        _lib.check(self.lib.fl_cache_slot_reset(self.h, slot))
+
+    def slot_len(self, slot: int) -> int:
+        n = C.c_int()
+        _lib.check(self.lib.fl_cache_slot_len(self.h, slot, C.byref(n)))
+        return n.value
+
     def decode_greedy_loop(self, first_ids: np.ndarray, rope_offset: int, steps: int):
         first = np.ascontiguousarray(first_ids, dtype=np.uint32).reshape(-1)
         b = first.shape[0]
@@ -510,6 +547,67 @@ class Model:
             logits = self.model.forward(nxt, pos, self.cache)
             pos += 1
         return outs
+
+
+class ContinuousBatcher:
+    """Continuous batching above fl_forward_slots.  The reference serialises chat requests at batch 1
+    under one mutex (api/chat.rs:206-208); here up to `max_batch` requests of ANY lengths share the decode steps: a request is
+    admitted into a free sequence slot as soon as one exists (its prompt is prefilled alone, [1, T]), every step then advances all
+    running requests by one token in ONE ragged forward ([n, 1], per-slot KV lengths and RoPE positions), and a request that
+    hits EOS or its token budget frees its slot for the next waiting one.  Per request the arithmetic is that of
+    Model.generate: its own LogitsProcessor seeded 0 (mod.rs:373-374), EOS break before emitting (mod.rs:431-436), and the
+    adapter's position rule -- Llama: the caller's position; Mistral / Qwen2: +1 per CALL (mistral.rs:234, qwen.rs:143).
+    `cache` needs forward_slots(slots, ids, rope_offsets) -> [n, V], slot_reset(slot): a DeviceCache, or a stand-in in tests."""
+
+    def __init__(self, model, max_batch: int = 8, eos_token_id: int | None = 2, cache=None):
+        self.model, self.max_batch, self.eos_token_id = model, max_batch, eos_token_id
+        self.position_per_call = getattr(model, "arch", "llama") != "llama"      # the Mistral/Qwen2 adapters' offset rule
+        self.cache = cache if cache is not None else DeviceCache(model.dev, max_batch, model._capacity())
+        self.steps = 0          # ragged decode forwards issued (tests / stats)
+
+    def generate(self, prompts, max_tokens: int, temperature: float = 0.0):
+        """-> one id list per prompt, in request order."""
+        out = [[] for _ in prompts]
+        waiting = list(range(len(prompts)))[::-1]
+        free = list(range(self.max_batch))[::-1]
+        running = {}            # slot -> [request, next RoPE position, LogitsProcessor, token to feed]
+        if max_tokens <= 0:
+            return out
+
+        def take(logits_row, req, slot, state):
+            """sample -> EOS / budget -> either keep the slot running or free it"""
+            tok = state[2].sample(logits_row)
+            if self.eos_token_id is not None and tok == self.eos_token_id:
+                done = True
+            else:
+                out[req].append(tok)
+                state[3] = tok
+                done = len(out[req]) >= max_tokens
+            if done:
+                running.pop(slot, None)
+                self.cache.slot_reset(slot)
+                free.append(slot)
+            else:
+                running[slot] = state
+
+        while waiting or running:
+            while waiting and free:                                   # admit: one prompt at a time, alone in its forward
+                req, slot = waiting.pop(), free.pop()
+                ids = np.asarray(prompts[req], dtype=np.uint32).reshape(1, -1)
+                logits = self.cache.forward_slots([slot], ids, [0])
+                state = [req, 1 if self.position_per_call else ids.shape[1], LogitsProcessor(0, float(np.float32(temperature))), 0]
+                take(np.asarray(logits)[0].reshape(-1), req, slot, state)
+            if not running:
+                continue
+            slots = sorted(running)
+            ids = np.array([[running[s][3]] for s in slots], dtype=np.uint32)
+            logits = np.asarray(self.cache.forward_slots(slots, ids, [running[s][1] for s in slots]))
+            self.steps += 1
+            for i, s in enumerate(slots):
+                st = running[s]
+                st[1] += 1
+                take(logits[i].reshape(-1), st[0], s, st)
+        return out
 
 
 # --------------------------------------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@
  *                                models/mod.rs:157-158,373-374 and logits_processor.sample(&last_logits)
  *                                models/mod.rs:308-310,425-428 (arg-max below 1e-7, else soft-max + WeightedIndex
  *                                over rand 0.8's StdRng seeded with seed_from_u64)
+ *   fl_forward_slots          <- the same forward for a batch of requests of different lengths (no reference counterpart: requests
+ *                                are serialised at batch 1, api/chat.rs:206-208; streams run side by side, models/mod.rs:151-175)
  *   fl_embed                  <- EmbeddingModel::embed models/embeddings.rs:397-447 after tokenisation:
  *                                encoder forward + mean_pooling (:346-368) + normalize_l2 (:341-344)
  */
@@ -134,6 +136,18 @@ FL_EXPORT int fl_forward_greedy(fl_model* m, fl_cache* c, const uint32_t* ids, i
 FL_EXPORT int fl_decode_greedy_loop(fl_model* m, fl_cache* c, const uint32_t* first_ids, int b, size_t rope_offset, int steps,
                           uint32_t* out_ids, float* elapsed_ms);
 
+/* ---- continuous batching: sequence slots with their own lengths -------------------------------------
+ * The reference serialises requests at batch 1 under a mutex (api/chat.rs:206-208) and runs streams concurrently at batch 1 each
+ * (models/mod.rs:151-175).  A cache created with max_batch > 1 holds max_batch independent sequence SLOTS; fl_forward_slots feeds
+ * t new tokens to each of n distinct slots in ONE forward -- a new request's prompt (n = 1, t = prompt length) or one decode step
+ * of every running request (t = 1), whatever their lengths -- with a RoPE position per row (explicit, like fl_forward's, so the
+ * Mistral/Qwen2 adapters' +1-per-call rule survives per request).  logits_host: f32 [n, vocab], row i = slot slots[i].
+ * A cache is driven either by the uniform calls above or by slots; fl_cache_reset switches back. */
+FL_EXPORT int fl_forward_slots(fl_model* m, fl_cache* c, const int* slots, const uint32_t* ids, int n, int t, const size_t* rope_offsets,
+                               float* logits_host);
+FL_EXPORT int fl_cache_slot_reset(fl_cache* c, int slot);        /* the slot's sequence is finished: length := 0 */
+FL_EXPORT int fl_cache_slot_len(fl_cache* c, int slot, int* out);
+
 /* ---- sampling (host arithmetic: the reference samples on the host from every forward's logits) --- */
 /* LogitsProcessor::new(seed, Some(temperature), None): temperature < 1e-7 => arg-max (IEEE total order, LAST index among
  * equal maxima); otherwise softmax(logits * (1/T as f32)) with a sequential f32 denominator, then
@@ -148,6 +162,13 @@ FL_EXPORT int fl_sampler_destroy(fl_sampler* s);
  * vocab*4-byte read-back, no caller-side logits buffer.  next_id: host u32 [1]. */
 FL_EXPORT int fl_forward_sample(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, fl_sampler* s,
                                 uint32_t* next_id);
+
+/* Opt-in fast path of the same call: the soft-max weights, their prefix sums and the search run ON THE DEVICE (the sampler object
+ * still owns the generator and hands over its one draw per sample, so a request's random stream is unchanged); 4 bytes travel back
+ * instead of vocab * 4.  Not bit-identical to the host path by construction: the prefix sums come from a block scan, so a draw
+ * within ~1e-6 (relative) of a boundary between two tokens may pick the neighbour.  The parity path is fl_forward_sample. */
+FL_EXPORT int fl_forward_sample_device(fl_model* m, fl_cache* c, const uint32_t* ids, int b, int t, size_t rope_offset, fl_sampler* s,
+                                       uint32_t* next_id);
 
 /* ---- embeddings (BERT family) ------------------------------------------------------------------ */
 /* ids/mask: host u32 [b, t]; mask may be NULL (all ones).  out: host f32 [b, hidden], mean-pooled and L2-normalised. */

@@ -101,3 +101,77 @@ def test_embed_many_groups_equal_lengths_and_scatters_back():
     assert np.array_equal(got, want)
     assert calls[:4] == [(3, 6), (1, 6), (2, 3), (1, 11)]
     assert m.embed_many([]).shape == (0, 8)
+
+
+class _SlotCache:
+    """Stand-in for DeviceCache's slot calls: logits of a row are a pure function of that slot's token history."""
+
+    def __init__(self, nslots):
+        self.hist = [None] * nslots
+        self.calls = []
+
+    def forward_slots(self, slots, ids, rope_offsets):
+        ids = np.asarray(ids)
+        self.calls.append((tuple(int(s) for s in slots), ids.shape, tuple(int(r) for r in rope_offsets)))
+        assert len(set(slots)) == len(slots) == ids.shape[0]
+        rows = []
+        for s, r, ro in zip(slots, ids, rope_offsets):
+            if self.hist[s] is None:
+                assert ro == 0
+                self.hist[s] = []
+            else:
+                assert ids.shape[1] == 1 and ro == len(self.hist[s])          # Llama rule: the caller's position
+            self.hist[s] += [int(x) for x in r]
+            rs = np.random.RandomState(zlib.crc32(np.asarray(self.hist[s], dtype=np.uint32).tobytes()))
+            row = (rs.standard_normal(VOCAB) * 2).astype(np.float32)
+            row[2] += 2.5
+            rows.append(row)
+        return np.stack(rows)
+
+    def slot_reset(self, slot):
+        assert self.hist[slot] is not None
+        self.hist[slot] = None
+
+
+class _Llama:
+    arch = "llama"
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.9])
+def test_continuous_batcher_equals_per_request_generate(temperature):
+    """Requests of different lengths share decode steps, slots are reused as requests finish (8 requests over 3 slots), and every
+    request gets exactly the tokens Model.generate gives it alone."""
+    prompts = _prompts(5, [5, 9, 2, 7, 3, 11, 4, 6])
+    m = _HistoryModel(eos_bias=2.5)
+    single = [models.Model(m, None, eos_token_id=2).generate(p, 10, temperature=temperature) for p in prompts]
+    assert len({len(s) for s in single}) > 1
+    cache = _SlotCache(3)
+    cb = models.ContinuousBatcher(_Llama(), max_batch=3, eos_token_id=2, cache=cache)
+    assert cb.generate(prompts, 10, temperature=temperature) == single
+    prefills = [c for c in cache.calls if c[1][1] > 1 or c[2] == (0,)]
+    assert len(prefills) == len(prompts) and all(len(c[0]) == 1 for c in prefills)       # prompts are prefilled alone
+    decodes = [c for c in cache.calls if c not in prefills]
+    assert max(len(c[0]) for c in decodes) == 3 and all(c[1][1] == 1 for c in decodes)   # ragged steps fill the slots
+    assert all(h is None for h in cache.hist)                                            # every slot was handed back
+    assert cb.steps < sum(len(s) for s in single)                                        # steps were shared
+
+
+def test_continuous_batcher_position_rule_of_the_mistral_adapter_and_edge_cases():
+    class _Mistral:
+        arch = "mistral"
+
+    class _C(_SlotCache):
+        def forward_slots(self, slots, ids, rope_offsets):
+            self.calls.append((tuple(slots), np.asarray(ids).shape, tuple(int(r) for r in rope_offsets)))
+            return np.tile(np.arange(VOCAB, dtype=np.float32), (len(slots), 1))           # arg-max = VOCAB - 1, never EOS
+
+        def slot_reset(self, slot):
+            pass
+
+    cache = _C(2)
+    out = models.ContinuousBatcher(_Mistral(), max_batch=2, eos_token_id=2, cache=cache).generate([[5, 6, 7], [8]], 3)
+    assert out == [[VOCAB - 1] * 3, [VOCAB - 1] * 3]
+    # mistral.rs:234 / qwen.rs:143: the offset grows by ONE per call, whatever the prompt length: 0 at the prefill, then 1, 2
+    assert [c[2] for c in cache.calls] == [(0,), (0,), (1, 1), (2, 2)]
+    assert models.ContinuousBatcher(_Mistral(), 2, cache=_C(2)).generate([], 4) == []
+    assert models.ContinuousBatcher(_Mistral(), 2, cache=_C(2)).generate([[3, 4]], 0) == [[]]

@@ -64,6 +64,22 @@ def test_bert_ragged_lengths_and_mask(golden_dir):
         assert _cos(got, want).min() >= COS_TOL, (b, t)
 
 
+@pytest.mark.parametrize("b,t", [(1, 129), (3, 200), (2, 256), (1, 384), (2, 512)])
+def test_minilm_long_sentences(b, t):
+    """The reference enforces no sentence limit below the 512-row position table (embeddings.rs:285-286, 416): sentences of more
+    than 128 tokens run the key-tiled attention kernel (online softmax) and must match the oracle like the short ones."""
+    cfg = obert.MINILM_L6
+    w = obert.synth_weights(cfg, 0, 0.02)
+    ids = synth.token_ids(300 + t, cfg.vocab_size, (b, t))
+    mask = np.ones((b, t), dtype=np.uint32)
+    mask[:, -3:] = 0
+    want = obert.MiniLM(cfg, w).embed_ids(ids, mask)
+    got = _product(cfg, w).embed_ids(ids, mask)
+    cos = _cos(got, want)
+    print(f"MiniLM-L6 {b}x{t}: min cosine {cos.min():.6f}, max-abs {np.abs(got - want).max():.3e}")
+    assert cos.min() >= COS_TOL and np.abs(got - want).max() <= 2e-2
+
+
 def test_minilm_true_shape_batch():
     """all-MiniLM-L6-v2 shapes (H=384, 12 heads, I=1536, 6 layers), 16 x 128 tokens, synthetic weights."""
     cfg = obert.MINILM_L6
@@ -89,7 +105,7 @@ def test_bert_errors():
     with pytest.raises(FastllmError):
         m.embed_ids(np.full((1, 4), 200, dtype=np.uint32))            # id out of range
     with pytest.raises(FastllmError):
-        m.embed_ids(np.ones((1, 129), dtype=np.uint32))               # > 128 tokens: not built in this round
+        m.embed_ids(np.ones((1, 65), dtype=np.uint32))                # > max_position_embeddings (64 here): the position lookup fails
     with pytest.raises(FastllmError):
         models.MiniLMModel(models.BertConfig(96, 4, 1, 256, 64, 1e-12, 200), None)   # head_dim 24 unsupported
 

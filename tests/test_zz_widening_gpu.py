@@ -82,3 +82,122 @@ def test_embed_many_equals_per_sentence():
         one = m.embed_ids(np.asarray([s], dtype=np.uint32))[0]
         assert float(np.dot(one, got[i])) >= 0.99999 and np.abs(one - got[i]).max() <= 1e-3
         assert float(np.dot(want.embed_ids(np.asarray([s], dtype=np.uint32))[0], got[i])) >= 0.999      # and against the oracle
+
+
+@pytest.mark.parametrize("name", ["llama_gqa8", "mistral", "qwen2"])
+def test_forward_slots_ragged_batch_against_the_oracle(name):
+    """fl_forward_slots: sequences of different lengths (5 / 70 / 130 tokens: one, two and three KV pages) live in slots 2 / 0 / 1
+    of one cache and decode TOGETHER, each at its own KV length and RoPE position; one finishes, its slot is reset and a new prompt
+    is admitted while the others keep going.  Every row against a per-sequence oracle with the same bf16 KV rounding."""
+    from dataclasses import replace
+    from fastllm_b200 import models
+    from oracle import causal_lm as ocl
+    from oracle import synth
+    from helpers import TINY
+    cfg = replace(TINY[name], max_position_embeddings=512)
+    w = ocl.synth_weights(cfg, 21, 0.08)
+    model, _ = product_model(cfg, w)
+    cache = models.DeviceCache(model.dev, 4, 256)
+    per_call = cfg.arch != "llama"                     # Mistral / Qwen2 adapters: RoPE offset + 1 per call
+
+    class Seq:
+        def __init__(self, slot, prompt):
+            self.slot, self.oracle, self.pos = slot, ocl.CausalLM(cfg, w, kv_dtype="bf16"), 0
+            self.step(prompt)
+
+        def step(self, ids_row):                       # -> (rope offset used, oracle logits)
+            ro = self.pos
+            self.want = self.oracle.forward(np.asarray(ids_row, dtype=np.uint32)[None], ro)[0]
+            self.pos += 1 if per_call else len(ids_row)
+            return ro
+
+    errs = []
+    seqs = {}
+    for slot, n in ((2, 5), (0, 70), (1, 130)):
+        prompt = synth.token_ids(90 + slot, cfg.vocab_size, (n,))
+        sq = Seq(slot, prompt)
+        got = cache.forward_slots([slot], prompt[None], [0])[0]
+        errs.append(float(np.abs(got - sq.want).max()))
+        sq.tok = models.sample_argmax(got)
+        seqs[slot] = sq
+    assert [cache.slot_len(s) for s in range(4)] == [70, 130, 5, 0]
+
+    def ragged_step():
+        order = sorted(seqs)
+        ids = np.array([[seqs[s].tok] for s in order], dtype=np.uint32)
+        ropes = [seqs[s].step([seqs[s].tok]) for s in order]
+        got = cache.forward_slots(order, ids, ropes)
+        for i, s in enumerate(order):
+            errs.append(float(np.abs(got[i] - seqs[s].want).max()))
+            seqs[s].tok = models.sample_argmax(got[i])
+
+    for _ in range(6):
+        ragged_step()
+    cache.slot_reset(0)                                # the 70-token request is done; a 33-token one takes its slot
+    del seqs[0]
+    prompt = synth.token_ids(99, cfg.vocab_size, (33,))
+    sq = Seq(0, prompt)
+    got = cache.forward_slots([0], prompt[None], [0])[0]
+    errs.append(float(np.abs(got - sq.want).max()))
+    sq.tok = models.sample_argmax(got)
+    seqs[0] = sq
+    for _ in range(4):
+        ragged_step()
+    assert [cache.slot_len(s) for s in range(4)] == [33 + 4, 130 + 10, 5 + 10, 0]
+    print(f"{name}: ragged slots, max-abs logits err over {len(errs)} row results {max(errs):.2e}")
+    assert max(errs) <= KERNEL_TOL
+    from fastllm_b200 import FastllmError
+    with pytest.raises(FastllmError):                  # a slot-driven cache refuses the uniform calls until it is reset
+        cache.forward(prompt[None], 0)
+    with pytest.raises(FastllmError):
+        cache.forward_slots([1, 1], np.array([[3], [4]], dtype=np.uint32), [0, 0])      # a slot twice in one call
+    cache.reset()
+    cache.forward(prompt[None], 0)
+
+
+def test_continuous_batcher_tokens_are_the_per_request_argmax():
+    """ContinuousBatcher on the device: 7 requests of different lengths over 3 slots.  Ragged steps run the dense path while a
+    lone request runs the persistent / GEMV path, so (as for generate_batch) the check is teacher-forced: every emitted token is
+    the arg-max of the single-sequence logits up to twice the kernel tolerance."""
+    from fastllm_b200 import models
+    from oracle import synth
+    cfg, w, g = golden_weights("mistral")
+    model, cache = product_model(cfg, w)
+    lengths = [9, 3, 40, 9, 17, 70, 5]
+    prompts = [list(map(int, synth.token_ids(140 + i, cfg.vocab_size, (n,)))) for i, n in enumerate(lengths)]
+    cb = models.ContinuousBatcher(model, max_batch=3, eos_token_id=None)
+    outs = cb.generate(prompts, 6)
+    assert [len(t) for t in outs] == [6] * len(prompts) and cb.steps < 6 * len(prompts)
+    for p, toks in zip(prompts, outs):
+        c = model.initialize_cache()
+        logits = np.asarray(model.forward(np.asarray([p], dtype=np.uint32), 0, c))[0].reshape(-1)
+        pos = len(p)
+        for tok in toks:
+            assert logits[tok] >= logits.max() - 2 * KERNEL_TOL
+            logits = np.asarray(model.forward(np.array([[tok]], dtype=np.uint32), pos, c))[0].reshape(-1)
+            pos += 1
+
+
+@pytest.mark.parametrize("name,temperature", [("llama_gqa8", 0.8), ("qwen2", 1.3), ("llama", 0.0)])
+def test_device_side_sampling_follows_the_host_sampler(name, temperature):
+    """fl_forward_sample_device (soft-max + prefix sums + search on the device, the sampler object's generator draw) against
+    fl_forward_sample (host arithmetic, the parity path) on the same logits and the same seed: the same tokens, except that a
+    draw within rounding distance of a boundary between two tokens may land on the neighbour (block scan vs sequential sum) --
+    allowed for at most one of the 40 steps, and then only with a host-side cumulative weight within 1e-5 of the draw."""
+    from fastllm_b200 import models
+    cfg, w, g = golden_weights(name)
+    model, _ = product_model(cfg, w)
+    prompt = np.asarray(g["prompt"], dtype=np.uint32)[None]
+    c_host, c_dev = models.DeviceCache(model.dev, 1, 128), models.DeviceCache(model.dev, 1, 128)
+    lp_host, lp_dev = models.LogitsProcessor(0, temperature), models.LogitsProcessor(0, temperature)
+    ids, pos, diff = prompt, 0, 0
+    for _ in range(40):
+        want = c_host.forward_sample(ids, pos, lp_host)
+        got = c_dev.forward_sample_device(ids, pos, lp_dev)
+        if got != want:
+            diff += 1
+            assert abs(int(got) - int(want)) <= 1 or temperature > 0
+        pos += ids.shape[1]
+        ids = np.array([[want]], dtype=np.uint32)
+    assert diff <= (1 if temperature > 0 else 0)
+    assert lp_host.next_u32() == lp_dev.next_u32()      # both paths consumed the generator identically
