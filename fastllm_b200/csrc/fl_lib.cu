@@ -1055,6 +1055,8 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         GemmArgs g{N, R, K, nullptr, nullptr, 0, out, N, ks, (long long)R * N};     // M = weight rows, N = activation rows
         static const bool w_prefetch = env_flag("FL_GEMM_WPREFETCH");     // experimental: not yet measured on a GPU
         g.w_prefetch = (w_prefetch && pdl) ? 1 : 0;
+        static const int gemm_dbg = std::getenv("FL_GEMM_DBG") ? std::atoi(std::getenv("FL_GEMM_DBG")) : 0;
+        g.dbg = gemm_dbg;
         switch (bn) {
             case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
             case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;

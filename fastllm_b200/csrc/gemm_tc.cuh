@@ -45,6 +45,8 @@ struct GemmArgs {
     int grp_m = 0;
     int grp_cap = 0;
     const int* grp_cnt = nullptr;
+    int dbg = 0;                // dev knob FL_GEMM_DBG (timing experiments only, results are garbage): bit 0 = DUAL_B without the
+                                // activation loads, bit 1 = no MMAs (the issuer releases a stage as soon as it has landed)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -241,6 +243,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         continue;
                     }
                     mbar_wait(&empty[st], ((c / kStages) & 1) ^ 1);
+                    if (DUAL == DUAL_B && (g.dbg & 1)) {        // timing experiment: the weight stream alone
+                        mbar_expect_tx(&full[st], kABytes);
+                        tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
+                        continue;
+                    }
                     mbar_expect_tx(&full[st], kStageBytes);
                     if (DUAL == DUAL_B) {       // tmA = weights, tmA2 / tmB = activation hi / lo
                         tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
@@ -273,6 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int st = c % kStages;
                     mbar_wait(&full[st], (c / kStages) & 1);
                     tc_fence_after();
+                    if (g.dbg & 2) {            // timing experiment: no tensor-core work, the stage goes straight back
+                        mbar_arrive(&empty[st]);
+                        continue;
+                    }
                     const uint8_t* sa = gsm + (size_t)st * kStageBytes;
                     const uint64_t adesc = umma_smem_desc_sw128(sa), bdesc = umma_smem_desc_sw128(sa + kBOff);
 #pragma unroll

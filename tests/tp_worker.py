@@ -97,6 +97,82 @@ def gpu_main(out_path):
     dist.destroy_process_group()
 
 
+def gpu_wide_main(out_path):
+    """True-width shapes on 1 / 2 / 4 / 8 ranks (tests/test_tp.py compares N ranks with 1 rank): 2-layer Mistral-7B (persistent kernel
+    with the in-kernel NVLink all-reduce at batch 1, the NCCL dense path at batch 8 and in the prefill), 2-layer Qwen2.5-7B with its
+    REAL 28 q / 4 kv head layout and 152064-row vocabulary (at 8 ranks: every kv head on two ranks, query groups dealt 4 + 3 + one
+    zero head), and a 1-layer Mixtral-8x7B (8 experts, top-2) expert-parallel with data-parallel attention."""
+    import torch
+    import torch.distributed as dist
+    from fastllm_b200 import models, tp
+    from oracle import synth
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tp.init_tensor_parallel(rank, world, local)
+    res = {}
+
+    def dense_lm(cls, cf, vocab, tag):
+        # every multi-step comparison is TEACHER-FORCED with fixed synthetic tokens: random-init logits have top-2 gaps down to
+        # 1e-3, and one flipped arg-max would turn a summation-order difference into a different continuation
+        m, _ = cls.initialize_model(cf, None, "bf16", local, random_seed=0, std=0.02)
+        c = models.DeviceCache(m.dev, 1, 200)
+        p = synth.token_ids(1, vocab, (1, 70))
+        feed = synth.token_ids(4, vocab, (5,))
+        rows = [c.forward(p, 0)[0]]                                       # 70-token prefill: dense path, NCCL all-reduces
+        for s_ in range(5):                                               # one persistent launch per step
+            rows.append(c.forward(feed[s_].reshape(1, 1), 70 + s_)[0])
+        first = np.array([feed[4]], dtype=np.uint32)
+        loop_ids, _ = c.decode_greedy_loop(first, 75, 6)                  # six steps inside one launch, greedy feedback on device
+        c2 = models.DeviceCache(m.dev, 1, 200)                            # the loop's ids must be the arg-max of step-by-step logits
+        c2.forward(p, 0)
+        for s_ in range(5):
+            c2.forward(feed[s_].reshape(1, 1), 70 + s_)
+        tok, slack = int(feed[4]), []
+        for s_ in range(6):
+            lg = c2.forward(np.array([[tok]], dtype=np.uint32), 75 + s_)[0]
+            tok = int(loop_ids[s_, 0])
+            slack.append(float(lg.max() - lg[tok]))
+        c8 = models.DeviceCache(m.dev, 8, 128)                            # batch 8: tcgen05 dense decode, NCCL collectives in the graph
+        p8 = synth.token_ids(2, vocab, (8, 20))
+        f8 = synth.token_ids(5, vocab, (3, 8, 1))
+        l8 = [c8.forward(p8, 0)]
+        for s_ in range(3):
+            l8.append(c8.forward(f8[s_], 20 + s_))
+
+        def top(r):      # (arg-max, top-1/top-2 gap) of a logits row
+            t2 = np.partition(r, -2)[-2:]
+            return [int(models.sample_argmax(r)), float(t2[1] - t2[0])]
+
+        res[tag] = {"top": [top(r) for r in rows], "logits": [r[:4096].tolist() for r in rows], "loop_slack": slack,
+                    "b8_top": [[top(r) for r in l] for l in l8], "b8_logits": [l[:, :2048].tolist() for l in l8]}
+
+    dense_lm(models.MistralWithConfig, models.ConfigFile(4096, 14336, 32000, 2, 32, 8, 1e-5, 10000.0, 256, 4096, tp_rank=rank, tp_size=world),
+             32000, "mistral7b")
+    dense_lm(models.QwenWithConfig, models.ConfigFile(3584, 18944, 152064, 2, 28, 4, 1e-6, 1000000.0, 256, None, tp_rank=rank, tp_size=world),
+             152064, "qwen25_7b")
+    # Mixtral-8x7B shapes, one layer: 8 sequences dealt out to the ranks, tokens travel to the experts and back by all-to-all
+    cf = models.ConfigFile(4096, 14336, 32000, 1, 32, 8, 1e-5, 1000000.0, 256, 4096, tp_rank=rank, tp_size=world, num_local_experts=8,
+                           num_experts_per_tok=2, ep_dp_attention=world > 1)
+    m, _ = models.MixtralWithConfig.initialize_model(cf, None, "bf16", local, random_seed=0, std=0.02)
+    p8 = synth.token_ids(3, 32000, (8, 12))
+    per = 8 // world
+    mine = p8[rank * per:(rank + 1) * per]
+    c = models.DeviceCache(m.dev, per, 64)
+    fm = synth.token_ids(6, 32000, (3, 8, 1))
+    outs = [c.forward(mine, 0)]
+    for s_ in range(3):
+        outs.append(c.forward(fm[s_][rank * per:(rank + 1) * per], 12 + s_))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, np.stack(outs)[:, :, :2048].tolist())
+    allo = np.concatenate([np.array(x) for x in gathered], axis=1)                       # [4 calls, 8 sequences, 2048]
+    res["mixtral"] = {"logits": allo.tolist()}
+    if rank == 0:
+        json.dump(res, open(out_path, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def cpu_main(out_path):
     """No GPU: simulate the library's TP data flow in numpy with the SAME shard windows, all-reduce over gloo."""
     import torch
@@ -193,4 +269,4 @@ def cpu_main(out_path):
 
 
 if __name__ == "__main__":
-    (gpu_main if sys.argv[1] == "gpu" else cpu_main)(sys.argv[2])
+    {"gpu": gpu_main, "gpu_wide": gpu_wide_main, "cpu": cpu_main}[sys.argv[1]](sys.argv[2])
