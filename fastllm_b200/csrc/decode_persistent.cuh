@@ -444,8 +444,15 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     auto load_x_rmsnorm = [&](const float* src, bool src_is_embed_row, const uint16_t* erow, const float* norm_w, int K,
                               float* resid_out) {
         constexpr int NV = kPkMaxNormK / 4 / kPkConsumers;      // float4 per thread
-        float4 v[NV];
+        float4 v[NV], wv[NV];
         float ss = 0.f;
+        // the norm weights do not depend on the previous phase: their loads go out first and travel together with the row's, so the
+        // scaling pass below finds them in registers instead of paying a second L2 round trip after the block reduction
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = tid + j * kPkConsumers;
+            wv[j] = i < K / 4 ? __ldg(reinterpret_cast<const float4*>(norm_w) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int i = tid + j * kPkConsumers;
@@ -467,19 +474,10 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         const float tot = block_sum(ss);
         const float m = sqrtf(tot / (float)K + a.eps);
 #pragma unroll
-        for (int h = 0; h < NV; h += 4) {       // norm weights four loads at a time (L2-resident: prefetched a phase earlier)
-            float4 wv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = tid + (h + j) * kPkConsumers;
-                wv[j] = i < K / 4 ? __ldg(reinterpret_cast<const float4*>(norm_w) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = tid + (h + j) * kPkConsumers;
-                const float4 x = v[h + j];
-                if (i < K / 4) store_x4(i, make_float4(x.x / m * wv[j].x, x.y / m * wv[j].y, x.z / m * wv[j].z, x.w / m * wv[j].w));
-            }
+        for (int j = 0; j < NV; ++j) {
+            const int i = tid + j * kPkConsumers;
+            const float4 x = v[j];
+            if (i < K / 4) store_x4(i, make_float4(x.x / m * wv[j].x, x.y / m * wv[j].y, x.z / m * wv[j].z, x.w / m * wv[j].w));
         }
         zero_x_tail(K);
         pk_named_sync();
@@ -545,6 +543,11 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
                     }
                 }
+            }
+            if (l == 0) {      // page-table entries of this CTA's attention items (constant during the launch): towards L1, off the
+                               // load -> load dependency chain of every layer's attention phase
+                const int npages = (len + kKvPage - 1) / kKvPage;
+                for (int i = tid * 32; i < npages; i += kPkConsumers * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.page_table + i));
             }
             if (l == 0)
                 load_x_rmsnorm(nullptr, true, a.embed + (size_t)tok_id * a.H, lw.ln1, a.H, cta == 0 ? a.resid : nullptr);
