@@ -46,8 +46,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         sys.stdout.write("\n".join(log))
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    # link next to the target and rename: a snapshot of the tree (gpurun) or a concurrent loader never sees a half-written library
+    tmp = LIB + ".tmp"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     subprocess.check_call(link)
+    os.replace(tmp, LIB)
     return LIB
 
 

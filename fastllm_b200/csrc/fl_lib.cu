@@ -1160,7 +1160,8 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 // and then decodes to thousands of tokens).  Splits beyond the last page are empty (p0 >= p1) and the merge skips
                 // them, so a fixed split count is correct at every length.
                 const int pairs = b * w.nkv, slots = 3 * kNumSMs;
-                const int want = pairs <= slots ? slots / pairs : (4 * slots + pairs - 1) / pairs;
+                static const int waves = std::getenv("FL_ATTN_WAVES") ? std::max(1, std::atoi(std::getenv("FL_ATTN_WAVES"))) : 4;   // dev knob
+                const int want = pairs <= slots ? slots / pairs : (waves * slots + pairs - 1) / pairs;
                 const int nsp = std::max(1, std::min(c.nsplit, want));
                 launch_attn_mma(lc, w.d, true, dim3(nsp, w.nkv, b), kv_bytes, at);
             } else {

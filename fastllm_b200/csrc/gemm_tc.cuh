@@ -149,7 +149,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t kStageBytes = (DUAL == DUAL_A ? 2 : 1) * kABytes + (DUAL == DUAL_B ? 2 : 1) * kBBytes;
     constexpr int kStages = (196608 / kStageBytes) < 8 ? (196608 / kStageBytes) : 8;   // <= 192 KB of ring, <= 8 stages
     constexpr uint32_t kBOff = (DUAL == DUAL_A ? 2 : 1) * kABytes;
-    constexpr uint32_t kAccCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    // DUAL_B: the hi and lo activation tiles sit back to back in a stage ([BN rows x 128 B] each, same swizzle), so ONE MMA of
+    // N = 2 BN multiplies the weight tile with both -- half the tcgen05.mma instructions per staged byte (at N = 16 the issue rate
+    // of these tiny MMAs, not the weight stream, was the limit: FL_GEMM_DBG=2 measured it) -- into two accumulator column blocks
+    // [W.hi | W.lo] that the epilogue adds.
+    constexpr int kMmaN = (DUAL == DUAL_B) ? 2 * BN : BN;
+    static_assert(kMmaN <= 256, "UMMA N <= 256");
+    constexpr uint32_t kAccCols = kMmaN <= 32 ? 32 : (kMmaN <= 64 ? 64 : (kMmaN <= 128 ? 128 : 256));
     constexpr uint32_t kTmemCols = 2 * kAccCols;          // two accumulator stages
 
     extern __shared__ uint8_t gsm_raw[];
@@ -264,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, kMmaN);
             uint32_t c = 0, ti = 0;
             if (grouped) pdl_wait();      // grp_cnt is written by the preceding kernel
             for (int item = blockIdx.x; item < ntiles; item += gridDim.x) {
@@ -293,11 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t a2desc = umma_smem_desc_sw128(sa + kABytes);
 #pragma unroll
                         for (int k = 0; k < kGemmBK / 16; ++k) umma_bf16(tacc, a2desc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                    } else if (DUAL == DUAL_B) {
-                        const uint64_t b2desc = umma_smem_desc_sw128(sa + kBOff + kBBytes);
-#pragma unroll
-                        for (int k = 0; k < kGemmBK / 16; ++k) umma_bf16(tacc, adesc + (uint64_t)(2 * k), b2desc + (uint64_t)(2 * k), idesc, 1u);
-                    }
+                    }       // DUAL_B: the first loop already covered hi | lo (N = 2 BN)
                     umma_commit(&empty[st]);                 // slot reusable once these MMAs have read it
                 }
                 umma_commit(&acc_full[as]);                  // accumulator of this tile complete
@@ -327,6 +329,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c0 = cslice * 32; c0 < BN; c0 += 128) {      // 32-column chunks dealt round-robin to the 4 warps of a lane quarter
                 uint32_t r[32];
                 tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (DUAL == DUAL_B) {       // accumulator columns [0, BN) = W . hi, [BN, 2 BN) = W . lo
+                    if (BN >= 32) {
+                        uint32_t r2[32];
+                        tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
+                    }
+                }
                 if (row < row_lim) {
                     const int col = n0 + c0;
                     if (EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16) {
