@@ -1037,7 +1037,11 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
     if (!xhi) { xhi = c.dw.xhi.p; xlo = c.dw.xlo.p; }
     const int nk = (K + kGemmBK - 1) / kGemmBK;
     const bool swap = R <= 128;
-    const int tiles = swap ? (N + 127) / 128 : ((R + kGemmBM - 1) / kGemmBM) * ((N + 127) / 128);
+    // prefill: 128 tokens x 256 weight rows per tile.  The hi/lo activation pair makes a k-block 2 x 16 KB of A next to the weight
+    // tile, and the GEMM is bound by the shared-memory fill rate (L2 -> SM), not by the tensor pipe: a 256-row weight tile is
+    // 64 KB per 2 x 128 x 256 x 64 MACs where the 128-row one is 48 KB per half of that -- 1.5x the arithmetic per staged byte.
+    static const int prefill_bn = env_flag("FL_PREFILL_BN128") ? 128 : 256;      // dev knob: the 128-row tile of round 1
+    const int tiles = swap ? (N + 127) / 128 : ((R + kGemmBM - 1) / kGemmBM) * ((N + prefill_bn - 1) / prefill_bn);
     const int ks = swap ? pick_ksplit(tiles, nk, R) : 1;
     ProfEntry pe;
     const bool prof = g_prof.on && !lc.capturing;
@@ -1067,10 +1071,12 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         const CUtensorMap hi = make_tmap_bf16(xhi, R, K, K, kGemmBM), lo = make_tmap_bf16(xlo, R, K, K, kGemmBM);
         if (silu_hi != nullptr) {       // prefill gate|up: SiLU(gate) * up + hi/lo split fused into the epilogue
             GemmArgs g{R, N, K, nullptr, nullptr, 0, silu_hi, N / 2, 1, 0, silu_lo};
-            launch_gemm_tc<128, GEPI_SILU_HL, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+            if (prefill_bn == 256) launch_gemm_tc<256, GEPI_SILU_HL, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+            else launch_gemm_tc<128, GEPI_SILU_HL, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
         } else {
             GemmArgs g{R, N, K, nullptr, nullptr, 0, out, N, 1, (long long)R * N};
-            launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+            if (prefill_bn == 256) launch_gemm_tc<256, GEPI_F32, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
+            else launch_gemm_tc<128, GEPI_F32, DUAL_A>(lc.stream, pdl, tiles, hi, lo, tmW, g);
         }
     }
     if (prof) {
@@ -1172,10 +1178,14 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
         const float* delta = d.y.p;
         auto tp_reduce = [&]() {   // row-parallel GEMM: fold the split-K slices, then all-reduce the partial sums across ranks
             if (w.tp <= 1) return;
-            launch(lc, "tp_sum_slices", 0, sum_slices_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)d.y.p, ks, (long long)R * w.H, R * w.H,
-                   d.tp_buf.p);
-            tp_allreduce_sum(lc, d.tp_buf.p, (size_t)R * w.H);
-            delta = d.tp_buf.p;
+            float* buf = d.tp_buf.p;
+            if (ks == 1)        // one slice (every prefill GEMM): the GEMM output is all-reduced in place, no copy pass over [R, H]
+                buf = d.y.p;
+            else
+                launch(lc, "tp_sum_slices", 0, sum_slices_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)d.y.p, ks, (long long)R * w.H, R * w.H,
+                       d.tp_buf.p);
+            tp_allreduce_sum(lc, buf, (size_t)R * w.H);
+            delta = buf;
             ks = 1;
         };
         tp_reduce();

@@ -263,6 +263,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_2d(sa, &tmA, kb * kGemmBK, m0, &full[st]);
                         if (DUAL == DUAL_A) tma_load_2d(sa + kABytes, &tmA2, kb * kGemmBK, m0, &full[st]);
                         tma_load_2d(sa + kBOff, &tmB, kb * kGemmBK, n0, &full[st]);
+                        // DUAL_A with a 256-row weight tile: the weight descriptors carry a 128-row box (the swap-AB decode GEMMs'
+                        // A operand), so the tile arrives as two boxes; rows past the matrix are zero-filled by the TMA engine
+                        if (DUAL == DUAL_A && BN == 256) tma_load_2d(sa + kBOff + kBBytes / 2, &tmB, kb * kGemmBK, n0 + 128, &full[st]);
                     }
                 }
             }
