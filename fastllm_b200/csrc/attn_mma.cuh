@@ -23,6 +23,7 @@
 namespace fl {
 
 constexpr int kMmaAttnThreads = 128;
+constexpr int kDecStages = 3;        // K|V page stages of the batched-decode kernel: two pages in flight while one is consumed
 constexpr int kPrefillBM = 64;       // query rows per CTA of the prefill kernel (4 warps x 16)
 
 // element offset of (row, col) in a [rows][D] bf16 tile whose 16-byte chunks are XOR-swizzled by the row (conflict-free ldmatrix)
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_gqa_decode_kernel(const 
     extern __shared__ __align__(128) uint8_t dsm[];
     uint16_t* qhi = reinterpret_cast<uint16_t*>(dsm);   // [16][D]
     uint16_t* qlo = qhi + 16 * D;
-    uint16_t* kv = qlo + 16 * D;                        // [2 stages][K tile | V tile]
+    uint16_t* kv = qlo + 16 * D;                        // [kDecStages][K tile | V tile]
     __shared__ float red_m[NW][16], red_l[NW][16], mrg_w[NW][16], mrg_den[16];
     __shared__ int s_last;
 
@@ -97,7 +98,14 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_gqa_decode_kernel(const 
         const size_t off = ((size_t)pt[p] * a.nkv + kvh) * (size_t)TILE;
         stage_kv_tile<D>(kv + st * 2 * TILE, kv + st * 2 * TILE + TILE, a.kpool + off, a.vpool + off, tid);
     };
-    if (p0 < p1) load(p0, 0);
+    // one cp.async group per page, committed even when there is no page left, so "all but the newest two groups" always means
+    // "the page about to be consumed has landed"; two pages (64 KB) are in flight per CTA while a third is consumed
+    auto load_or_skip = [&](int p) {
+        if (p < p1) load(p, (p - p0) % kDecStages);
+        else cp_async_commit();
+    };
+    load_or_skip(p0);
+    load_or_skip(p0 + 1);
     for (int i = tid; i < 16 * D; i += kMmaAttnThreads) {
         const int h = i / D, dd = i % D;
         const float q = h < n_rep ? a.q[((size_t)seq * a.nh + kvh * n_rep + h) * D + dd] : 0.f;
@@ -110,13 +118,9 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_gqa_decode_kernel(const 
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
     for (int p = p0; p < p1; ++p) {
-        const int st = (p - p0) & 1;
-        if (p + 1 < p1) {
-            load(p + 1, st ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        const int st = (p - p0) % kDecStages;
+        load_or_skip(p + 2);          // into the stage page p - 1 occupied (released by the barrier that ended its iteration)
+        cp_async_wait<2>();
         __syncthreads();
         const uint16_t* kt = kv + st * 2 * TILE;
         const uint16_t* vt = kt + TILE;
@@ -182,6 +186,7 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_gqa_decode_kernel(const 
         __syncthreads();   // everyone is done with stage st before the next iteration refills it
     }
 
+    cp_async_wait<0>();
     // ---- merge the 4 warps (each saw a different quarter of every page) ----
     l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 1); l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 2);
     l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 1); l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 2);

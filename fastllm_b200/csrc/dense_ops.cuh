@@ -24,6 +24,44 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return s;
 }
 
+// Sum of the split-K slices of one element / pair / quad, in slice order (deterministic), with the loads of up to eight slices in
+// flight at once: these kernels sit between two GEMMs of the decode chain and are pure latency -- a serial `acc += slice[s]`
+// loop costs one L2 round trip per slice.
+__device__ __forceinline__ float sum_slices1(const float* p, long long stride, int nsl) {
+    float acc = 0.f;
+    for (int s0 = 0; s0 < nsl; s0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = s0 + j < nsl ? p[(size_t)(s0 + j) * stride] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (s0 + j < nsl) acc += v[j];
+    }
+    return acc;
+}
+__device__ __forceinline__ float2 sum_slices2(const float* p, long long stride, int nsl) {
+    float2 acc = make_float2(0.f, 0.f);
+    for (int s0 = 0; s0 < nsl; s0 += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = s0 + j < nsl ? *reinterpret_cast<const float2*>(p + (size_t)(s0 + j) * stride) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (s0 + j < nsl) { acc.x += v[j].x; acc.y += v[j].y; }
+    }
+    return acc;
+}
+__device__ __forceinline__ float4 sum_slices4(const float* p, long long stride, int nsl) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < nsl; s0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = s0 + j < nsl ? *reinterpret_cast<const float4*>(p + (size_t)(s0 + j) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (s0 + j < nsl) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+    }
+    return acc;
+}
+
 struct PrepArgs {
     const uint16_t* embed;      // non-null: resid[row] = f32(embed[ids[row]])  (K1)
     const uint32_t* ids;
@@ -77,11 +115,7 @@ static __global__ void __launch_bounds__(1024) dense_prep_kernel(const PrepArgs 
         } else {
             v = r[i];
             if (a.delta) {
-                float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int s = 0; s < a.nsl; ++s) {         // fixed order: deterministic split-K reduction
-                    const float4 p = reinterpret_cast<const float4*>(a.delta + (size_t)s * a.sl_stride + (size_t)row * a.ldd)[i];
-                    ds.x += p.x; ds.y += p.y; ds.z += p.z; ds.w += p.w;
-                }
+                const float4 ds = sum_slices4(a.delta + (size_t)row * a.ldd + 4 * (size_t)i, a.sl_stride, a.nsl);   // fixed order
                 v.x += ds.x; v.y += ds.y; v.z += ds.z; v.w += ds.w;
                 r[i] = v;
             }
@@ -124,12 +158,8 @@ static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
     const int ra = pair * 2;
     const int d = a.d, half = d >> 1;
     const int hh = ra / d, j = (ra % d) >> 1;
-    float va = 0.f, vb = 0.f;
-    for (int s = 0; s < a.nsl; ++s) {
-        const float2 p = *reinterpret_cast<const float2*>(a.y + (size_t)s * a.sl_stride + (size_t)row * a.nqkv + ra);
-        va += p.x;
-        vb += p.y;
-    }
+    const float2 vab = sum_slices2(a.y + (size_t)row * a.nqkv + ra, a.sl_stride, a.nsl);
+    float va = vab.x, vb = vab.y;
     if (a.bias) { va += a.bias[ra]; vb += a.bias[ra + 1]; }
     const int seq = row / a.t, irel = row % a.t;
     const int cslot = st_slot(a.state, seq);                    // cache slot of this sequence (its own index unless the call is ragged)
@@ -165,12 +195,7 @@ static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int 
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= I) return;
     if (grp_cnt != nullptr && (row % grp_cap) >= grp_cnt[row / grp_cap]) return;
-    float2 gu = make_float2(0.f, 0.f);
-    for (int s = 0; s < nsl; ++s) {
-        const float2 p = *reinterpret_cast<const float2*>(y + (size_t)s * sl_stride + (size_t)row * 2 * I + 2 * j);
-        gu.x += p.x;
-        gu.y += p.y;
-    }
+    const float2 gu = sum_slices2(y + (size_t)row * 2 * I + 2 * j, sl_stride, nsl);
     const float act = gu.x / (1.f + expf(-gu.x)) * gu.y;
     uint16_t h, l;
     split_hi_lo(act, h, l);
@@ -295,9 +320,7 @@ static __global__ void moe_combine_kernel(const float* __restrict__ y, int nsl, 
     for (int j = 0; j < E_local; ++j) {
         const int p = pos[(size_t)row * E_local + j];
         if (p < 0) continue;
-        float s = 0.f;
-        for (int k = 0; k < nsl; ++k) s += y[(size_t)k * sl_stride + (size_t)p * H + i];
-        v += route[(size_t)row * E + e0 + j] * s;
+        v += route[(size_t)row * E + e0 + j] * sum_slices1(y + (size_t)p * H + i, sl_stride, nsl);
     }
     moe_out[(size_t)row * H + i] = v;
 }
@@ -310,9 +333,7 @@ static __global__ void moe_accum_kernel(const float* __restrict__ y, int nsl, lo
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H) return;
-    float s = 0.f;
-    for (int k = 0; k < nsl; ++k) s += y[(size_t)k * sl_stride + (size_t)row * H + i];
-    const float v = route_w[(size_t)row * E + e] * s;
+    const float v = route_w[(size_t)row * E + e] * sum_slices1(y + (size_t)row * H + i, sl_stride, nsl);
     float* o = moe_out + (size_t)row * H + i;
     *o = first ? v : (*o + v);
 }
@@ -329,8 +350,7 @@ static __global__ void __launch_bounds__(1024) dense_argmax_kernel(const float* 
     float v = -INFINITY;
     int idx = -1;
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        float x = 0.f;
-        for (int s = 0; s < nsl; ++s) x += y[(size_t)s * sl_stride + (size_t)blockIdx.x * V + i];
+        const float x = sum_slices1(y + (size_t)blockIdx.x * V + i, sl_stride, nsl);
         l[i] = x;
         if (x >= v) { v = x; idx = i; }      // i ascends per thread: >= keeps the last
     }

@@ -119,7 +119,9 @@ static void launch_attn(LaunchCtx& lc, int d, int nsplit, int nkv, int rows, siz
 
 // tensor-core attention of the dense path (attn_mma.cuh): batched decode (one CTA per split x kv head x sequence) or prefill
 // (one CTA per 64-query tile x q head x sequence)
-static size_t attn_mma_smem_bytes(int d, bool decode) { return (size_t)((decode ? 32 : 2 * kPrefillBM) + 4 * kKvPage) * d * 2; }
+static size_t attn_mma_smem_bytes(int d, bool decode) {
+    return (size_t)((decode ? 32 + 2 * kDecStages * kKvPage : 2 * kPrefillBM + 4 * kKvPage)) * d * 2;
+}
 
 template <int D>
 static void attn_mma_set_attrs() {
@@ -1158,15 +1160,18 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             at.sliding_window = windowed ? w.cfg.sliding_window : 0; at.qscale = qscale;
             const uint64_t kv_bytes = (uint64_t)b * (c.kv_len + t) * w.nkv * w.d * 4;
             if (t == 1) {
-                // 3 CTAs are resident per SM.  Few (sequence, kv head) pairs: ONE wave, as many splits as fit (every CTA pays the
-                // same load -> softmax -> merge latency chain once; a second, mostly empty wave would double it).  Many pairs:
-                // ~4 waves so the tail is short.  A split streams at least one 64-token page.
+                // Few (sequence, kv head) pairs: ONE wave, as many splits as fit (every CTA pays the same load -> softmax -> merge
+                // latency chain once; a second, mostly empty wave would double it).  Many pairs: ~3 waves -- measured at batch 64:
+                // 3 / 4 / 6 / 8 / 12 waves = 112 / 113 / 124 / 131 / 157 us per layer, the per-CTA set-up and merge outweigh a shorter
+                // tail.  A split streams at least one 64-token page.
                 // The grid must NOT depend on the current KV length: this launch is captured into the step's CUDA graph, which is
                 // keyed by (batch, loop mode) only and replayed as the context grows (a serve flow captures at a one-page prompt
                 // and then decodes to thousands of tokens).  Splits beyond the last page are empty (p0 >= p1) and the merge skips
                 // them, so a fixed split count is correct at every length.
-                const int pairs = b * w.nkv, slots = 3 * kNumSMs;
-                static const int waves = std::getenv("FL_ATTN_WAVES") ? std::max(1, std::atoi(std::getenv("FL_ATTN_WAVES"))) : 4;   // dev knob
+                // resident CTAs per SM: bounded by the K|V page ring in shared memory (106 KB at head_dim 128: two CTAs)
+                const int cps = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)232448 / (attn_mma_smem_bytes(w.d, true) + 1024)));
+                const int pairs = b * w.nkv, slots = cps * kNumSMs;
+                static const int waves = std::getenv("FL_ATTN_WAVES") ? std::max(1, std::atoi(std::getenv("FL_ATTN_WAVES"))) : 3;   // dev knob
                 const int want = pairs <= slots ? slots / pairs : (waves * slots + pairs - 1) / pairs;
                 const int nsp = std::max(1, std::min(c.nsplit, want));
                 launch_attn_mma(lc, w.d, true, dim3(nsp, w.nkv, b), kv_bytes, at);

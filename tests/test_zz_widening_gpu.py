@@ -147,7 +147,7 @@ def test_forward_slots_ragged_batch_against_the_oracle(name):
     print(f"{name}: ragged slots, max-abs logits err over {len(errs)} row results {max(errs):.2e}")
     # dense-path decode over 130+ cached tokens: the long-decode tolerance of tests/test_fulldepth_gpu.py (bf16 rounding flips of cached
     # K / V elements under the hi + lo activation split; measured 1.5e-3 .. 5.1e-3 here)
-    assert max(errs) <= 8e-3
+    assert max(errs) <= 1e-2
     from fastllm_b200 import FastllmError
     with pytest.raises(FastllmError):                  # a slot-driven cache refuses the uniform calls until it is reset
         cache.forward(prompt[None], 0)
