@@ -25,10 +25,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries ONE JSON line: NCCL's INFO log (communicator size, transports, NVLS) goes to stderr, where a driver can read the
-# `nranks` of the communicator the library created.  Both are defaults only: an explicit NCCL_DEBUG / NCCL_DEBUG_FILE wins.
-os.environ.setdefault("NCCL_DEBUG", "INFO")
-os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+# `nranks` of the communicator the library created.  An explicit NCCL_DEBUG=INFO/TRACE or NCCL_DEBUG_FILE from the caller wins.
+if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("FL_BENCH_ENV_DEBUG"):
+    sys.stderr.write("bench.py env: " + repr({k: v for k, v in os.environ.items() if k.startswith(("NCCL", "TORCH_NCCL", "OMP"))}) + "\n")
 # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank.  The CPU arm (`--impl reference`) runs on rank 0 ALONE and must
 # use all host cores at every N, so the BLAS pool is sized before numpy loads it (and pinned again at run time, run_reference).
 if "--impl" in sys.argv and "reference" in sys.argv and int(os.environ.get("RANK", "0")) == 0:
@@ -375,15 +378,30 @@ def decode_loop_ms(cache, batch, ctx, steps, warm):
     return ms
 
 
-def greedy_trace(model_dev, prompts, steps):
-    """Real prefill of `prompts` [b, T] + `steps` greedy tokens (first from the prefill, the rest in the device-resident loop)
-    -> u32 [steps, b].  Used by the correctness legs: the ids of a sharded run must equal the single-GPU ids."""
+def teacher_forced_logits(model_dev, prompts, feed):
+    """Real prefill of `prompts` [b, T], then one decode step per row of `feed` [steps, b] (FIXED tokens, not the arg-max: random-init
+    logits have top-2 gaps down to 1e-3, and one flipped arg-max would turn a summation-order difference into a different
+    continuation) -> f32 logits [steps + 1, b, vocab].  Used by the correctness legs of the sharded runs."""
     from fastllm_b200 import models
     b, T = prompts.shape
-    cache = models.DeviceCache(model_dev, b, T + steps + 8)
-    first = cache.forward_greedy(prompts, 0)
-    rest, _ = cache.decode_greedy_loop(first, T, steps - 1)
-    return np.concatenate([first[None, :], rest], axis=0)
+    cache = models.DeviceCache(model_dev, b, T + feed.shape[0] + 8)
+    out = [cache.forward(prompts, 0)]
+    for s in range(feed.shape[0]):
+        out.append(cache.forward(np.ascontiguousarray(feed[s]).reshape(b, 1), T + s))
+    return np.stack(out)
+
+
+def compare_sharded(got, want, what):
+    """N-GPU logits against the single-GPU logits of the same synthetic weights and tokens: max-abs difference (the split changes the
+    summation order) and arg-max identity -- a differing arg-max is explained only by a single-GPU top-2 gap inside twice that
+    difference."""
+    diff = float(np.abs(got - want).max())
+    top2 = np.partition(want, -2, axis=-1)[..., -2:]
+    margin = top2[..., 1] - top2[..., 0]
+    ag, aw = got.argmax(-1), want.argmax(-1)
+    unexplained = int(((ag != aw) & (margin > 2 * diff)).sum())
+    return {"check": what, "max_abs": diff, "tol": 6e-3, "argmax_identical": int((ag == aw).sum()), "of": int(ag.size),
+            "unexplained_flips": unexplained, "min_margin": float(margin.min()), "greedy32": bool(unexplained == 0 and diff <= 6e-3)}
 
 
 def tinyllama_parity(local_rank):
@@ -500,25 +518,23 @@ def run_ours(args, rank, world, local_rank):
     # must equal the ids rank 0 computes alone on an unsharded copy of the same synthetic weights -------------------------------
     parity = None
     if sharded:
-        steps_p = 32
-        ptoks = 96 if use_tp else 48
+        steps_p = 32 if use_tp else 12
+        ptoks = 96 if use_tp else 40
         allp = (np.arange(batch * ptoks, dtype=np.uint64).reshape(batch, ptoks) * 7919 % (cf.vocab_size - 3) + 3).astype(np.uint32)
-        mine = allp[rank * local_batch:(rank + 1) * local_batch] if use_ep else allp
-        got = greedy_trace(model.dev, mine, steps_p)                      # every rank: the forward contains collectives
-        if use_ep:                                                        # sequences are data-parallel: collect every rank's columns
+        feed = (np.arange(steps_p * batch, dtype=np.uint64).reshape(steps_p, batch) * 104729 % (cf.vocab_size - 3) + 3).astype(np.uint32)
+        sl = slice(rank * local_batch, (rank + 1) * local_batch) if use_ep else slice(None)
+        got = teacher_forced_logits(model.dev, allp[sl], feed[:, sl])            # every rank: the forward contains collectives
+        if use_ep:                                                                # sequences are data-parallel: collect every rank's rows
             parts = [None] * world
-            dist.all_gather_object(parts, got.tolist())
-            got = np.concatenate([np.asarray(x, dtype=np.uint32) for x in parts], axis=1)
+            dist.all_gather_object(parts, got)
+            got = np.concatenate(parts, axis=1)
         barrier()
         if rank == 0:
             solo, _ = cls.initialize_model(cf1, None, "bf16", local_rank, random_seed=0, std=0.02)
-            want = greedy_trace(solo.dev, allp, steps_p)
+            want = teacher_forced_logits(solo.dev, allp, feed)
             del solo
-            same = int(np.all(got == want, axis=1).sum()) if got.shape == want.shape else 0
-            first_bad = next((i for i in range(steps_p) if not np.array_equal(got[i], want[i])), steps_p)
-            parity = {"check": f"{'tp' if use_tp else 'ep'}{world} greedy ids == single-GPU ids (same synthetic weights, real {ptoks}-token prefill + "
-                               f"{steps_p} decode steps, batch {batch})", "greedy32": bool(first_bad >= steps_p), "identical_steps": first_bad,
-                      "of": steps_p}
+            parity = compare_sharded(got, want, f"{'tp' if use_tp else 'ep'}{world} logits vs single-GPU logits (same synthetic weights; real {ptoks}-token "
+                                                f"prefill + {steps_p} teacher-forced decode steps, batch {batch})")
         barrier()
 
     # ---- the rest of the headline metric in the same job: Mistral-7B batch 8 / 64 (tensor-parallel at N > 1), and Mixtral-8x7B
@@ -612,9 +628,10 @@ def run_ours(args, rank, world, local_rank):
             "batch_sweep": sweep, "moe": moe}
     print(json.dumps(line), flush=True)
     barrier()
-    if parity is not None and parity.get("greedy32") is False and sharded:
-        sys.stderr.write("bench.py: the sharded run's greedy ids differ from the single-GPU ids: " + json.dumps(parity) + "\n")
-        sys.exit(3)
+    for leg in (parity if sharded else None, (moe or {}).get("parity")):
+        if leg is not None and leg.get("greedy32") is False:
+            sys.stderr.write("bench.py: the sharded run does not reproduce the single-GPU results: " + json.dumps(leg) + "\n")
+            sys.exit(3)
 
 
 def moe_leg(args, rank, world, local_rank, dist, peak):
@@ -648,21 +665,21 @@ def moe_leg(args, rank, world, local_rank, dist, peak):
                "parallelism": "single GPU" if world == 1 else f"ep{world}: {cf.num_local_experts // world} expert(s) + {lb} sequences per GPU, dispatch/combine all-to-all",
                "algorithmic_bytes_per_gpu": by, "achieved_gbs_per_gpu": by / (ms / 1e3) / 1e9, "hbm_frac": by / (ms / 1e3) / 1e9 / peak}
         if world > 1:
-            steps_p, ptoks = 16, 40
+            steps_p, ptoks = 12, 40
             allp = (np.arange(batch * ptoks, dtype=np.uint64).reshape(batch, ptoks) * 7919 % (cf.vocab_size - 3) + 3).astype(np.uint32)
-            got = greedy_trace(model.dev, allp[rank * lb:(rank + 1) * lb], steps_p)
+            feed = (np.arange(steps_p * batch, dtype=np.uint64).reshape(steps_p, batch) * 104729 % (cf.vocab_size - 3) + 3).astype(np.uint32)
+            got = teacher_forced_logits(model.dev, allp[rank * lb:(rank + 1) * lb], feed[:, rank * lb:(rank + 1) * lb])
             parts = [None] * world
-            dist.all_gather_object(parts, got.tolist())
-            got = np.concatenate([np.asarray(x, dtype=np.uint32) for x in parts], axis=1)
+            dist.all_gather_object(parts, got)
+            got = np.concatenate(parts, axis=1)
             del model
             dist.barrier()
             if rank == 0:
                 solo, _ = cls.initialize_model(cf1, None, "bf16", local_rank, random_seed=0, std=0.02)
-                want = greedy_trace(solo.dev, allp, steps_p)
+                want = teacher_forced_logits(solo.dev, allp, feed)
                 del solo
-                bad = next((i for i in range(steps_p) if not np.array_equal(got[i], want[i])), steps_p)
-                rec["parity"] = {"check": f"ep{world} greedy ids == single-GPU ids (real {ptoks}-token prefill + {steps_p} decode steps, batch {batch})",
-                                 "identical_steps": bad, "of": steps_p, "ids_equal": bool(bad >= steps_p)}
+                rec["parity"] = compare_sharded(got, want, f"ep{world} logits vs single-GPU logits (real {ptoks}-token prefill + {steps_p} "
+                                                            f"teacher-forced decode steps, batch {batch})")
             dist.barrier()
         return rec if rank == 0 else None
     except Exception as ex:

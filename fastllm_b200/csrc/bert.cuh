@@ -15,6 +15,8 @@ namespace fl {
 static __global__ void embed_ln_kernel(const uint16_t* __restrict__ wemb, const uint16_t* __restrict__ pemb, const float* __restrict__ lnw,
                                 const float* __restrict__ lnb, const uint32_t* __restrict__ ids, int T, int t, int H, int vocab, int maxpos,
                                 float eps, uint16_t* __restrict__ out) {
+    pdl_launch_dependents();      // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();                   // ... and nothing below runs before the previous kernel has completed
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     uint32_t id = ids[row];
@@ -50,6 +52,8 @@ static __global__ void embed_ln_kernel(const uint16_t* __restrict__ wemb, const 
 // LayerNorm over f32 rows [T, H] -> bf16 [T, H]; one warp per row.
 static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ lnw, const float* __restrict__ lnb, int T, int H,
                                  float eps, uint16_t* __restrict__ out) {
+    pdl_launch_dependents();      // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();                   // ... and nothing below runs before the previous kernel has completed
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     const float* xr = x + (size_t)row * H;
@@ -84,6 +88,8 @@ constexpr int kBertLd = 40;      // padded smem row (80 bytes): conflict-free ld
 
 // grid (heads, sentences), 128 threads: warp w owns query rows [32w, 32w+32).  qkv bf16 [T, 3H] (q | k | v), ctx bf16 [T, H].
 static __global__ void __launch_bounds__(128) bert_attn_kernel(const uint16_t* __restrict__ qkv, int t, int H, float scale, uint16_t* __restrict__ ctx) {
+    pdl_launch_dependents();      // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();                   // ... and nothing below runs before the previous kernel has completed
     __shared__ __align__(16) uint16_t sq[kBertS * kBertLd], sk[kBertS * kBertLd], sv[kBertS * kBertLd];
     const int head = blockIdx.x, sent = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t row0 = (size_t)sent * t;
@@ -185,6 +191,8 @@ static __global__ void __launch_bounds__(128) bert_attn_kernel(const uint16_t* _
 // row, accumulator rescaled when the max moves) -- algebraically the reference's max-subtract / exp / sum / div over all keys.
 static __global__ void __launch_bounds__(128) bert_attn_long_kernel(const uint16_t* __restrict__ qkv, int t, int H, float scale,
                                                                     uint16_t* __restrict__ ctx) {
+    pdl_launch_dependents();      // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();                   // ... and nothing below runs before the previous kernel has completed
     __shared__ __align__(16) uint16_t sq[kBertS * kBertLd], sk[kBertS * kBertLd], sv[kBertS * kBertLd];
     const int head = blockIdx.x, sent = blockIdx.y, q0 = blockIdx.z * kBertS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t row0 = (size_t)sent * t;
@@ -303,6 +311,8 @@ static __global__ void __launch_bounds__(128) bert_attn_long_kernel(const uint16
 
 // mean_pooling + normalize_l2: one CTA per sentence, thread per hidden column (H <= 1024).
 static __global__ void pool_l2_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__ mask, int t, int H, float* __restrict__ out) {
+    pdl_launch_dependents();      // programmatic dependent launch: the next kernel may start its prologue now ...
+    pdl_wait();                   // ... and nothing below runs before the previous kernel has completed
     __shared__ float red[32];
     const int sent = blockIdx.x, c = threadIdx.x;
     float acc = 0.f, cnt = 0.f;

@@ -65,6 +65,28 @@ CUtensorMap make_tmap_pk(const void* ptr, uint64_t N, uint64_t K) {
     return m;
 }
 
+// Every kernel of the encoder is launched with programmatic stream serialization: each calls griddepcontrol.launch_dependents at
+// entry and griddepcontrol.wait before it touches anything the previous kernel wrote, so a kernel's prologue (barrier / TMEM
+// set-up, descriptor fetch, block scheduling) overlaps its predecessor's tail instead of following it.
+static bool g_bert_pdl = !env_flag("FL_NO_PDL");
+template <typename... KArgs, typename... Args>
+static void blaunch(cudaStream_t st, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (g_bert_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    FL_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
 template <int EPI>
 static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
     constexpr int BN = kBertBN;
@@ -75,8 +97,7 @@ static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
         attr_set = true;
     }
     const int tiles = ((g.M + kGemmBM - 1) / kGemmBM) * ((g.N + BN - 1) / BN);
-    gemm_tc_kernel<BN, EPI><<<std::min(tiles, kNumSMs), kGemmThreads, smem, st>>>(tmA, tmA, tmB, g);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    blaunch(st, gemm_tc_kernel<BN, EPI>, dim3(std::min(tiles, kNumSMs)), dim3(kGemmThreads), smem, tmA, tmA, tmB, g);
 }
 
 // ---- weights -------------------------------------------------------------------------------------------------------------
@@ -247,9 +268,9 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
     const int T = b * t, H = m.H, I = m.I;
     cudaStream_t st = m.stream;
     const int rows_per_cta = 8;
-    embed_ln_kernel<<<(T + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(m.wemb, m.pemb, m.lnw, m.lnb, m.ids.p, T, t, H, m.V,
-                                                                                      m.maxpos, 1e-12f, m.x.p);
-    g_launches.fetch_add(1);
+    const dim3 row_grid((T + rows_per_cta - 1) / rows_per_cta), row_block(rows_per_cta * 32);
+    blaunch(st, embed_ln_kernel, row_grid, row_block, 0, (const uint16_t*)m.wemb, (const uint16_t*)m.pemb, (const float*)m.lnw, (const float*)m.lnb,
+            (const uint32_t*)m.ids.p, T, t, H, m.V, m.maxpos, 1e-12f, m.x.p);
     const CUtensorMap tm_x = make_tmap_bf16(m.x.p, T, H, H, kGemmBM), tm_x1 = make_tmap_bf16(m.x1.p, T, H, H, kGemmBM),
                       tm_ctx = make_tmap_bf16(m.ctx.p, T, H, H, kGemmBM), tm_h = make_tmap_bf16(m.hbuf.p, T, I, I, kGemmBM);
     const float eps = m.cfg.norm_eps;
@@ -260,24 +281,21 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
         launch_gemm<GEPI_BIAS_BF16>(st, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
         // B3+B4: per (sentence, head) softmax(QK^T / sqrt(d)) V, no mask
         if (t <= kBertS)
-            bert_attn_kernel<<<dim3(m.nh, b), 128, 0, st>>>(m.qkv.p, t, H, scale, m.ctx.p);
+            blaunch(st, bert_attn_kernel, dim3(m.nh, b), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
         else
-            bert_attn_long_kernel<<<dim3(m.nh, b, (t + kBertS - 1) / kBertS), 128, 0, st>>>(m.qkv.p, t, H, scale, m.ctx.p);
-        g_launches.fetch_add(1);
+            blaunch(st, bert_attn_long_kernel, dim3(m.nh, b, (t + kBertS - 1) / kBertS), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
         // B5: attention output dense + bias + residual -> f32, then LayerNorm -> bf16
         launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
-        layernorm_kernel<<<(T + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(m.pre.p, w.ln1w, w.ln1b, T, H, eps, m.x1.p);
-        g_launches.fetch_add(1);
+        blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln1w, (const float*)w.ln1b, T, H, eps, m.x1.p);
         // B6: intermediate dense + bias + GELU(tanh) -> bf16 [T, I]
         launch_gemm<GEPI_BIAS_GELU_BF16>(st, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
         // B7: output dense + bias + residual -> f32, LayerNorm -> bf16
         launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H, 1, 0});
-        layernorm_kernel<<<(T + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(m.pre.p, w.ln2w, w.ln2b, T, H, eps, m.x.p);
-        g_launches.fetch_add(1);
+        blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln2w, (const float*)w.ln2b, T, H, eps, m.x.p);
     }
     // B8: masked mean pooling + L2 normalise -> f32 [b, H]
-    pool_l2_kernel<<<b, (H + 31) / 32 * 32, 0, st>>>(m.x.p, has_mask ? m.mask.p : nullptr, t, H, m.out.p);
-    g_launches.fetch_add(1);
+    blaunch(st, pool_l2_kernel, dim3(b), dim3((H + 31) / 32 * 32), 0, (const uint16_t*)m.x.p, has_mask ? (const uint32_t*)m.mask.p : (const uint32_t*)nullptr,
+            t, H, m.out.p);
 }
 
 void bert_embed(BertModel& m, const uint32_t* ids, const uint32_t* mask, int b, int t, float* out, float* device_ms) {
