@@ -15,8 +15,29 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemv.cuh"
 
 namespace fl {
+
+// Fused tail of a swap-AB split-K GEMM (GemmArgs.fuse): the CTA that completes the LAST k slice of an output tile (atomic ticket per
+// tile) sums the slices in slice order -- deterministic, whichever CTA arrives last -- and applies the consumer's element-wise step
+// in place of a separate kernel launch between two GEMMs of the decode chain:
+//   FUSE_SUM : the sum overwrites slice 0 (consumers read ONE slice)
+//   FUSE_SILU: rows interleave gate_j / up_j -> act_j = silu(gate_j) * up_j written as the hi / lo bf16 operand of the next GEMM
+//   FUSE_QKV : bias + RoPE (rotate-half; partner rows are adjacent) + q store + in-place paged KV append
+enum : int { FUSE_NONE = 0, FUSE_SUM = 1, FUSE_SILU = 2, FUSE_QKV = 3 };
+struct GemmQkvFuse {
+    const float* bias;          // [nqkv] or null
+    float* q_out;               // [R, nh * d]
+    uint16_t* kpool;
+    uint16_t* vpool;
+    const int* page_table;
+    int pt_stride;
+    const StepState* state;
+    const float* rope_cos;
+    const float* rope_sin;
+    int nh, nkv, d, max_pos, t;
+};
 
 enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5, GEPI_SILU_HL = 6 };
 enum : int { DUAL_NONE = 0, DUAL_A = 1, DUAL_B = 2 };
@@ -45,6 +66,12 @@ struct GemmArgs {
     int grp_m = 0;
     int grp_cap = 0;
     const int* grp_cnt = nullptr;
+    int fuse = FUSE_NONE;       // GEPI_F32_T: fused tail (see FUSE_*)
+    int* tile_ctr = nullptr;    // [tiles] arrival tickets of the k slices, zero between launches (the last arriver re-arms its tile)
+    uint16_t* act_hi = nullptr; // FUSE_SILU: [rows, act_ld] hi / lo halves
+    uint16_t* act_lo = nullptr;
+    int act_ld = 0;
+    GemmQkvFuse qkv{};          // FUSE_QKV
     int dbg = 0;                // dev knob FL_GEMM_DBG (timing experiments only, results are garbage): bit 0 = DUAL_B without the
                                 // activation loads, bit 1 = no MMAs (the issuer releases a stage as soon as it has landed)
 };
@@ -97,6 +124,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16-column variant (register pressure: the hi | lo halves of a DUAL_B accumulator are added 16 columns at a time)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes with the 128-byte swizzle
 // (exactly what TMA SWIZZLE_128B writes): start address >> 4, LBO = 1 (ignored for swizzled K-major), SBO = 1024 B >> 4
 // (stride between 8-row groups), version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
@@ -130,6 +169,91 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return x * r;
 }
 
+// The fused tail of the last-arriving k slice (see FUSE_*), out of line: the epilogue warps of an 18-warp CTA have 96 registers each
+// and the accumulator read-out already uses most of them.  `row` is the weight row of this thread (thread == TMEM lane), `grp` the
+// group of a grouped GEMM (0 otherwise); 16 activation rows (columns of the swapped product) are handled at a time.
+static __device__ __noinline__ void gemm_fused_tail(const GemmArgs& g, int BN, int ksplit, int grp, int row, int row_lim, int col_lim, int cslice,
+                                                    int lane) {
+#pragma unroll 1
+        for (int c0 = cslice * 32; c0 < BN; c0 += (c0 & 16) ? 112 : 16) {   // 16 columns at a time: both halves of a 32-column chunk, then this warp's next chunk
+            const int ncol = min(16, col_lim - c0);                         // valid activation rows of this half chunk
+            if (ncol <= 0) continue;
+            const size_t orow0 = (size_t)grp * g.grp_cap + c0;              // first row of the stacked output
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            if (row < row_lim) {
+                const float* src = reinterpret_cast<const float*>(g.out) + orow0 * g.ldo + row;
+                for (int sl = 0; sl < ksplit; ++sl) {                       // slice order: deterministic
+                    const float* pj = src + (size_t)sl * (size_t)g.split_stride;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j, pj += g.ldo)
+                        if (j < ncol) v[j] += __ldcg(pj);
+                }
+            }
+            if (g.fuse == FUSE_SUM) {
+                if (row < row_lim) {
+                    float* dst = reinterpret_cast<float*>(g.out) + orow0 * g.ldo + row;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < ncol) dst[(size_t)j * g.ldo] = v[j];
+                }
+            } else if (g.fuse == FUSE_SILU) {
+                // even lane = gate_j, odd lane = up_j (rows 2j, 2j + 1); the even lane writes act_j
+                const int jj = row >> 1;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float up = __shfl_down_sync(0xFFFFFFFFu, v[j], 1);
+                    if (j < ncol && !(lane & 1) && row + 1 < row_lim) {
+                        const float act = v[j] / (1.f + expf(-v[j])) * up;
+                        uint16_t h, l;
+                        h = f32_to_bf16_rne(act);
+                        l = f32_to_bf16_rne(act - __uint_as_float((uint32_t)h << 16));
+                        g.act_hi[(orow0 + j) * g.act_ld + jj] = h;
+                        g.act_lo[(orow0 + j) * g.act_ld + jj] = l;
+                    }
+                }
+            } else if (g.fuse == FUSE_QKV) {
+                // even lane = row ra, odd lane = its RoPE partner ra + 1 (the q / k rows are pair-permuted on upload)
+                const GemmQkvFuse& f = g.qkv;
+                const int d = f.d, half = d >> 1;
+                const int hh = row / d, jr = (row % d) >> 1;
+                float ba = 0.f, bb = 0.f;
+                if (f.bias != nullptr && row + 1 < row_lim) { ba = f.bias[row & ~1]; bb = f.bias[(row & ~1) + 1]; }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1);
+                    if (j < ncol && !(lane & 1) && row + 1 < row_lim) {
+                        const float va = v[j] + ba, vb = other + bb;
+                        const int arow = c0 + j;                            // activation row = seq * t + irel
+                        const int seq = arow / f.t, irel = arow % f.t;
+                        const int cslot = st_slot(f.state, seq);
+                        const int slot = f.state->kv_base[cslot] + irel;
+                        const int page = f.page_table[cslot * f.pt_stride + slot / kKvPage];
+                        if (hh < f.nh + f.nkv) {
+                            int pos = st_rope(f.state, seq) + irel;
+                            pos = pos < f.max_pos ? pos : f.max_pos - 1;
+                            const float cs = f.rope_cos[(size_t)pos * half + jr], sn = f.rope_sin[(size_t)pos * half + jr];
+                            const float o1 = va * cs - vb * sn, o2 = va * sn + vb * cs;
+                            if (hh < f.nh) {
+                                float* qp = f.q_out + ((size_t)arow * f.nh + hh) * d;
+                                qp[jr] = o1;
+                                qp[jr + half] = o2;
+                            } else {
+                                uint16_t* kp = f.kpool + (((size_t)page * f.nkv + (hh - f.nh)) * kKvPage + slot % kKvPage) * d;
+                                kp[jr] = f32_to_bf16_rne(o1);
+                                kp[jr + half] = f32_to_bf16_rne(o2);
+                            }
+                        } else {
+                            uint16_t* vp = f.vpool + (((size_t)page * f.nkv + (hh - f.nh - f.nkv)) * kKvPage + slot % kKvPage) * d;
+                            *reinterpret_cast<uint32_t*>(vp + 2 * jr) = (uint32_t)f32_to_bf16_rne(va) | ((uint32_t)f32_to_bf16_rne(vb) << 16);
+                        }
+                    }
+                }
+            }
+        }
+}
+
 // Persistent, warp-specialised: grid = min(#SMs, #tiles); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so
 // the CTAs running concurrently share activation rows through L2).  Three pipelines: shared-memory ring (TMA -> MMA),
 // two TMEM accumulator stages (MMA -> epilogue: the epilogue of tile i overlaps the MMAs of tile i+1), and the tile walk.
@@ -142,7 +266,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 template <int BN, int EPI, int DUAL = DUAL_NONE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-               const GemmArgs g) {
+               const __grid_constant__ GemmArgs g) {
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
     constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;   // 16 KB
     constexpr uint32_t kBBytes = BN * kGemmBK * 2;
@@ -163,6 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_last_slice;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (g.K + kGemmBK - 1) / kGemmBK;
@@ -334,10 +459,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 if (DUAL == DUAL_B) {       // accumulator columns [0, BN) = W . hi, [BN, 2 BN) = W . lo
                     if (BN >= 32) {
-                        uint32_t r2[32];
-                        tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            uint32_t r2[16];
+                            tmem_ld16(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0 + 16 * hlf), r2);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r[16 * hlf + j] = __float_as_uint(__uint_as_float(r[16 * hlf + j]) + __uint_as_float(r2[j]));
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
@@ -428,6 +556,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
+
+            if (EPI == GEPI_F32_T && g.fuse != FUSE_NONE) {
+                // ---- fused tail: the last k slice of this tile to arrive sums the slices and applies the consumer's step ----
+                bool last = true;
+                if (ksplit > 1) {
+                    __threadfence();                                                   // this item's slice is visible before its ticket
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
+                    if (warp == 2 && lane == 0) {
+                        const int ticket = atomicAdd(g.tile_ctr + tile, 1);
+                        s_last_slice = ticket == ksplit - 1;
+                        if (ticket == ksplit - 1) g.tile_ctr[tile] = 0;
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
+                    last = s_last_slice != 0;
+                    if (last) __threadfence();
+                }
+                if (last) gemm_fused_tail(g, BN, ksplit, grp, row, row_lim, col_lim, cslice, lane);
+            }
         }
     }
     tc_fence_before();
