@@ -4,6 +4,7 @@
 #include <memory>
 
 #include "bert.cuh"
+#include "bert_gemm_ln.cuh"
 #include "bert_model.cuh"
 #include "gemm_tc.cuh"
 #include "synth.cuh"
@@ -248,6 +249,15 @@ void bert_finalize(BertModel& m) {
         w.tm_wi = make_tmap_bf16(w.wi, m.I, m.H, m.H, kBertBN);
         w.tm_wo2 = make_tmap_bf16(w.wo2, m.H, m.I, m.I, kBertBN);
     }
+    // residual projection + LayerNorm in one kernel: a CTA owns complete rows (two MMAs of N = H / 2 into one TMEM accumulator)
+    m.ln_fused = m.H % 128 == 0 && !env_flag("FL_BERT_NO_LNFUSE");
+    if (m.ln_fused) {
+        for (BertLayerW& w : m.layers) {
+            w.tm_wo_ln = make_tmap_bf16(w.wo, m.H, m.H, m.H, m.H / 2);
+            w.tm_wo2_ln = make_tmap_bf16(w.wo2, m.H, m.I, m.I, m.H / 2);
+        }
+        FL_CUDA(cudaFuncSetAttribute(bert_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bert_ln_gemm_smem(m.H)));
+    }
     m.finalized = true;
 }
 
@@ -284,14 +294,25 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
             blaunch(st, bert_attn_kernel, dim3(m.nh, b), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
         else
             blaunch(st, bert_attn_long_kernel, dim3(m.nh, b, (t + kBertS - 1) / kBertS), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
-        // B5: attention output dense + bias + residual -> f32, then LayerNorm -> bf16
-        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
-        blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln1w, (const float*)w.ln1b, T, H, eps, m.x1.p);
+        // B5: attention output dense + bias + residual, LayerNorm -> bf16 (one kernel when the hidden size allows)
+        const int ln_grid = std::min((T + kGemmBM - 1) / kGemmBM, kNumSMs);
+        if (m.ln_fused) {
+            blaunch(st, bert_gemm_ln_kernel, dim3(ln_grid), dim3(kGemmThreads), bert_ln_gemm_smem(H), tm_ctx, w.tm_wo_ln,
+                    BertLnGemmArgs{T, H, H, w.bo, m.x.p, w.ln1w, w.ln1b, eps, m.x1.p});
+        } else {
+            launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
+            blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln1w, (const float*)w.ln1b, T, H, eps, m.x1.p);
+        }
         // B6: intermediate dense + bias + GELU(tanh) -> bf16 [T, I]
         launch_gemm<GEPI_BIAS_GELU_BF16>(st, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
         // B7: output dense + bias + residual -> f32, LayerNorm -> bf16
-        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H, 1, 0});
-        blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln2w, (const float*)w.ln2b, T, H, eps, m.x.p);
+        if (m.ln_fused) {
+            blaunch(st, bert_gemm_ln_kernel, dim3(ln_grid), dim3(kGemmThreads), bert_ln_gemm_smem(H), tm_h, w.tm_wo2_ln,
+                    BertLnGemmArgs{T, H, I, w.bo2, m.x1.p, w.ln2w, w.ln2b, eps, m.x.p});
+        } else {
+            launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H, 1, 0});
+            blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln2w, (const float*)w.ln2b, T, H, eps, m.x.p);
+        }
     }
     // B8: masked mean pooling + L2 normalise -> f32 [b, H]
     blaunch(st, pool_l2_kernel, dim3(b), dim3((H + 31) / 32 * 32), 0, (const uint16_t*)m.x.p, has_mask ? (const uint32_t*)m.mask.p : (const uint32_t*)nullptr,

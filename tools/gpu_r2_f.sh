@@ -9,4 +9,5 @@ timeout 400 python bench.py --workload mixtral8x7b_b32 --steps 32 --warmup 4 --n
 FL_NO_FUSE=1 timeout 400 python bench.py --workload mixtral8x7b_b32 --steps 32 --warmup 4 --no-cpu > $O/f_mixtral_nofuse.json 2> $O/f_mixtral_nofuse.err
 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm.json 2> $O/f_minilm.err
 FL_NO_PDL=1 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm_nopdl.json 2> $O/f_minilm_nopdl.err
+FL_BERT_NO_LNFUSE=1 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm_nolnfuse.json 2> $O/f_minilm_nolnfuse.err
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/f_bench_default.json 2> $O/f_bench_default.err; echo "rc=$?" >> $O/f_bench_default.err
