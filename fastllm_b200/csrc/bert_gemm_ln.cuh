@@ -177,4 +177,146 @@ bert_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ---- weight-stationary GEMM for the K = hidden projections (q|k|v, intermediate) ---------------------------------------------
+// D[M, N] = A[M, K] . B[N, K]^T + bias (-> GELU) -> bf16 with K <= 384.  At hidden 384 a 128 x 192 output tile of gemm_tc_kernel
+// pulls 96 KB of activations AND 144 KB of weights through L2 -> shared memory for 18.9 MFLOP: the encoder's big GEMMs are bound by
+// that fill rate (~47 GB/s per SM), 4x above their tensor time.  Here a CTA keeps ONE 192-row weight tile (all of K: <= 144 KB)
+// resident in shared memory and walks the row tiles of its column block, so a tile costs only its 96 KB of activations: 2.5x less
+// traffic per tile.  grid = (148 / nt) * nt CTAs, CTA c owns column block c % nt and row tiles c / nt, + grid / nt, ...
+constexpr int kBresBN = 192;
+constexpr int kBresMaxNk = 6;        // K <= 384
+constexpr int kBresStages = 5;       // activation ring (16 KB stages) next to the resident weights
+
+inline size_t bert_bres_smem(int K) { return (size_t)((K + kGemmBK - 1) / kGemmBK) * kBresBN * kGemmBK * 2 + (size_t)kBresStages * kGemmBM * kGemmBK * 2 + 1024; }
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+bert_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    static_assert(EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16, "weight-stationary variant: bf16 outputs only");
+    constexpr int BN = kBresBN;
+    constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2, kBBytes = BN * kGemmBK * 2;
+    constexpr uint32_t kAccCols = 256, kTmemCols = 512;
+
+    extern __shared__ uint8_t bsm_raw[];
+    uint8_t* gsm = bsm_raw + ((1024u - (smem_u32(bsm_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t bfull, full[kBresStages], empty[kBresStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (g.K + kGemmBK - 1) / kGemmBK;
+    const int mt = (g.M + kGemmBM - 1) / kGemmBM, nt = (g.N + BN - 1) / BN;
+    const int groups = gridDim.x / nt, tile_n = blockIdx.x % nt, m_first = blockIdx.x / nt;
+    const int n0 = tile_n * BN;
+    uint8_t* resB = gsm;                                   // [nk][BN x 128 B]
+    uint8_t* ring = gsm + (size_t)nk * kBBytes;            // [kBresStages][128 x 128 B]
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        mbar_init(&bfull, 1);
+        for (int s = 0; s < kBresStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], kGemmEpiWarps);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the weights do not depend on the previous kernel: they are requested before the dependency wait
+            mbar_expect_tx(&bfull, (uint32_t)nk * kBBytes);
+            for (int kb = 0; kb < nk; ++kb) tma_load_2d(resB + (size_t)kb * kBBytes, &tmB, kb * kGemmBK, n0, &bfull);
+            pdl_wait();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            uint32_t c = 0;
+            for (int tm = m_first; tm < mt; tm += groups) {
+                for (int kb = 0; kb < nk; ++kb, ++c) {
+                    const int st = c % kBresStages;
+                    mbar_wait(&empty[st], ((c / kBresStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[st], kABytes);
+                    tma_load_2d(ring + (size_t)st * kABytes, &tmA, kb * kGemmBK, tm * kGemmBM, &full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN);
+            uint32_t c = 0, ti = 0;
+            mbar_wait(&bfull, 0);
+            tc_fence_after();
+            for (int tm = m_first; tm < mt; tm += groups, ++ti) {
+                const uint32_t as = ti & 1;
+                mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + as * kAccCols;
+                for (int kb = 0; kb < nk; ++kb, ++c) {
+                    const int st = c % kBresStages;
+                    mbar_wait(&full[st], (c / kBresStages) & 1);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_smem_desc_sw128(ring + (size_t)st * kABytes), bdesc = umma_smem_desc_sw128(resB + (size_t)kb * kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; ++k)
+                        umma_bf16(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[st]);
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3, cslice = (warp - 2) >> 2;
+        uint32_t ti = 0;
+        for (int tm = m_first; tm < mt; tm += groups, ++ti) {
+            const uint32_t as = ti & 1;
+            const int row = tm * kGemmBM + q * 32 + lane;
+            mbar_wait(&acc_full[as], (ti >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = cslice * 32; c0 < BN; c0 += 128) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + as * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (row < g.M) {
+                    const int col = n0 + c0;
+                    uint16_t* o = reinterpret_cast<uint16_t*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (col + j < g.N) {
+                            uint32_t pk[4];
+                            const float4 b0 = g.bias ? *reinterpret_cast<const float4*>(g.bias + col + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 b1 = g.bias ? *reinterpret_cast<const float4*>(g.bias + col + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                float v0 = __uint_as_float(r[j + e]) + bb[e];
+                                float v1 = __uint_as_float(r[j + e + 1]) + bb[e + 1];
+                                if (EPI == GEPI_BIAS_GELU_BF16) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); }
+                                pk[e >> 1] = pack_bf16x2(v0, v1);
+                            }
+                            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 }  // namespace fl

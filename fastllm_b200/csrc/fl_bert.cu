@@ -101,6 +101,25 @@ static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
     blaunch(st, gemm_tc_kernel<BN, EPI>, dim3(std::min(tiles, kNumSMs)), dim3(kGemmThreads), smem, tmA, tmA, tmB, g);
 }
 
+// weight-stationary variant for the K = hidden GEMMs (bert_gemm_ln.cuh); falls back to gemm_tc_kernel when K is too deep
+template <int EPI>
+static void launch_gemm_khidden(cudaStream_t st, bool bres, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
+    const int nt = (g.N + kBresBN - 1) / kBresBN;
+    if (!bres || (g.K + kGemmBK - 1) / kGemmBK > kBresMaxNk || nt > kNumSMs) {
+        launch_gemm<EPI>(st, tmA, tmB, g);
+        return;
+    }
+    const size_t smem = bert_bres_smem(g.K);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FL_CUDA(cudaFuncSetAttribute(bert_gemm_bres_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bert_bres_smem(kBresMaxNk * kGemmBK)));
+        attr_set = true;
+    }
+    const int mt = (g.M + kGemmBM - 1) / kGemmBM;
+    const int groups = std::max(1, std::min(kNumSMs / nt, mt));
+    blaunch(st, bert_gemm_bres_kernel<EPI>, dim3(groups * nt), dim3(kGemmThreads), smem, tmA, tmB, g);
+}
+
 // ---- weights -------------------------------------------------------------------------------------------------------------
 void bert_build(BertModel& m) {
     const fl_config& c = m.cfg;
@@ -285,10 +304,11 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
                       tm_ctx = make_tmap_bf16(m.ctx.p, T, H, H, kGemmBM), tm_h = make_tmap_bf16(m.hbuf.p, T, I, I, kGemmBM);
     const float eps = m.cfg.norm_eps;
     const float scale = (float)std::sqrt((double)m.d);
+    static const bool bres = !env_flag("FL_BERT_NO_BRES");      // dev knob: the K = hidden GEMMs on gemm_tc_kernel (round-1 plan)
     for (int l = 0; l < m.L; ++l) {
         const BertLayerW& w = m.layers[l];
         // B2: fused q|k|v projection + bias -> bf16 [T, 3H]
-        launch_gemm<GEPI_BIAS_BF16>(st, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
+        launch_gemm_khidden<GEPI_BIAS_BF16>(st, bres, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
         // B3+B4: per (sentence, head) softmax(QK^T / sqrt(d)) V, no mask
         if (t <= kBertS)
             blaunch(st, bert_attn_kernel, dim3(m.nh, b), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
@@ -304,7 +324,7 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
             blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln1w, (const float*)w.ln1b, T, H, eps, m.x1.p);
         }
         // B6: intermediate dense + bias + GELU(tanh) -> bf16 [T, I]
-        launch_gemm<GEPI_BIAS_GELU_BF16>(st, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
+        launch_gemm_khidden<GEPI_BIAS_GELU_BF16>(st, bres, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
         // B7: output dense + bias + residual -> f32, LayerNorm -> bf16
         if (m.ln_fused) {
             blaunch(st, bert_gemm_ln_kernel, dim3(ln_grid), dim3(kGemmThreads), bert_ln_gemm_smem(H), tm_h, w.tm_wo2_ln,

@@ -10,4 +10,6 @@ FL_NO_FUSE=1 timeout 400 python bench.py --workload mixtral8x7b_b32 --steps 32 -
 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm.json 2> $O/f_minilm.err
 FL_NO_PDL=1 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm_nopdl.json 2> $O/f_minilm_nopdl.err
 FL_BERT_NO_LNFUSE=1 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm_nolnfuse.json 2> $O/f_minilm_nolnfuse.err
+FL_BERT_NO_BRES=1 timeout 300 python bench.py --workload minilm_256x128 --steps 30 --warmup 5 --no-cpu > $O/f_minilm_nobres.json 2> $O/f_minilm_nobres.err
+timeout 300 python tools/bert_perf.py > $O/f_bert_perf.log 2>&1
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/f_bench_default.json 2> $O/f_bench_default.err; echo "rc=$?" >> $O/f_bench_default.err
