@@ -1035,7 +1035,9 @@ static int pick_ksplit(int tiles, int nk, int R) {
 //   R <= 128 (decode batches, short prefills): swap-AB -- the weights are the 128-row MMA operand, the activations a tiny
 //             N = R tile, the result is stored transposed; the only large shared-memory traffic is the weight stream.
 //   R  > 128 (prefill): tokens are the M dimension, 128 x 128 output tiles.
-// Fused tail of a decode (swap-AB) GEMM: see FUSE_* in gemm_tc.cuh.  FL_NO_FUSE=1 (dev knob) keeps the separate element-wise kernels.
+// Fused tail of a decode (swap-AB) GEMM: see FUSE_* in gemm_tc.cuh.  EXPERIMENTAL, off unless FL_FUSE=1: parity-green, but the first
+// measurement (round 2, Mistral-7B batch 8) had gate|up at 730 us against 45 us unfused and o_proj at 83 against 15 -- the per-item
+// fence + ticket + re-read chain sits on the epilogue warps' critical path -- so the separate element-wise kernels stay the default.
 struct FuseSpec {
     int kind = FUSE_NONE;
     uint16_t* act_hi = nullptr;
@@ -1044,8 +1046,7 @@ struct FuseSpec {
     GemmQkvFuse qkv{};
 };
 static bool fuse_on(int rows) {
-    static const bool off = env_flag("FL_NO_FUSE");
-    return !off && rows <= 128;
+    return rows <= 128 && env_flag("FL_FUSE");      // read per enqueue (a graph keeps the plan it was captured with)
 }
 
 static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N, int K, const CUtensorMap& tmW, float* out,
