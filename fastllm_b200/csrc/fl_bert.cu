@@ -91,7 +91,7 @@ static void blaunch(cudaStream_t st, void (*kern)(KArgs...), dim3 grid, dim3 blo
 template <int EPI>
 static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
     constexpr int BN = kBertBN;
-    const size_t smem = gemm_smem_bytes(BN, DUAL_NONE);
+    const size_t smem = gemm_smem_bytes(BN, DUAL_NONE) + (gemm_epi_staged(EPI) ? kEpiStageBytes : 0);
     static bool attr_set = false;
     if (!attr_set) {
         FL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -269,7 +269,9 @@ void bert_finalize(BertModel& m) {
         w.tm_wo2 = make_tmap_bf16(w.wo2, m.H, m.I, m.I, kBertBN);
     }
     // residual projection + LayerNorm in one kernel: a CTA owns complete rows (two MMAs of N = H / 2 into one TMEM accumulator)
-    m.ln_fused = m.H % 128 == 0 && !env_flag("FL_BERT_NO_LNFUSE");
+    // EXPERIMENTAL, off unless FL_BERT_LNFUSE=1: measured slower than GEMM + LayerNorm kernel (89.8 vs 60.5 + 19.6 us per block at 256 x 128:
+    // its thread-per-row residual reads and two TMEM passes cost more than the f32 round trip they save)
+    m.ln_fused = m.H % 128 == 0 && env_flag("FL_BERT_LNFUSE");
     if (m.ln_fused) {
         for (BertLayerW& w : m.layers) {
             w.tm_wo_ln = make_tmap_bf16(w.wo, m.H, m.H, m.H, m.H / 2);
@@ -304,7 +306,9 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
                       tm_ctx = make_tmap_bf16(m.ctx.p, T, H, H, kGemmBM), tm_h = make_tmap_bf16(m.hbuf.p, T, I, I, kGemmBM);
     const float eps = m.cfg.norm_eps;
     const float scale = (float)std::sqrt((double)m.d);
-    static const bool bres = !env_flag("FL_BERT_NO_BRES");      // dev knob: the K = hidden GEMMs on gemm_tc_kernel (round-1 plan)
+    // EXPERIMENTAL, off unless FL_BERT_BRES=1: weight-stationary variant of the K = hidden GEMMs; measured slower (58 / 83 us against
+    // 55 / 76): these GEMMs were bound by their epilogue's stores, not by the operand traffic the variant saves
+    static const bool bres = env_flag("FL_BERT_BRES");
     for (int l = 0; l < m.L; ++l) {
         const BertLayerW& w = m.layers[l];
         // B2: fused q|k|v projection + bias -> bf16 [T, 3H]

@@ -1084,6 +1084,14 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
             g.fuse = fz->kind; g.tile_ctr = c.dw.tile_ctr.p;
             g.act_hi = fz->act_hi; g.act_lo = fz->act_lo; g.act_ld = fz->act_ld; g.qkv = fz->qkv;
         }
+        if (g.fuse != FUSE_NONE) {
+            switch (bn) {
+                case 16: launch_gemm_tc<16, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+                case 32: launch_gemm_tc<32, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+                case 64: launch_gemm_tc<64, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+                default: launch_gemm_tc<128, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
+            }
+        } else
         switch (bn) {
             case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
             case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
@@ -1138,6 +1146,14 @@ static int dense_gemm_grouped(fl_cache& c, LaunchCtx& lc, const char* tag, int g
         g.fuse = fz->kind; g.tile_ctr = c.dw.tile_ctr.p;
         g.act_hi = fz->act_hi; g.act_lo = fz->act_lo; g.act_ld = fz->act_ld;
     }
+    if (fused) {
+        switch (cap) {
+            case 16: launch_gemm_tc<16, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+            case 32: launch_gemm_tc<32, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+            case 64: launch_gemm_tc<64, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+            default: launch_gemm_tc<128, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
+        }
+    } else
     switch (cap) {
         case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
         case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;

@@ -39,7 +39,7 @@ struct GemmQkvFuse {
     int nh, nkv, d, max_pos, t;
 };
 
-enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5, GEPI_SILU_HL = 6 };
+enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5, GEPI_SILU_HL = 6, GEPI_F32_TF = 7 };      // _TF: F32_T + the fused tails (own instantiation: the default kernel stays as measured)
 enum : int { DUAL_NONE = 0, DUAL_A = 1, DUAL_B = 2 };
 
 constexpr int kGemmBM = 128;
@@ -149,6 +149,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // dynamic shared memory of gemm_tc_kernel<BN, *, DUAL> (ring + 1 KB alignment slack); mirrors the constants in the kernel
+// bf16-output epilogues (GEPI_BIAS_BF16 / GEPI_BIAS_GELU_BF16) stage every warp's 32 rows x 32 columns in shared memory (rows padded
+// to 80 bytes: conflict-free 16-byte accesses) and write them back 8 rows x 64 bytes per instruction.  thread == accumulator row is
+// what tcgen05.ld hands out, and storing that way scatters every 16-byte store of a warp over 32 lines: ncu had the encoder's GEMMs
+// at 27 % tensor activity with the LSU as the busiest unit.
+constexpr int kEpiStageRow = 80;
+constexpr int kEpiStageBytes = kGemmEpiWarps * 32 * kEpiStageRow;      // 40 KB
+__host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi == GEPI_BIAS_BF16 || epi == GEPI_BIAS_GELU_BF16; }
+
 inline size_t gemm_smem_bytes(int BN, int dual) {
     const size_t stage = (size_t)(dual == DUAL_A ? 2 : 1) * kGemmBM * kGemmBK * 2 + (size_t)(dual == DUAL_B ? 2 : 1) * BN * kGemmBK * 2;
     const size_t stages = std::min<size_t>(196608 / stage, 8);
@@ -169,89 +177,94 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return x * r;
 }
 
-// The fused tail of the last-arriving k slice (see FUSE_*), out of line: the epilogue warps of an 18-warp CTA have 96 registers each
-// and the accumulator read-out already uses most of them.  `row` is the weight row of this thread (thread == TMEM lane), `grp` the
-// group of a grouped GEMM (0 otherwise); 16 activation rows (columns of the swapped product) are handled at a time.
-static __device__ __noinline__ void gemm_fused_tail(const GemmArgs& g, int BN, int ksplit, int grp, int row, int row_lim, int col_lim, int cslice,
-                                                    int lane) {
+// The fused tails of the last-arriving k slice (see FUSE_*), out of line: the epilogue warps of an 18-warp CTA have 96 registers each
+// and the accumulator read-out already uses most of them.  `row` is the weight row of this thread (thread == TMEM lane), `orow0` the
+// first activation row (column of the swapped product) of the 16 handled per call, `ncol` how many of them are valid.  Everything a
+// tail needs arrives BY VALUE: fields of the kernel's parameter struct read through a reference would be re-fetched from parameter
+// space after every store (the compiler must assume the stores alias it) -- the first version did that and ran 10x slower.
+__device__ __forceinline__ void gemm_tail_sum16(float (&v)[16], const float* src, size_t split_stride, int ldo, int ksplit, int ncol, bool live) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    if (!live) return;
+    for (int sl = 0; sl < ksplit; ++sl) {                       // slice order: deterministic
+        const float* pj = src + (size_t)sl * split_stride;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < ncol) v[j] += __ldcg(pj + (size_t)j * ldo);
+    }
+}
+
+static __device__ __noinline__ void gemm_tail_sum(float* out, size_t split_stride, int ldo, int ksplit, size_t orow0, int ncol, int row, bool live) {
+    float v[16];
+    gemm_tail_sum16(v, out + orow0 * ldo + row, split_stride, ldo, ksplit, ncol, live);
+    if (live) {
+        float* dst = out + orow0 * ldo + row;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < ncol) dst[(size_t)j * ldo] = v[j];
+    }
+}
+
+// even lane = gate_j, odd lane = up_j (rows 2j, 2j + 1); the even lane writes act_j = silu(gate_j) * up_j as a hi / lo bf16 pair
+static __device__ __noinline__ void gemm_tail_silu(const float* out, size_t split_stride, int ldo, int ksplit, size_t orow0, int ncol, int row,
+                                                   bool live, bool pair_live, int lane, uint16_t* act_hi, uint16_t* act_lo, int act_ld) {
+    float v[16];
+    gemm_tail_sum16(v, out + orow0 * ldo + row, split_stride, ldo, ksplit, ncol, live);
+    const int jj = row >> 1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float up = __shfl_down_sync(0xFFFFFFFFu, v[j], 1);
+        if (j < ncol && !(lane & 1) && pair_live) {
+            const float act = v[j] / (1.f + expf(-v[j])) * up;
+            const uint16_t h = f32_to_bf16_rne(act);
+            const uint16_t l = f32_to_bf16_rne(act - __uint_as_float((uint32_t)h << 16));
+            act_hi[(orow0 + j) * act_ld + jj] = h;
+            act_lo[(orow0 + j) * act_ld + jj] = l;
+        }
+    }
+}
+
+// even lane = row ra, odd lane = its RoPE partner ra + 1 (the q / k rows are pair-permuted on upload): bias, rotate-half RoPE, q store,
+// in-place paged KV append -- what dense_qkv_epi_kernel does as a separate launch
+static __device__ __noinline__ void gemm_tail_qkv(const float* out, size_t split_stride, int ldo, int ksplit, int c0, int ncol, int row, bool live,
+                                                  bool pair_live, int lane, const GemmQkvFuse* fp) {
+    const GemmQkvFuse f = *fp;          // ONE copy out of the caller's parameter block (see above)
+    float v[16];
+    gemm_tail_sum16(v, out + (size_t)c0 * ldo + row, split_stride, ldo, ksplit, ncol, live);
+    const int d = f.d, half = d >> 1;
+    const int hh = row / d, jr = (row % d) >> 1;
+    float ba = 0.f, bb = 0.f;
+    if (f.bias != nullptr && pair_live) { ba = f.bias[row & ~1]; bb = f.bias[(row & ~1) + 1]; }
 #pragma unroll 1
-        for (int c0 = cslice * 32; c0 < BN; c0 += (c0 & 16) ? 112 : 16) {   // 16 columns at a time: both halves of a 32-column chunk, then this warp's next chunk
-            const int ncol = min(16, col_lim - c0);                         // valid activation rows of this half chunk
-            if (ncol <= 0) continue;
-            const size_t orow0 = (size_t)grp * g.grp_cap + c0;              // first row of the stacked output
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            if (row < row_lim) {
-                const float* src = reinterpret_cast<const float*>(g.out) + orow0 * g.ldo + row;
-                for (int sl = 0; sl < ksplit; ++sl) {                       // slice order: deterministic
-                    const float* pj = src + (size_t)sl * (size_t)g.split_stride;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j, pj += g.ldo)
-                        if (j < ncol) v[j] += __ldcg(pj);
+    for (int j = 0; j < 16; ++j) {
+        const float other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1);
+        if (j < ncol && !(lane & 1) && pair_live) {
+            const float va = v[j] + ba, vb = other + bb;
+            const int arow = c0 + j;                            // activation row = seq * t + irel
+            const int seq = arow / f.t, irel = arow % f.t;
+            const int cslot = st_slot(f.state, seq);
+            const int slot = f.state->kv_base[cslot] + irel;
+            const int page = f.page_table[cslot * f.pt_stride + slot / kKvPage];
+            if (hh < f.nh + f.nkv) {
+                int pos = st_rope(f.state, seq) + irel;
+                pos = pos < f.max_pos ? pos : f.max_pos - 1;
+                const float cs = f.rope_cos[(size_t)pos * half + jr], sn = f.rope_sin[(size_t)pos * half + jr];
+                const float o1 = va * cs - vb * sn, o2 = va * sn + vb * cs;
+                if (hh < f.nh) {
+                    float* qp = f.q_out + ((size_t)arow * f.nh + hh) * d;
+                    qp[jr] = o1;
+                    qp[jr + half] = o2;
+                } else {
+                    uint16_t* kp = f.kpool + (((size_t)page * f.nkv + (hh - f.nh)) * kKvPage + slot % kKvPage) * d;
+                    kp[jr] = f32_to_bf16_rne(o1);
+                    kp[jr + half] = f32_to_bf16_rne(o2);
                 }
-            }
-            if (g.fuse == FUSE_SUM) {
-                if (row < row_lim) {
-                    float* dst = reinterpret_cast<float*>(g.out) + orow0 * g.ldo + row;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < ncol) dst[(size_t)j * g.ldo] = v[j];
-                }
-            } else if (g.fuse == FUSE_SILU) {
-                // even lane = gate_j, odd lane = up_j (rows 2j, 2j + 1); the even lane writes act_j
-                const int jj = row >> 1;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float up = __shfl_down_sync(0xFFFFFFFFu, v[j], 1);
-                    if (j < ncol && !(lane & 1) && row + 1 < row_lim) {
-                        const float act = v[j] / (1.f + expf(-v[j])) * up;
-                        uint16_t h, l;
-                        h = f32_to_bf16_rne(act);
-                        l = f32_to_bf16_rne(act - __uint_as_float((uint32_t)h << 16));
-                        g.act_hi[(orow0 + j) * g.act_ld + jj] = h;
-                        g.act_lo[(orow0 + j) * g.act_ld + jj] = l;
-                    }
-                }
-            } else if (g.fuse == FUSE_QKV) {
-                // even lane = row ra, odd lane = its RoPE partner ra + 1 (the q / k rows are pair-permuted on upload)
-                const GemmQkvFuse& f = g.qkv;
-                const int d = f.d, half = d >> 1;
-                const int hh = row / d, jr = (row % d) >> 1;
-                float ba = 0.f, bb = 0.f;
-                if (f.bias != nullptr && row + 1 < row_lim) { ba = f.bias[row & ~1]; bb = f.bias[(row & ~1) + 1]; }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1);
-                    if (j < ncol && !(lane & 1) && row + 1 < row_lim) {
-                        const float va = v[j] + ba, vb = other + bb;
-                        const int arow = c0 + j;                            // activation row = seq * t + irel
-                        const int seq = arow / f.t, irel = arow % f.t;
-                        const int cslot = st_slot(f.state, seq);
-                        const int slot = f.state->kv_base[cslot] + irel;
-                        const int page = f.page_table[cslot * f.pt_stride + slot / kKvPage];
-                        if (hh < f.nh + f.nkv) {
-                            int pos = st_rope(f.state, seq) + irel;
-                            pos = pos < f.max_pos ? pos : f.max_pos - 1;
-                            const float cs = f.rope_cos[(size_t)pos * half + jr], sn = f.rope_sin[(size_t)pos * half + jr];
-                            const float o1 = va * cs - vb * sn, o2 = va * sn + vb * cs;
-                            if (hh < f.nh) {
-                                float* qp = f.q_out + ((size_t)arow * f.nh + hh) * d;
-                                qp[jr] = o1;
-                                qp[jr + half] = o2;
-                            } else {
-                                uint16_t* kp = f.kpool + (((size_t)page * f.nkv + (hh - f.nh)) * kKvPage + slot % kKvPage) * d;
-                                kp[jr] = f32_to_bf16_rne(o1);
-                                kp[jr + half] = f32_to_bf16_rne(o2);
-                            }
-                        } else {
-                            uint16_t* vp = f.vpool + (((size_t)page * f.nkv + (hh - f.nh - f.nkv)) * kKvPage + slot % kKvPage) * d;
-                            *reinterpret_cast<uint32_t*>(vp + 2 * jr) = (uint32_t)f32_to_bf16_rne(va) | ((uint32_t)f32_to_bf16_rne(vb) << 16);
-                        }
-                    }
-                }
+            } else {
+                uint16_t* vp = f.vpool + (((size_t)page * f.nkv + (hh - f.nh - f.nkv)) * kKvPage + slot % kKvPage) * d;
+                *reinterpret_cast<uint32_t*>(vp + 2 * jr) = (uint32_t)f32_to_bf16_rne(va) | ((uint32_t)f32_to_bf16_rne(vb) << 16);
             }
         }
+    }
 }
 
 // Persistent, warp-specialised: grid = min(#SMs, #tiles); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so
@@ -266,7 +279,7 @@ static __device__ __noinline__ void gemm_fused_tail(const GemmArgs& g, int BN, i
 template <int BN, int EPI, int DUAL = DUAL_NONE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ GemmArgs g) {
+               const GemmArgs g) {
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16, 256]");
     constexpr uint32_t kABytes = kGemmBM * kGemmBK * 2;   // 16 KB
     constexpr uint32_t kBBytes = BN * kGemmBK * 2;
@@ -471,6 +484,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
                     }
                 }
+                if (gemm_epi_staged(EPI)) {
+                    // stage this lane's row (32 columns = 64 bytes), then the warp stores 8 rows x 64 bytes per instruction
+                    uint8_t* stg = gsm + (size_t)kStages * kStageBytes + (size_t)(warp - 2) * (32 * kEpiStageRow);
+                    const int col = n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                        if (col + j < g.N) {
+                            const float4 b0 = g.bias ? *reinterpret_cast<const float4*>(g.bias + col + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 b1 = g.bias ? *reinterpret_cast<const float4*>(g.bias + col + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                float v0 = __uint_as_float(r[j + e]) + bb[e];
+                                float v1 = __uint_as_float(r[j + e + 1]) + bb[e + 1];
+                                if (EPI == GEPI_BIAS_GELU_BF16) { v0 = gelu_tanh_f(v0); v1 = gelu_tanh_f(v1); }
+                                pk[e >> 1] = pack_bf16x2(v0, v1);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(stg + lane * kEpiStageRow + (j >> 3) * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    __syncwarp();
+                    uint16_t* obase = reinterpret_cast<uint16_t*>(g.out);
+#pragma unroll
+                    for (int p = lane; p < 128; p += 32) {
+                        const int rr = p >> 2, part = p & 3;
+                        const int grow = m0 + q * 32 + rr, gcol = col + part * 8;
+                        if (grow < g.M && gcol < g.N)
+                            *reinterpret_cast<uint4*>(obase + (size_t)grow * g.ldo + gcol) = *reinterpret_cast<const uint4*>(stg + rr * kEpiStageRow + part * 16);
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (row < row_lim) {
                     const int col = n0 + c0;
                     if (EPI == GEPI_BIAS_BF16 || EPI == GEPI_BIAS_GELU_BF16) {
@@ -513,7 +559,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 *reinterpret_cast<uint4*>(ol + (j >> 1)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                             }
                         }
-                    } else if (EPI == GEPI_F32_T) {
+                    } else if (EPI == GEPI_F32_T || EPI == GEPI_F32_TF) {
                         // transposed store: D[row = weight row, col = activation row] -> out[slice][col, row]; for a fixed col the
                         // 32 lanes of the warp write 32 consecutive floats
                         float* o = reinterpret_cast<float*>(g.out) + (size_t)ksi * (size_t)g.split_stride + (size_t)grp * g.grp_cap * g.ldo + row;
@@ -557,7 +603,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
 
-            if (EPI == GEPI_F32_T && g.fuse != FUSE_NONE) {
+            if (EPI == GEPI_F32_TF && g.fuse != FUSE_NONE) {
                 // ---- fused tail: the last k slice of this tile to arrive sums the slices and applies the consumer's step ----
                 bool last = true;
                 if (ksplit > 1) {
@@ -572,7 +618,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     last = s_last_slice != 0;
                     if (last) __threadfence();
                 }
-                if (last) gemm_fused_tail(g, BN, ksplit, grp, row, row_lim, col_lim, cslice, lane);
+                if (last) {
+                    float* const outp = reinterpret_cast<float*>(g.out);
+                    const bool live = row < row_lim, pair_live = row + 1 < row_lim;
+#pragma unroll 1
+                    for (int c0 = cslice * 32; c0 < BN; c0 += (c0 & 16) ? 112 : 16) {   // 16 columns at a time: both halves of a 32-column chunk, then this warp's next chunk
+                        const int ncol = min(16, col_lim - c0);                         // valid activation rows of this half chunk
+                        if (ncol <= 0) continue;
+                        const size_t orow0 = (size_t)grp * g.grp_cap + c0;              // first row of the (stacked) output
+                        if (g.fuse == FUSE_SUM) gemm_tail_sum(outp, (size_t)g.split_stride, g.ldo, ksplit, orow0, ncol, row, live);
+                        else if (g.fuse == FUSE_SILU)
+                            gemm_tail_silu(outp, (size_t)g.split_stride, g.ldo, ksplit, orow0, ncol, row, live, pair_live, lane, g.act_hi, g.act_lo, g.act_ld);
+                        else gemm_tail_qkv(outp, (size_t)g.split_stride, g.ldo, ksplit, c0, ncol, row, live, pair_live, lane, &g.qkv);
+                    }
+                }
             }
         }
     }

@@ -59,8 +59,10 @@ def test_spills_only_where_known():
     assert len(res) >= 90
     names = sorted(res)
     spilled = {p for n, p in zip(names, sass_summary.demangle(names)) if res[n][2] or res[n][3]}
-    unexpected = {p for p in spilled if not (p.startswith("decode_persistent_kernel<") or p.startswith("gemv_kernel<2, 5,"))}
+    # (gemm_tc_kernel<BN, 7, 2> = the opt-in fused-tail variant FL_FUSE=1: its out-of-line tails cost a few caller-saved registers)
+    unexpected = {p for p in spilled if not (p.startswith("decode_persistent_kernel<") or p.startswith("gemv_kernel<2, 5,") or
+                                             p.startswith("gemm_tail_") or (p.startswith("gemm_tc_kernel<") and ", 7, 2>" in p))}
     assert not unexpected, unexpected
     for n, p in zip(names, sass_summary.demangle(names)):
-        if p.startswith("gemm_tc_kernel<") or p.startswith("attn_"):
+        if (p.startswith("gemm_tc_kernel<") and ", 7, 2>" not in p) or p.startswith("attn_"):
             assert res[n][2] == 0 and res[n][3] == 0, p
