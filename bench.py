@@ -71,10 +71,12 @@ def peaks(kind="hbm"):
 
 def ncu_traffic_per_step():
     """(DRAM bytes per decode step, source) of decode_persistent_kernel from the newest committed `ncu --set full` capture
-    (profiles/rNN_persistent*_full_raw.csv: one launch of 8 steps, Mistral-7B b=1, KV 2048).  The figure is NOT measured in this
-    run -- ncu cannot run inside a timed bench -- so the line names the file it comes from; (None, None) if unavailable."""
+    (profiles/rNN_persistent*_full_raw.csv: one launch of Mistral-7B b=1 at KV 2048; `_<n>step_` in the file name = decode steps
+    inside the captured launch, 8 when absent).  The figure is NOT measured in this run -- ncu cannot run inside a timed bench --
+    so the line names the file it comes from; (None, None) if unavailable."""
     import csv
     import glob
+    import re
     cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_persistent*_full_raw.csv")))
     if not cands:
         return None, None
@@ -87,7 +89,9 @@ def ncu_traffic_per_step():
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             tot += float(r[i]) * scale[units[i]]
-        return tot / 8.0, "committed ncu capture " + os.path.relpath(p, ROOT) + " (8 steps per launch)"
+        m = re.search(r"_(\d+)step_", os.path.basename(p))
+        steps = int(m.group(1)) if m else 8
+        return tot / steps, "committed ncu capture " + os.path.relpath(p, ROOT) + f" ({steps} step(s) per launch)"
     except Exception:
         return None, None
 
