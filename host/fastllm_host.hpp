@@ -123,6 +123,7 @@ struct LlamaWithConfig {
     using Config = ConfigFile;
     using Cache = LlamaCache;
     std::shared_ptr<DeviceModel> dev;
+    static constexpr bool kPositionPerCall = false;   // the caller's position is the RoPE offset (llama.rs:147-149)
     static const char* get_family() { return "Llama"; }
     static bool supports_architecture(const std::string& a) { return a == "LlamaForCausalLM"; }
     // initialize_model(&Config, HashMap<String,Tensor>, DType, &Device) -> (Self, Cache)   llama.rs:98-123
@@ -148,6 +149,7 @@ struct OffsetAdapter {
     using Cache = CacheT;
     std::shared_ptr<DeviceModel> dev;
     mutable std::unique_ptr<DeviceCache> kv;   // candle keeps the KV inside the model (RefCell<Model>)
+    static constexpr bool kPositionPerCall = true;    // RoPE offset + 1 per CALL (mistral.rs:234, qwen.rs:143)
     static std::pair<OffsetAdapter, Cache> initialize_model(const Config& cfg, const TensorMap& tensors, int device) {
         check(fl_init(device));
         // mistral.rs:139 / qwen.rs:49: sliding_window.unwrap_or(4096); bad head dims make fl_model_create fail where the reference asserts
@@ -205,6 +207,78 @@ struct Model {
             out.push_back(tok);
             logits = model.forward(&tok, 1, 1, pos, cache);
             pos += 1;
+        }
+        return out;
+    }
+};
+
+// ---- continuous batching above fl_forward_slots (the reference serialises requests at batch 1 under one
+// mutex, api/chat.rs:206-208).  Transliteration of fastllm_b200/models.py ContinuousBatcher: a request is admitted into a free
+// sequence slot (its prompt prefilled alone), every step advances all running requests by one token in ONE ragged forward, a
+// finished request frees its slot.  Per request: its own LogitsProcessor seeded 0, EOS break before emitting, the adapter's
+// position rule.
+template <typename M>
+struct ContinuousBatcher {
+    const M& model;
+    int max_batch;
+    std::optional<uint32_t> eos_token_id = 2;
+    DeviceCache cache;
+    int steps = 0;      // ragged decode forwards issued
+    ContinuousBatcher(const M& m, int max_batch_, std::optional<uint32_t> eos = 2)
+        : model(m), max_batch(max_batch_), eos_token_id(eos),
+          cache(m.dev->h, max_batch_, std::min(kKvCapacity, m.dev->cfg.max_position_embeddings)) {}
+
+    std::vector<std::vector<uint32_t>> generate(const std::vector<std::vector<uint32_t>>& prompts, int max_tokens, float temperature = 0.0f) {
+        struct Running { size_t req; size_t rope; std::unique_ptr<LogitsProcessor> lp; uint32_t tok; };
+        std::vector<std::vector<uint32_t>> out(prompts.size());
+        if (max_tokens <= 0) return out;
+        std::vector<size_t> waiting;
+        for (size_t i = prompts.size(); i-- > 0;) waiting.push_back(i);
+        std::vector<int> free_slots;
+        for (int s = max_batch; s-- > 0;) free_slots.push_back(s);
+        std::map<int, Running> running;
+        const int V = model.dev->cfg.vocab_size;
+        std::vector<float> logits((size_t)max_batch * V);
+        auto take = [&](const float* row, int slot, Running&& st) {      // sample -> EOS / budget -> keep the slot or free it
+            const uint32_t tok = st.lp->sample(row, (size_t)V);
+            bool done;
+            if (eos_token_id && tok == *eos_token_id) {
+                done = true;
+            } else {
+                out[st.req].push_back(tok);
+                st.tok = tok;
+                done = (int)out[st.req].size() >= max_tokens;
+            }
+            if (done) {
+                running.erase(slot);
+                check(fl_cache_slot_reset(cache.h, slot));
+                free_slots.push_back(slot);
+            } else {
+                running[slot] = std::move(st);
+            }
+        };
+        while (!waiting.empty() || !running.empty()) {
+            while (!waiting.empty() && !free_slots.empty()) {             // admit: one prompt at a time, alone in its forward
+                const size_t req = waiting.back(); waiting.pop_back();
+                const int slot = free_slots.back(); free_slots.pop_back();
+                const std::vector<uint32_t>& p = prompts[req];
+                const size_t ro = 0;
+                check(fl_forward_slots(model.dev->h, cache.h, &slot, p.data(), 1, (int)p.size(), &ro, logits.data()));
+                Running st{req, M::kPositionPerCall ? (size_t)1 : p.size(), std::make_unique<LogitsProcessor>(0, (double)temperature), 0};
+                take(logits.data(), slot, std::move(st));
+            }
+            if (running.empty()) continue;
+            std::vector<int> slots;
+            std::vector<uint32_t> ids;
+            std::vector<size_t> ropes;
+            for (auto& kv : running) { slots.push_back(kv.first); ids.push_back(kv.second.tok); ropes.push_back(kv.second.rope); }   // ascending slots
+            check(fl_forward_slots(model.dev->h, cache.h, slots.data(), ids.data(), (int)slots.size(), 1, ropes.data(), logits.data()));
+            steps += 1;
+            for (size_t i = 0; i < slots.size(); ++i) {
+                Running st = std::move(running[slots[i]]);
+                st.rope += 1;
+                take(logits.data() + i * (size_t)V, slots[i], std::move(st));
+            }
         }
         return out;
     }

@@ -54,6 +54,27 @@ int main(int argc, char** argv) {
             tensors[name] = fastllm::HostTensor{FL_DTYPE_F32, shape, storage.back().data()};
         }
         const int max_tokens = std::atoi(argv[3]);
+        if (argc > 5 && std::strcmp(argv[4], "--batch") == 0) {
+            // host_selftest manifest weights max_tokens --batch max_batch id id / id id id / ...: the C++ ContinuousBatcher over sequence slots
+            const int max_batch = std::atoi(argv[5]);
+            std::vector<std::vector<uint32_t>> prompts(1);
+            for (int i = 6; i < argc; ++i) {
+                if (std::strcmp(argv[i], "/") == 0) prompts.emplace_back();
+                else prompts.back().push_back((uint32_t)std::strtoul(argv[i], nullptr, 10));
+            }
+            auto pr = fastllm::LlamaWithConfig::initialize_model(cfg, tensors, 0);
+            fastllm::ContinuousBatcher<fastllm::LlamaWithConfig> cb(pr.first, max_batch, std::nullopt);
+            const auto outs = cb.generate(prompts, max_tokens);
+            std::printf("[");
+            for (size_t r = 0; r < outs.size(); ++r) {
+                std::printf("%s[", r ? "," : "");
+                for (size_t i = 0; i < outs[r].size(); ++i) std::printf("%s%u", i ? "," : "", outs[r][i]);
+                std::printf("]");
+            }
+            std::printf("]\n");
+            std::fprintf(stderr, "ragged steps: %d\n", cb.steps);
+            return 0;
+        }
         std::vector<uint32_t> prompt;
         for (int i = 4; i < argc; ++i) prompt.push_back((uint32_t)std::strtoul(argv[i], nullptr, 10));
         auto pair = fastllm::LlamaWithConfig::initialize_model(cfg, tensors, 0);

@@ -39,3 +39,24 @@ def test_cpp_host_mirror_generates_oracle_ids(tmp_path):
     assert out.returncode == 0, out.stderr
     assert json.loads(out.stdout.strip().splitlines()[0]) == [int(t) for t in g["faithful_ids"]]
     assert "expected error" in out.stderr          # Llama t x t mask failure point is an error, not a crash
+
+
+@pytest.mark.gpu
+def test_cpp_continuous_batcher_equals_the_python_mirror(tmp_path):
+    """host/fastllm_host.hpp ContinuousBatcher (compiled) and fastllm_b200/models.py ContinuousBatcher issue the same fl_forward_slots
+    calls in the same order on the same weights: the ids must be identical (5 requests of different lengths over 2 slots)."""
+    from fastllm_b200 import models
+    from oracle import synth
+    from helpers import product_model
+    cfg, w, g = golden_weights("llama_gqa8")
+    _write_inputs(str(tmp_path), cfg, w)
+    prompts = [list(map(int, synth.token_ids(200 + i, cfg.vocab_size, (n,)))) for i, n in enumerate([7, 3, 19, 5, 11])]
+    args = []
+    for i, p in enumerate(prompts):
+        args += (["/"] if i else []) + [str(t) for t in p]
+    out = subprocess.run([EXE, str(tmp_path / "manifest.txt"), str(tmp_path / "weights.bin"), "5", "--batch", "2"] + args,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    model, _ = product_model(cfg, w)
+    want = models.ContinuousBatcher(model, max_batch=2, eos_token_id=None).generate(prompts, 5)
+    assert json.loads(out.stdout.strip().splitlines()[0]) == want
