@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     int* s_flag = reinterpret_cast<int*>(lrun + 8);
     __shared__ __align__(8) uint64_t full[kPkMaxStages];
     __shared__ __align__(8) uint64_t empty[kPkMaxStages];
+    __shared__ __align__(8) uint64_t xbar;      // completion of the bulk copies that bring a phase's hi/lo activation vector in
     __shared__ int2 meta[kPkMaxStages];      // per stage: {first row of the block, column chunk | last-chunk flag | end-of-phase flag}
     __shared__ int blk_rows[kPkMaxSlots];    // first rows of the blocks processed in the current phase
 
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kPkConsumerWarps);
         }
+        mbar_init(&xbar, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -482,15 +484,19 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         zero_x_tail(K);
         pk_named_sync();
     };
-    // plain activation vectors arrive already split (written hi | lo by their producers): a straight L2 -> shared copy
+    // plain activation vectors arrive already split (written hi | lo by their producers): a straight L2 -> shared copy, issued as
+    // two bulk copies (TMA engine, 1-D) by one thread -- one request per half instead of 14 load / store pairs per thread
+    unsigned int xphase = 0;
     auto load_x_plain = [&](const uint16_t* hi, int K) {
-        const uint4* h4 = reinterpret_cast<const uint4*>(hi);
-        const uint4* l4 = reinterpret_cast<const uint4*>(hi + K);
-        for (int i = tid; i < K / 8; i += kPkConsumers) {
-            reinterpret_cast<uint4*>(xh)[i] = ldcg_u4(h4 + i);
-            reinterpret_cast<uint4*>(xl)[i] = ldcg_u4(l4 + i);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores (ordered by the grid barrier) -> bulk reads
+            mbar_expect_tx(&xbar, (uint32_t)K * 4u);
+            bulk_g2s(xh, hi, (uint32_t)K * 2u, &xbar);
+            bulk_g2s(xl, hi + K, (uint32_t)K * 2u, &xbar);
         }
         zero_x_tail(K);
+        mbar_wait(&xbar, xphase & 1u);
+        xphase ^= 1u;
         pk_named_sync();
     };
 
