@@ -601,7 +601,7 @@ def run_ours(args, rank, world, local_rank):
         moe = moe_leg(args, rank, world, local_rank, dist, peak)
         if world == 1:
             try:
-                r = minilm_measure(local_rank, 256, 128, 20, 5)
+                r = minilm_measure(local_rank, 256, 128, 100, 10, warm=5)     # 100 device-resident batches (~0.2 s): short runs read 5-10 % apart
                 secondary = {"metric": "embeddings_per_s", "workload": WORKLOADS["minilm_256x128"][3], "value": 256 / (r["ms"] / 1e3),
                              "e2e": 256 / r["e2e_s"], "unit": "emb/s", "ms_per_batch": r["ms"],
                              "tensor_tflops": MINILM_FLOP_PER_TOKEN * 256 * 128 / (r["ms"] / 1e3) / 1e12}

@@ -149,13 +149,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // dynamic shared memory of gemm_tc_kernel<BN, *, DUAL> (ring + 1 KB alignment slack); mirrors the constants in the kernel
-// bf16-output epilogues (GEPI_BIAS_BF16 / GEPI_BIAS_GELU_BF16) stage every warp's 32 rows x 32 columns in shared memory (rows padded
-// to 80 bytes: conflict-free 16-byte accesses) and write them back 8 rows x 64 bytes per instruction.  thread == accumulator row is
+// The encoder's epilogues (GEPI_BIAS_BF16 / GEPI_BIAS_GELU_BF16: 32 bf16 columns per pass; GEPI_BIAS_RESID_F32: 16 f32 columns per
+// pass, its bf16 residual rows read through the same buffer) stage every warp's 32 rows x 64 bytes in shared memory (rows padded
+// to 80 bytes: conflict-free 16-byte accesses) and move them 8 rows x 64 bytes per instruction.  thread == accumulator row is
 // what tcgen05.ld hands out, and storing that way scatters every 16-byte store of a warp over 32 lines: ncu had the encoder's GEMMs
 // at 27 % tensor activity with the LSU as the busiest unit.
 constexpr int kEpiStageRow = 80;
 constexpr int kEpiStageBytes = kGemmEpiWarps * 32 * kEpiStageRow;      // 40 KB
-__host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi == GEPI_BIAS_BF16 || epi == GEPI_BIAS_GELU_BF16; }
+__host__ __device__ constexpr bool gemm_epi_staged(int epi) { return epi == GEPI_BIAS_BF16 || epi == GEPI_BIAS_GELU_BF16 || epi == GEPI_BIAS_RESID_F32; }
 
 inline size_t gemm_smem_bytes(int BN, int dual) {
     const size_t stage = (size_t)(dual == DUAL_A ? 2 : 1) * kGemmBM * kGemmBK * 2 + (size_t)(dual == DUAL_B ? 2 : 1) * BN * kGemmBK * 2;
@@ -483,6 +484,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r[j + 16]));
                     }
+                }
+                if (EPI == GEPI_BIAS_RESID_F32) {
+                    // f32 out = acc + bias + bf16 residual, 16 columns (64 bytes of f32) per pass: the residual rows (32 bytes each) come
+                    // in through the staging buffer two rows per lane, the results leave through it 8 rows x 64 bytes per instruction
+                    uint8_t* stg = gsm + (size_t)kStages * kStageBytes + (size_t)(warp - 2) * (32 * kEpiStageRow);
+                    float* obase = reinterpret_cast<float*>(g.out);
+#pragma unroll
+                    for (int hc = 0; hc < 32; hc += 16) {
+                        const int col = n0 + c0 + hc;
+                        if (g.resid != nullptr) {
+#pragma unroll
+                            for (int p = lane; p < 64; p += 32) {
+                                const int rr = p >> 1, part = p & 1;
+                                const int grow = m0 + q * 32 + rr, gcol = col + part * 8;
+                                uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                                if (grow < g.M && gcol < g.N) rv = *reinterpret_cast<const uint4*>(g.resid + (size_t)grow * g.ldr + gcol);
+                                *reinterpret_cast<uint4*>(stg + rr * kEpiStageRow + part * 16) = rv;
+                            }
+                            __syncwarp();
+                        }
+                        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                        if (g.resid != nullptr) {
+                            r0 = *reinterpret_cast<const uint4*>(stg + lane * kEpiStageRow);
+                            r1 = *reinterpret_cast<const uint4*>(stg + lane * kEpiStageRow + 16);
+                            __syncwarp();
+                        }
+                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 v = make_float4(__uint_as_float(r[hc + j]), __uint_as_float(r[hc + j + 1]), __uint_as_float(r[hc + j + 2]),
+                                                   __uint_as_float(r[hc + j + 3]));
+                            if (g.bias != nullptr && col + j < g.N) {
+                                const float4 bv = *reinterpret_cast<const float4*>(g.bias + col + j);
+                                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            }
+                            v.x += bf16lo(rw[j >> 1]); v.y += bf16hi(rw[j >> 1]); v.z += bf16lo(rw[(j >> 1) + 1]); v.w += bf16hi(rw[(j >> 1) + 1]);
+                            *reinterpret_cast<float4*>(stg + lane * kEpiStageRow + j * 4) = v;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int p = lane; p < 128; p += 32) {
+                            const int rr = p >> 2, part = p & 3;
+                            const int grow = m0 + q * 32 + rr, gcol = col + part * 4;
+                            if (grow < g.M && gcol < g.N)
+                                *reinterpret_cast<uint4*>(obase + (size_t)grow * g.ldo + gcol) = *reinterpret_cast<const uint4*>(stg + rr * kEpiStageRow + part * 16);
+                        }
+                        __syncwarp();
+                    }
+                    continue;
                 }
                 if (gemm_epi_staged(EPI)) {
                     // stage this lane's row (32 columns = 64 bytes), then the warp stores 8 rows x 64 bytes per instruction
