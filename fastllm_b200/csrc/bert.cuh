@@ -49,35 +49,40 @@ static __global__ void embed_ln_kernel(const uint16_t* __restrict__ wemb, const 
     }
 }
 
-// LayerNorm over f32 rows [T, H] -> bf16 [T, H]; one warp per row.
+// LayerNorm over f32 rows [T, H] -> bf16 [T, H]; one warp per row, 128-bit loads / 64-bit stores (H % 4 == 0, H <= 512).
 static __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ lnw, const float* __restrict__ lnb, int T, int H,
                                  float eps, uint16_t* __restrict__ out) {
     pdl_launch_dependents();      // programmatic dependent launch: the next kernel may start its prologue now ...
     pdl_wait();                   // ... and nothing below runs before the previous kernel has completed
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
-    const float* xr = x + (size_t)row * H;
-    float v[16];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * H);
+    const int H4 = H >> 2;
+    float4 v[4];
     float s = 0.f, s2 = 0.f;
-    const int per = (H + 31) / 32;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 4; ++j) {
         const int c = lane + 32 * j;
-        v[j] = 0.f;
-        if (j < per && c < H) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < H4) {
             v[j] = xr[c];
-            s += v[j];
-            s2 = fmaf(v[j], v[j], s2);
+            s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            s2 = fmaf(v[j].x, v[j].x, s2); s2 = fmaf(v[j].y, v[j].y, s2); s2 = fmaf(v[j].z, v[j].z, s2); s2 = fmaf(v[j].w, v[j].w, s2);
         }
     }
     s = warp_sum(s);
     s2 = warp_sum(s2);
     const float mean = s / (float)H;
     const float inv = 1.f / sqrtf(s2 / (float)H - mean * mean + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + (size_t)row * H);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 4; ++j) {
         const int c = lane + 32 * j;
-        if (j < per && c < H) out[(size_t)row * H + c] = f32_to_bf16_rne((v[j] - mean) * inv * lnw[c] + lnb[c]);
+        if (c < H4) {
+            const float4 w4 = reinterpret_cast<const float4*>(lnw)[c], b4 = reinterpret_cast<const float4*>(lnb)[c];
+            orow[c] = make_uint2(pack_bf16x2((v[j].x - mean) * inv * w4.x + b4.x, (v[j].y - mean) * inv * w4.y + b4.y),
+                                 pack_bf16x2((v[j].z - mean) * inv * w4.z + b4.z, (v[j].w - mean) * inv * w4.w + b4.w));
+        }
     }
 }
 
