@@ -17,7 +17,6 @@ struct BertLayerW {
     float *bqkv = nullptr, *bo = nullptr, *bi = nullptr, *bo2 = nullptr;
     float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
     CUtensorMap tm_wqkv, tm_wo, tm_wi, tm_wo2;
-    CUtensorMap tm_wo_ln, tm_wo2_ln;     // the two residual projections with a box of H / 2 rows (bert_gemm_ln_kernel)
 };
 
 struct BertModel {
@@ -29,7 +28,6 @@ struct BertModel {
     std::vector<BertLayerW> layers;
     std::set<std::string> have;
     bool finalized = false;
-    bool ln_fused = false;               // residual GEMM + LayerNorm as one kernel (hidden % 128 == 0)
     cudaStream_t stream = nullptr;
     std::mutex mu;
     // workspace (grown on demand)

@@ -4,7 +4,6 @@
 #include <memory>
 
 #include "bert.cuh"
-#include "bert_gemm_ln.cuh"
 #include "bert_model.cuh"
 #include "gemm_tc.cuh"
 #include "synth.cuh"
@@ -99,25 +98,6 @@ static void launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
     }
     const int tiles = ((g.M + kGemmBM - 1) / kGemmBM) * ((g.N + BN - 1) / BN);
     blaunch(st, gemm_tc_kernel<BN, EPI>, dim3(std::min(tiles, kNumSMs)), dim3(kGemmThreads), smem, tmA, tmA, tmB, g);
-}
-
-// weight-stationary variant for the K = hidden GEMMs (bert_gemm_ln.cuh); falls back to gemm_tc_kernel when K is too deep
-template <int EPI>
-static void launch_gemm_khidden(cudaStream_t st, bool bres, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
-    const int nt = (g.N + kBresBN - 1) / kBresBN;
-    if (!bres || (g.K + kGemmBK - 1) / kGemmBK > kBresMaxNk || nt > kNumSMs) {
-        launch_gemm<EPI>(st, tmA, tmB, g);
-        return;
-    }
-    const size_t smem = bert_bres_smem(g.K);
-    static bool attr_set = false;
-    if (!attr_set) {
-        FL_CUDA(cudaFuncSetAttribute(bert_gemm_bres_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bert_bres_smem(kBresMaxNk * kGemmBK)));
-        attr_set = true;
-    }
-    const int mt = (g.M + kGemmBM - 1) / kGemmBM;
-    const int groups = std::max(1, std::min(kNumSMs / nt, mt));
-    blaunch(st, bert_gemm_bres_kernel<EPI>, dim3(groups * nt), dim3(kGemmThreads), smem, tmA, tmB, g);
 }
 
 // ---- weights -------------------------------------------------------------------------------------------------------------
@@ -268,17 +248,6 @@ void bert_finalize(BertModel& m) {
         w.tm_wi = make_tmap_bf16(w.wi, m.I, m.H, m.H, kBertBN);
         w.tm_wo2 = make_tmap_bf16(w.wo2, m.H, m.I, m.I, kBertBN);
     }
-    // residual projection + LayerNorm in one kernel: a CTA owns complete rows (two MMAs of N = H / 2 into one TMEM accumulator)
-    // EXPERIMENTAL, off unless FL_BERT_LNFUSE=1: measured slower than GEMM + LayerNorm kernel (89.8 vs 60.5 + 19.6 us per block at 256 x 128:
-    // its thread-per-row residual reads and two TMEM passes cost more than the f32 round trip they save)
-    m.ln_fused = m.H % 128 == 0 && env_flag("FL_BERT_LNFUSE");
-    if (m.ln_fused) {
-        for (BertLayerW& w : m.layers) {
-            w.tm_wo_ln = make_tmap_bf16(w.wo, m.H, m.H, m.H, m.H / 2);
-            w.tm_wo2_ln = make_tmap_bf16(w.wo2, m.H, m.I, m.I, m.H / 2);
-        }
-        FL_CUDA(cudaFuncSetAttribute(bert_gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bert_ln_gemm_smem(m.H)));
-    }
     m.finalized = true;
 }
 
@@ -306,37 +275,23 @@ static void bert_enqueue(BertModel& m, int b, int t, bool has_mask) {
                       tm_ctx = make_tmap_bf16(m.ctx.p, T, H, H, kGemmBM), tm_h = make_tmap_bf16(m.hbuf.p, T, I, I, kGemmBM);
     const float eps = m.cfg.norm_eps;
     const float scale = (float)std::sqrt((double)m.d);
-    // EXPERIMENTAL, off unless FL_BERT_BRES=1: weight-stationary variant of the K = hidden GEMMs; measured slower (58 / 83 us against
-    // 55 / 76): these GEMMs were bound by their epilogue's stores, not by the operand traffic the variant saves
-    static const bool bres = env_flag("FL_BERT_BRES");
     for (int l = 0; l < m.L; ++l) {
         const BertLayerW& w = m.layers[l];
         // B2: fused q|k|v projection + bias -> bf16 [T, 3H]
-        launch_gemm_khidden<GEPI_BIAS_BF16>(st, bres, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
+        launch_gemm<GEPI_BIAS_BF16>(st, tm_x, w.tm_wqkv, GemmArgs{T, 3 * H, H, w.bqkv, nullptr, 0, m.qkv.p, 3 * H, 1, 0});
         // B3+B4: per (sentence, head) softmax(QK^T / sqrt(d)) V, no mask
         if (t <= kBertS)
             blaunch(st, bert_attn_kernel, dim3(m.nh, b), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
         else
             blaunch(st, bert_attn_long_kernel, dim3(m.nh, b, (t + kBertS - 1) / kBertS), dim3(128), 0, (const uint16_t*)m.qkv.p, t, H, scale, m.ctx.p);
-        // B5: attention output dense + bias + residual, LayerNorm -> bf16 (one kernel when the hidden size allows)
-        const int ln_grid = std::min((T + kGemmBM - 1) / kGemmBM, kNumSMs);
-        if (m.ln_fused) {
-            blaunch(st, bert_gemm_ln_kernel, dim3(ln_grid), dim3(kGemmThreads), bert_ln_gemm_smem(H), tm_ctx, w.tm_wo_ln,
-                    BertLnGemmArgs{T, H, H, w.bo, m.x.p, w.ln1w, w.ln1b, eps, m.x1.p});
-        } else {
-            launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
-            blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln1w, (const float*)w.ln1b, T, H, eps, m.x1.p);
-        }
+        // B5: attention output dense + bias + residual -> f32, then LayerNorm -> bf16
+        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_ctx, w.tm_wo, GemmArgs{T, H, H, w.bo, m.x.p, H, m.pre.p, H, 1, 0});
+        blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln1w, (const float*)w.ln1b, T, H, eps, m.x1.p);
         // B6: intermediate dense + bias + GELU(tanh) -> bf16 [T, I]
-        launch_gemm_khidden<GEPI_BIAS_GELU_BF16>(st, bres, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
+        launch_gemm<GEPI_BIAS_GELU_BF16>(st, tm_x1, w.tm_wi, GemmArgs{T, I, H, w.bi, nullptr, 0, m.hbuf.p, I, 1, 0});
         // B7: output dense + bias + residual -> f32, LayerNorm -> bf16
-        if (m.ln_fused) {
-            blaunch(st, bert_gemm_ln_kernel, dim3(ln_grid), dim3(kGemmThreads), bert_ln_gemm_smem(H), tm_h, w.tm_wo2_ln,
-                    BertLnGemmArgs{T, H, I, w.bo2, m.x1.p, w.ln2w, w.ln2b, eps, m.x.p});
-        } else {
-            launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H, 1, 0});
-            blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln2w, (const float*)w.ln2b, T, H, eps, m.x.p);
-        }
+        launch_gemm<GEPI_BIAS_RESID_F32>(st, tm_h, w.tm_wo2, GemmArgs{T, H, I, w.bo2, m.x1.p, H, m.pre.p, H, 1, 0});
+        blaunch(st, layernorm_kernel, row_grid, row_block, 0, (const float*)m.pre.p, (const float*)w.ln2w, (const float*)w.ln2b, T, H, eps, m.x.p);
     }
     // B8: masked mean pooling + L2 normalise -> f32 [b, H]
     blaunch(st, pool_l2_kernel, dim3(b), dim3((H + 31) / 32 * 32), 0, (const uint16_t*)m.x.p, has_mask ? (const uint32_t*)m.mask.p : (const uint32_t*)nullptr,

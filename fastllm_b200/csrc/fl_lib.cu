@@ -968,8 +968,7 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     }
     d.resid.alloc(R * w.H); d.q.alloc(R * nq);      // the attention output goes straight into xhi / xlo (hi/lo operand of o_proj)
     if (w.tp > 1) d.tp_buf.alloc(R * w.H);
-    if (w.cfg.arch != FL_ARCH_MIXTRAL) { d.xhi2.alloc(R * (size_t)w.I); d.xlo2.alloc(R * (size_t)w.I); }   // the MLP activation (down_proj operand)
-    if (d.tile_ctr.p == nullptr) d.tile_ctr.alloc(kTileCtrs, true);
+    if (w.cfg.arch != FL_ARCH_MIXTRAL && R > 128) { d.xhi2.alloc(R * (size_t)w.I); d.xlo2.alloc(R * (size_t)w.I); }
     if (w.cfg.arch == FL_ARCH_MIXTRAL) {
         // grouped path (calls with <= 128 expert rows): E_local blocks of up to grp_cap rows; masked path (prefill): Rm rows
         d.grp_cap = moe_group_cap((int)std::min<size_t>(Rm, 128));
@@ -1035,23 +1034,8 @@ static int pick_ksplit(int tiles, int nk, int R) {
 //   R <= 128 (decode batches, short prefills): swap-AB -- the weights are the 128-row MMA operand, the activations a tiny
 //             N = R tile, the result is stored transposed; the only large shared-memory traffic is the weight stream.
 //   R  > 128 (prefill): tokens are the M dimension, 128 x 128 output tiles.
-// Fused tail of a decode (swap-AB) GEMM: see FUSE_* in gemm_tc.cuh.  EXPERIMENTAL, off unless FL_FUSE=1: parity-green, but the first
-// measurement (round 2, Mistral-7B batch 8) had gate|up at 730 us against 45 us unfused and o_proj at 83 against 15 -- the per-item
-// fence + ticket + re-read chain sits on the epilogue warps' critical path -- so the separate element-wise kernels stay the default.
-struct FuseSpec {
-    int kind = FUSE_NONE;
-    uint16_t* act_hi = nullptr;
-    uint16_t* act_lo = nullptr;
-    int act_ld = 0;
-    GemmQkvFuse qkv{};
-};
-static bool fuse_on(int rows) {
-    return rows <= 128 && env_flag("FL_FUSE");      // read per enqueue (a graph keeps the plan it was captured with)
-}
-
 static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N, int K, const CUtensorMap& tmW, float* out,
-                      const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, uint16_t* silu_hi = nullptr, uint16_t* silu_lo = nullptr,
-                      const FuseSpec* fz = nullptr) {
+                      const uint16_t* xhi = nullptr, const uint16_t* xlo = nullptr, uint16_t* silu_hi = nullptr, uint16_t* silu_lo = nullptr) {
     if (!xhi) { xhi = c.dw.xhi.p; xlo = c.dw.xlo.p; }
     const int nk = (K + kGemmBK - 1) / kGemmBK;
     const bool swap = R <= 128;
@@ -1079,19 +1063,6 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         g.w_prefetch = (w_prefetch && pdl) ? 1 : 0;
         static const int gemm_dbg = std::getenv("FL_GEMM_DBG") ? std::atoi(std::getenv("FL_GEMM_DBG")) : 0;
         g.dbg = gemm_dbg;
-        if (fz != nullptr && fz->kind != FUSE_NONE && fuse_on(R)) {
-            FL_CHECK(tiles <= kTileCtrs, FL_ERR_UNSUPPORTED, "internal: more output tiles than arrival counters");
-            g.fuse = fz->kind; g.tile_ctr = c.dw.tile_ctr.p;
-            g.act_hi = fz->act_hi; g.act_lo = fz->act_lo; g.act_ld = fz->act_ld; g.qkv = fz->qkv;
-        }
-        if (g.fuse != FUSE_NONE) {
-            switch (bn) {
-                case 16: launch_gemm_tc<16, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
-                case 32: launch_gemm_tc<32, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
-                case 64: launch_gemm_tc<64, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
-                default: launch_gemm_tc<128, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
-            }
-        } else
         switch (bn) {
             case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
             case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmW, hi, lo, g); break;
@@ -1115,7 +1086,6 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
         g_prof.entries.push_back(pe);
     }
     if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (swap && fz != nullptr && fz->kind != FUSE_NONE && fuse_on(R)) return 1;     // the fused tail left ONE slice (or consumed them)
     return ks;
 }
 
@@ -1123,7 +1093,7 @@ static int dense_gemm(fl_cache& c, LaunchCtx& lc, const char* tag, int R, int N,
 // `cap` rows, cnt[j] valid) with ITS matrix (block j of the stacked weights, Ne rows): out[ks][j * cap + n][Ne].  ONE launch over
 // (expert, weight tile, k slice) work items; an expert without rows costs nothing.  Returns the split-K factor.
 static int dense_gemm_grouped(fl_cache& c, LaunchCtx& lc, const char* tag, int groups, int cap, int Ne, int K, const CUtensorMap& tmWall,
-                              float* out, const uint16_t* xhi, const uint16_t* xlo, const int* cnt, const FuseSpec* fz = nullptr) {
+                              float* out, const uint16_t* xhi, const uint16_t* xlo, const int* cnt) {
     const int nk = (K + kGemmBK - 1) / kGemmBK;
     const int tiles = groups * ((Ne + kGemmBM - 1) / kGemmBM);
     const int ks = pick_ksplit(tiles, nk, cap);
@@ -1140,20 +1110,6 @@ static int dense_gemm_grouped(fl_cache& c, LaunchCtx& lc, const char* tag, int g
     const CUtensorMap hi = make_tmap_bf16(xhi, (uint64_t)groups * cap, K, K, cap), lo = make_tmap_bf16(xlo, (uint64_t)groups * cap, K, K, cap);
     GemmArgs g{groups * Ne, cap, K, nullptr, nullptr, 0, out, Ne, ks, (long long)groups * cap * Ne};
     g.grp_m = Ne; g.grp_cap = cap; g.grp_cnt = cnt;
-    const bool fused = fz != nullptr && fz->kind != FUSE_NONE && fuse_on(cap);
-    if (fused) {
-        FL_CHECK(tiles <= kTileCtrs, FL_ERR_UNSUPPORTED, "internal: more output tiles than arrival counters");
-        g.fuse = fz->kind; g.tile_ctr = c.dw.tile_ctr.p;
-        g.act_hi = fz->act_hi; g.act_lo = fz->act_lo; g.act_ld = fz->act_ld;
-    }
-    if (fused) {
-        switch (cap) {
-            case 16: launch_gemm_tc<16, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
-            case 32: launch_gemm_tc<32, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
-            case 64: launch_gemm_tc<64, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
-            default: launch_gemm_tc<128, GEPI_F32_TF, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
-        }
-    } else
     switch (cap) {
         case 16: launch_gemm_tc<16, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
         case 32: launch_gemm_tc<32, GEPI_F32_T, DUAL_B>(lc.stream, pdl, tiles * ks, tmWall, hi, lo, g); break;
@@ -1165,7 +1121,7 @@ static int dense_gemm_grouped(fl_cache& c, LaunchCtx& lc, const char* tag, int g
         g_prof.entries.push_back(pe);
     }
     if (lc.capturing) lc.captured++; else g_launches.fetch_add(1, std::memory_order_relaxed);
-    return fused ? 1 : ks;
+    return ks;
 }
 
 static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool loop_mode) {
@@ -1192,15 +1148,10 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
         const LayerW& lw = w.layers[l];
         uint16_t* kpool = c.kpool.p + (size_t)l * c.layer_pool_elems;
         uint16_t* vpool = c.vpool.p + (size_t)l * c.layer_pool_elems;
-        FuseSpec fq;      // decode batches: bias + RoPE + q store + KV append run in the GEMM's fused tail
-        fq.kind = FUSE_QKV;
-        fq.qkv = GemmQkvFuse{lw.bqkv, d.q.p, kpool, vpool, c.page_table.p, c.pages_per_seq, c.state.p, w.rope_cos, w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t};
-        int ks = dense_gemm(c, lc, "gemm_tc_qkv", R, w.nqkv, w.H, lw.tm_wqkv, d.y.p, nullptr, nullptr, nullptr, nullptr, &fq);
-        if (!fuse_on(R)) {
-            QkvEpiArgs qa{ks, (long long)R * w.nqkv, d.y.p, lw.bqkv, d.q.p, kpool, vpool, c.page_table.p, c.pages_per_seq, c.state.p, w.rope_cos,
-                          w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t, w.nqkv};
-            launch(lc, "dense_qkv_rope_append", 0, dense_qkv_epi_kernel, dim3((w.nqkv / 2 + 255) / 256, R), dim3(256), 0, qa);
-        }
+        int ks = dense_gemm(c, lc, "gemm_tc_qkv", R, w.nqkv, w.H, lw.tm_wqkv, d.y.p);
+        QkvEpiArgs qa{ks, (long long)R * w.nqkv, d.y.p, lw.bqkv, d.q.p, kpool, vpool, c.page_table.p, c.pages_per_seq, c.state.p, w.rope_cos,
+                      w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t, w.nqkv};
+        launch(lc, "dense_qkv_rope_append", 0, dense_qkv_epi_kernel, dim3((w.nqkv / 2 + 255) / 256, R), dim3(256), 0, qa);
         {   // K7-K11 on tensor cores; the output lands as the hi/lo bf16 operands of the o_proj GEMM
             AttnArgs at{};
             at.q = d.q.p; at.kpool = kpool; at.vpool = vpool; at.page_table = c.page_table.p; at.pt_stride = c.pages_per_seq;
@@ -1228,9 +1179,7 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 launch_attn_mma(lc, w.d, false, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
             }
         }
-        FuseSpec fsum;
-        fsum.kind = FUSE_SUM;
-        ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p, nullptr, nullptr, nullptr, nullptr, &fsum);
+        ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p);
         const float* delta = d.y.p;
         auto tp_reduce = [&]() {   // row-parallel GEMM: fold the split-K slices, then all-reduce the partial sums across ranks
             if (w.tp <= 1) return;
@@ -1273,15 +1222,11 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 const int cap = moe_group_cap(Rm), Rg = w.E_local * cap, e0 = w.rank * w.E_local;
                 MoeGatherArgs ga{ex_hi, ex_lo, ex_route, Rm, w.H, w.E, e0, w.E_local, cap, d.gx_hi.p, d.gx_lo.p, d.grp_cnt.p, d.grp_pos.p};
                 launch(lc, "moe_gather", 0, moe_gather_kernel, dim3(w.E_local, std::max(1, std::min(Rm, 2 * kNumSMs / w.E_local))), dim3(256), 0, ga);
-                FuseSpec fsilu;
-                fsilu.kind = FUSE_SILU; fsilu.act_hi = d.xhi2.p; fsilu.act_lo = d.xlo2.p; fsilu.act_ld = w.I;
                 int ke = dense_gemm_grouped(c, lc, "gemm_tc_moe_w13", w.E_local, cap, 2 * w.I, w.H, lw.tm_ewgu_all, d.y.p, d.gx_hi.p, d.gx_lo.p,
-                                            d.grp_cnt.p, &fsilu);
-                if (!fuse_on(cap))
-                    launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, Rg), dim3(256), 0, (const float*)d.y.p, ke,
-                           (long long)Rg * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p, (const int*)d.grp_cnt.p, cap);
-                ke = dense_gemm_grouped(c, lc, "gemm_tc_moe_w2", w.E_local, cap, w.H, w.I, lw.tm_ewdown_all, d.y.p, d.xhi2.p, d.xlo2.p, d.grp_cnt.p,
-                                        &fsum);
+                                            d.grp_cnt.p);
+                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, Rg), dim3(256), 0, (const float*)d.y.p, ke,
+                       (long long)Rg * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p, (const int*)d.grp_cnt.p, cap);
+                ke = dense_gemm_grouped(c, lc, "gemm_tc_moe_w2", w.E_local, cap, w.H, w.I, lw.tm_ewdown_all, d.y.p, d.xhi2.p, d.xlo2.p, d.grp_cnt.p);
                 launch(lc, "moe_combine", 0, moe_combine_kernel, dim3((w.H + 255) / 256, Rm), dim3(256), 0, (const float*)d.y.p, ke,
                        (long long)Rg * w.H, w.H, ex_route, w.E, e0, w.E_local, (const int*)d.grp_pos.p, d.moe_out.p);
             } else
@@ -1311,15 +1256,10 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p, nullptr, nullptr, d.xhi2.p, d.xlo2.p);
                 ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p, d.xhi2.p, d.xlo2.p);
             } else {
-                // decode batches: SiLU(gate) * up + the hi/lo split run in the gate|up GEMM's fused tail, straight into the down_proj
-                // operand (a second buffer pair: other CTAs are still reading the block input from xhi / xlo)
-                FuseSpec fsilu;
-                fsilu.kind = FUSE_SILU; fsilu.act_hi = d.xhi2.p; fsilu.act_lo = d.xlo2.p; fsilu.act_ld = w.I;
-                ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p, nullptr, nullptr, nullptr, nullptr, &fsilu);
-                if (!fuse_on(R))
-                    launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
-                           (long long)R * 2 * w.I, w.I, d.xhi2.p, d.xlo2.p, (const int*)nullptr, 0);
-                ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p, d.xhi2.p, d.xlo2.p, nullptr, nullptr, &fsum);
+                ks = dense_gemm(c, lc, "gemm_tc_gateup", R, 2 * w.I, w.H, lw.tm_wgu, d.y.p);
+                launch(lc, "dense_silu_split", 0, dense_silu_split_kernel, dim3((w.I + 255) / 256, R), dim3(256), 0, (const float*)d.y.p, ks,
+                       (long long)R * 2 * w.I, w.I, d.xhi.p, d.xlo.p, (const int*)nullptr, 0);
+                ks = dense_gemm(c, lc, "gemm_tc_down", R, w.H, w.I, lw.tm_wdown, d.y.p);
             }
             delta = d.y.p;
             tp_reduce();
@@ -1334,9 +1274,7 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             prep("dense_final_rmsnorm", pa, b);
         }
     }
-    FuseSpec fhead;
-    fhead.kind = FUSE_SUM;
-    const int ksh = dense_gemm(c, lc, "gemm_tc_lm_head", b, w.V, w.H, w.tm_head, d.y.p, nullptr, nullptr, nullptr, nullptr, &fhead);
+    const int ksh = dense_gemm(c, lc, "gemm_tc_lm_head", b, w.V, w.H, w.tm_head, d.y.p);
     if (w.tp > 1) {   // vocab-parallel head
         launch(lc, "tp_sum_slices", 0, sum_slices_kernel, dim3(kNumSMs), dim3(256), 0, (const float*)d.y.p, ksh, (long long)b * w.V, b * w.V,
                c.tp_local.p);

@@ -15,31 +15,10 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "gemv.cuh"
 
 namespace fl {
 
-// Fused tail of a swap-AB split-K GEMM (GemmArgs.fuse): the CTA that completes the LAST k slice of an output tile (atomic ticket per
-// tile) sums the slices in slice order -- deterministic, whichever CTA arrives last -- and applies the consumer's element-wise step
-// in place of a separate kernel launch between two GEMMs of the decode chain:
-//   FUSE_SUM : the sum overwrites slice 0 (consumers read ONE slice)
-//   FUSE_SILU: rows interleave gate_j / up_j -> act_j = silu(gate_j) * up_j written as the hi / lo bf16 operand of the next GEMM
-//   FUSE_QKV : bias + RoPE (rotate-half; partner rows are adjacent) + q store + in-place paged KV append
-enum : int { FUSE_NONE = 0, FUSE_SUM = 1, FUSE_SILU = 2, FUSE_QKV = 3 };
-struct GemmQkvFuse {
-    const float* bias;          // [nqkv] or null
-    float* q_out;               // [R, nh * d]
-    uint16_t* kpool;
-    uint16_t* vpool;
-    const int* page_table;
-    int pt_stride;
-    const StepState* state;
-    const float* rope_cos;
-    const float* rope_sin;
-    int nh, nkv, d, max_pos, t;
-};
-
-enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5, GEPI_SILU_HL = 6, GEPI_F32_TF = 7 };      // _TF: F32_T + the fused tails (own instantiation: the default kernel stays as measured)
+enum : int { GEPI_BIAS_BF16 = 0, GEPI_BIAS_GELU_BF16 = 1, GEPI_BIAS_RESID_F32 = 2, GEPI_F32 = 3, GEPI_ATOMIC_F32 = 4, GEPI_F32_T = 5, GEPI_SILU_HL = 6 };
 enum : int { DUAL_NONE = 0, DUAL_A = 1, DUAL_B = 2 };
 
 constexpr int kGemmBM = 128;
@@ -66,12 +45,6 @@ struct GemmArgs {
     int grp_m = 0;
     int grp_cap = 0;
     const int* grp_cnt = nullptr;
-    int fuse = FUSE_NONE;       // GEPI_F32_T: fused tail (see FUSE_*)
-    int* tile_ctr = nullptr;    // [tiles] arrival tickets of the k slices, zero between launches (the last arriver re-arms its tile)
-    uint16_t* act_hi = nullptr; // FUSE_SILU: [rows, act_ld] hi / lo halves
-    uint16_t* act_lo = nullptr;
-    int act_ld = 0;
-    GemmQkvFuse qkv{};          // FUSE_QKV
     int dbg = 0;                // dev knob FL_GEMM_DBG (timing experiments only, results are garbage): bit 0 = DUAL_B without the
                                 // activation loads, bit 1 = no MMAs (the issuer releases a stage as soon as it has landed)
 };
@@ -176,96 +149,6 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return fmaf(hx, t, hx);
 }
 
-// The fused tails of the last-arriving k slice (see FUSE_*), out of line: the epilogue warps of an 18-warp CTA have 96 registers each
-// and the accumulator read-out already uses most of them.  `row` is the weight row of this thread (thread == TMEM lane), `orow0` the
-// first activation row (column of the swapped product) of the 16 handled per call, `ncol` how many of them are valid.  Everything a
-// tail needs arrives BY VALUE: fields of the kernel's parameter struct read through a reference would be re-fetched from parameter
-// space after every store (the compiler must assume the stores alias it) -- the first version did that and ran 10x slower.
-__device__ __forceinline__ void gemm_tail_sum16(float (&v)[16], const float* src, size_t split_stride, int ldo, int ksplit, int ncol, bool live) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-    if (!live) return;
-    for (int sl = 0; sl < ksplit; ++sl) {                       // slice order: deterministic
-        const float* pj = src + (size_t)sl * split_stride;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < ncol) v[j] += __ldcg(pj + (size_t)j * ldo);
-    }
-}
-
-static __device__ __noinline__ void gemm_tail_sum(float* out, size_t split_stride, int ldo, int ksplit, size_t orow0, int ncol, int row, bool live) {
-    float v[16];
-    gemm_tail_sum16(v, out + orow0 * ldo + row, split_stride, ldo, ksplit, ncol, live);
-    if (live) {
-        float* dst = out + orow0 * ldo + row;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < ncol) dst[(size_t)j * ldo] = v[j];
-    }
-}
-
-// even lane = gate_j, odd lane = up_j (rows 2j, 2j + 1); the even lane writes act_j = silu(gate_j) * up_j as a hi / lo bf16 pair
-static __device__ __noinline__ void gemm_tail_silu(const float* out, size_t split_stride, int ldo, int ksplit, size_t orow0, int ncol, int row,
-                                                   bool live, bool pair_live, int lane, uint16_t* act_hi, uint16_t* act_lo, int act_ld) {
-    float v[16];
-    gemm_tail_sum16(v, out + orow0 * ldo + row, split_stride, ldo, ksplit, ncol, live);
-    const int jj = row >> 1;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float up = __shfl_down_sync(0xFFFFFFFFu, v[j], 1);
-        if (j < ncol && !(lane & 1) && pair_live) {
-            const float act = v[j] / (1.f + expf(-v[j])) * up;
-            const uint16_t h = f32_to_bf16_rne(act);
-            const uint16_t l = f32_to_bf16_rne(act - __uint_as_float((uint32_t)h << 16));
-            act_hi[(orow0 + j) * act_ld + jj] = h;
-            act_lo[(orow0 + j) * act_ld + jj] = l;
-        }
-    }
-}
-
-// even lane = row ra, odd lane = its RoPE partner ra + 1 (the q / k rows are pair-permuted on upload): bias, rotate-half RoPE, q store,
-// in-place paged KV append -- what dense_qkv_epi_kernel does as a separate launch
-static __device__ __noinline__ void gemm_tail_qkv(const float* out, size_t split_stride, int ldo, int ksplit, int c0, int ncol, int row, bool live,
-                                                  bool pair_live, int lane, const GemmQkvFuse* fp) {
-    const GemmQkvFuse f = *fp;          // ONE copy out of the caller's parameter block (see above)
-    float v[16];
-    gemm_tail_sum16(v, out + (size_t)c0 * ldo + row, split_stride, ldo, ksplit, ncol, live);
-    const int d = f.d, half = d >> 1;
-    const int hh = row / d, jr = (row % d) >> 1;
-    float ba = 0.f, bb = 0.f;
-    if (f.bias != nullptr && pair_live) { ba = f.bias[row & ~1]; bb = f.bias[(row & ~1) + 1]; }
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
-        const float other = __shfl_xor_sync(0xFFFFFFFFu, v[j], 1);
-        if (j < ncol && !(lane & 1) && pair_live) {
-            const float va = v[j] + ba, vb = other + bb;
-            const int arow = c0 + j;                            // activation row = seq * t + irel
-            const int seq = arow / f.t, irel = arow % f.t;
-            const int cslot = st_slot(f.state, seq);
-            const int slot = f.state->kv_base[cslot] + irel;
-            const int page = f.page_table[cslot * f.pt_stride + slot / kKvPage];
-            if (hh < f.nh + f.nkv) {
-                int pos = st_rope(f.state, seq) + irel;
-                pos = pos < f.max_pos ? pos : f.max_pos - 1;
-                const float cs = f.rope_cos[(size_t)pos * half + jr], sn = f.rope_sin[(size_t)pos * half + jr];
-                const float o1 = va * cs - vb * sn, o2 = va * sn + vb * cs;
-                if (hh < f.nh) {
-                    float* qp = f.q_out + ((size_t)arow * f.nh + hh) * d;
-                    qp[jr] = o1;
-                    qp[jr + half] = o2;
-                } else {
-                    uint16_t* kp = f.kpool + (((size_t)page * f.nkv + (hh - f.nh)) * kKvPage + slot % kKvPage) * d;
-                    kp[jr] = f32_to_bf16_rne(o1);
-                    kp[jr + half] = f32_to_bf16_rne(o2);
-                }
-            } else {
-                uint16_t* vp = f.vpool + (((size_t)page * f.nkv + (hh - f.nh - f.nkv)) * kKvPage + slot % kKvPage) * d;
-                *reinterpret_cast<uint32_t*>(vp + 2 * jr) = (uint32_t)f32_to_bf16_rne(va) | ((uint32_t)f32_to_bf16_rne(vb) << 16);
-            }
-        }
-    }
-}
-
 // Persistent, warp-specialised: grid = min(#SMs, #tiles); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n fastest, so
 // the CTAs running concurrently share activation rows through L2).  Three pipelines: shared-memory ring (TMA -> MMA),
 // two TMEM accumulator stages (MMA -> epilogue: the epilogue of tile i overlaps the MMAs of tile i+1), and the tile walk.
@@ -299,7 +182,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* gsm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ int s_last_slice;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (g.K + kGemmBK - 1) / kGemmBK;
@@ -607,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 *reinterpret_cast<uint4*>(ol + (j >> 1)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                             }
                         }
-                    } else if (EPI == GEPI_F32_T || EPI == GEPI_F32_TF) {
+                    } else if (EPI == GEPI_F32_T) {
                         // transposed store: D[row = weight row, col = activation row] -> out[slice][col, row]; for a fixed col the
                         // 32 lanes of the warp write 32 consecutive floats
                         float* o = reinterpret_cast<float*>(g.out) + (size_t)ksi * (size_t)g.split_stride + (size_t)grp * g.grp_cap * g.ldo + row;
@@ -650,37 +532,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
-
-            if (EPI == GEPI_F32_TF && g.fuse != FUSE_NONE) {
-                // ---- fused tail: the last k slice of this tile to arrive sums the slices and applies the consumer's step ----
-                bool last = true;
-                if (ksplit > 1) {
-                    __threadfence();                                                   // this item's slice is visible before its ticket
-                    asm volatile("bar.sync 2, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
-                    if (warp == 2 && lane == 0) {
-                        const int ticket = atomicAdd(g.tile_ctr + tile, 1);
-                        s_last_slice = ticket == ksplit - 1;
-                        if (ticket == ksplit - 1) g.tile_ctr[tile] = 0;
-                    }
-                    asm volatile("bar.sync 2, %0;" ::"n"(32 * kGemmEpiWarps) : "memory");
-                    last = s_last_slice != 0;
-                    if (last) __threadfence();
-                }
-                if (last) {
-                    float* const outp = reinterpret_cast<float*>(g.out);
-                    const bool live = row < row_lim, pair_live = row + 1 < row_lim;
-#pragma unroll 1
-                    for (int c0 = cslice * 32; c0 < BN; c0 += (c0 & 16) ? 112 : 16) {   // 16 columns at a time: both halves of a 32-column chunk, then this warp's next chunk
-                        const int ncol = min(16, col_lim - c0);                         // valid activation rows of this half chunk
-                        if (ncol <= 0) continue;
-                        const size_t orow0 = (size_t)grp * g.grp_cap + c0;              // first row of the (stacked) output
-                        if (g.fuse == FUSE_SUM) gemm_tail_sum(outp, (size_t)g.split_stride, g.ldo, ksplit, orow0, ncol, row, live);
-                        else if (g.fuse == FUSE_SILU)
-                            gemm_tail_silu(outp, (size_t)g.split_stride, g.ldo, ksplit, orow0, ncol, row, live, pair_live, lane, g.act_hi, g.act_lo, g.act_ld);
-                        else gemm_tail_qkv(outp, (size_t)g.split_stride, g.ldo, ksplit, c0, ncol, row, live, pair_live, lane, &g.qkv);
-                    }
-                }
-            }
         }
     }
     tc_fence_before();

@@ -94,9 +94,7 @@ struct DenseWs {
     DevBuf<float> comb;              // [ep sources][rows, H] expert outputs returned to this rank
     DevBuf<float> part_acc, part_ml;
     DevBuf<int> counters;
-    DevBuf<int> tile_ctr;            // [kTileCtrs] k-slice arrival tickets of the fused GEMM tails (zero between launches)
 };
-constexpr int kTileCtrs = 8192;
 
 struct GraphKey {
     int b;

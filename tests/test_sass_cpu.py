@@ -59,17 +59,14 @@ def test_spills_only_where_known():
     assert len(res) >= 90
     names = sorted(res)
     spilled = {p for n, p in zip(names, sass_summary.demangle(names)) if res[n][2] or res[n][3]}
-    # (gemm_tc_kernel<BN, 7, 2> = the opt-in fused-tail variant FL_FUSE=1: its out-of-line tails cost a few caller-saved registers;
-    #  gemm_tc_kernel<BN >= 32, 5, 2> = the swap-AB decode GEMM: an 18-warp CTA leaves 96 registers per thread and the hi|lo accumulator
-    #  read-out spills two of them (8 bytes) outside the k loop -- measured: no effect on the GEMM's time)
+    # (gemm_tc_kernel<BN >= 32, 5, 2> = the swap-AB decode GEMM: an 18-warp CTA leaves 96 registers per thread and the hi|lo accumulator
+    #  read-out may spill two of them (<= 16 bytes) outside the k loop -- measured: no effect on the GEMM's time)
     def tolerated(p, n):
-        if p.startswith("decode_persistent_kernel<") or p.startswith("gemv_kernel<2, 5,") or p.startswith("gemm_tail_"):
-            return True
-        if p.startswith("gemm_tc_kernel<") and ", 7, 2>" in p:
+        if p.startswith("decode_persistent_kernel<") or p.startswith("gemv_kernel<2, 5,"):
             return True
         return p.startswith("gemm_tc_kernel<") and ", 5, 2>" in p and res[n][2] <= 16 and res[n][3] <= 16
     unexpected = {p for n, p in zip(names, sass_summary.demangle(names)) if (res[n][2] or res[n][3]) and not tolerated(p, n)}
     assert not unexpected, unexpected
     for n, p in zip(names, sass_summary.demangle(names)):
-        if (p.startswith("gemm_tc_kernel<") and ", 7, 2>" not in p and ", 5, 2>" not in p) or p.startswith("attn_"):
+        if (p.startswith("gemm_tc_kernel<") and ", 5, 2>" not in p) or p.startswith("attn_"):
             assert res[n][2] == 0 and res[n][3] == 0, p
