@@ -61,6 +61,7 @@ SYMBOLS = {
     "fl_forward_slots": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP]),
     "fl_cache_slot_reset": (_I, [_VP, _I]),
     "fl_cache_slot_len": (_I, [_VP, _I, C.POINTER(_I)]),
+    "fl_cache_moe_routing": (_I, [_VP, _I, _VP, _VP]),
     "fl_forward_sample_device": (_I, [_VP, _VP, _VP, _I, _I, _SZ, _VP, C.POINTER(C.c_uint32)]),
     "fl_embed": (_I, [_VP, _VP, _VP, _I, _I, _VP]),
     "fl_embed_timed": (_I, [_VP, _VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_float)]),

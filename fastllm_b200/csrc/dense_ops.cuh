@@ -204,7 +204,8 @@ static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int 
 // take top_k, renormalise by their sum; route_w[row][e] = weight or 0.  One CTA per row, one WARP per expert (128-bit loads,
 // one shuffle reduction each): the eight dot products of a Mixtral row run side by side instead of as eight block reductions.
 static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* __restrict__ xhi, const uint16_t* __restrict__ xlo, int H,
-                                                                const float* __restrict__ wgate, int E, int top_k, float* __restrict__ route_w) {
+                                                                const float* __restrict__ wgate, int E, int top_k, float* __restrict__ route_w,
+                                                                int* __restrict__ sel_log, float* __restrict__ margin_log) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float logit[64];
@@ -246,6 +247,15 @@ static __global__ void __launch_bounds__(256) moe_router_kernel(const uint16_t* 
             picked_sum += logit[best];                               // sum::<f32>() in rank order
         }
         for (int k = 0; k < top_k; ++k) rw[picked[k]] = logit[picked[k]] / picked_sum;
+        // routing record for the sharded-vs-single-GPU checks (fl_cache_moe_routing): the picked experts in rank order and how far
+        // the last pick was from not being picked (softmax-probability gap to the best expert left out)
+        if (sel_log != nullptr) {
+            float next = -INFINITY;
+            for (int e = 0; e < E; ++e)
+                if (!((taken >> e) & 1ull)) next = fmaxf(next, logit[e]);
+            for (int k = 0; k < top_k; ++k) sel_log[(size_t)row * top_k + k] = picked[k];
+            margin_log[row] = logit[picked[top_k - 1]] - next;
+        }
     }
 }
 

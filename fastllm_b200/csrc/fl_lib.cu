@@ -977,6 +977,7 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
         d.gx_hi.alloc(Rg * w.H, true); d.gx_lo.alloc(Rg * w.H, true);
         d.grp_cnt.alloc(w.E_local, true); d.grp_pos.alloc(Rm * w.E_local);
         d.moe_out.alloc(Rm * w.H); d.route_w.alloc(R * w.E);
+        d.route_sel.alloc((size_t)w.L * R * w.top_k, true); d.route_margin.alloc((size_t)w.L * R, true);
         if (w.ep_dp) {
             d.g_xhi.alloc(Rm * w.H); d.g_xlo.alloc(Rm * w.H); d.g_route.alloc(Rm * w.E);
             d.comb.alloc(Rm * w.H);
@@ -1204,7 +1205,7 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
             // experts, or (prefill, > 128 rows) stream every local expert over all rows with the routing weight as a mask (zero
             // when not selected).  No host sync either way, and a fixed summation order (experts ascending).
             launch(lc, "moe_router", 0, moe_router_kernel, dim3(R), dim3(256), 0, (const uint16_t*)d.xhi.p, (const uint16_t*)d.xlo.p, w.H,
-                   (const float*)lw.wgate, w.E, w.top_k, d.route_w.p);
+                   (const float*)lw.wgate, w.E, w.top_k, d.route_w.p, d.route_sel.p + (size_t)l * R * w.top_k, d.route_margin.p + (size_t)l * R);
             // expert parallelism with data-parallel attention: DISPATCH -- this rank's rows (hi/lo halves + routing weights)
             // travel to the expert ranks, which then see the rows of all ranks in rank-major order
             const int Rm = w.ep_dp ? R * w.ep : R;
@@ -1343,6 +1344,7 @@ static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t r
     set_state_kernel<<<1, 1, 0, c.stream>>>(c.state.p, (int)rope_offset);
     g_launches.fetch_add(1);
     const bool use_graph = (t == 1) && !g_prof.on && !env_flag("FL_NO_GRAPH");
+    c.dw.route_rows = b * t;
     if (b == 1 && t == 1 && c.pk.ok) {
         launch_persistent(c, 1, false);
     } else if (use_graph) {
@@ -1381,6 +1383,7 @@ static void run_forward_slots(fl_cache& c, const int* slots, const uint32_t* ids
     }
     for (int i = 0; i < n * t; ++i) FL_CHECK(ids[i] < (uint32_t)w.Vfull, FL_ERR_INVALID, "token id out of range");
     ensure_dense_ws(c, n * t);
+    c.dw.route_rows = n * t;
     c.slots_used = true;
     std::memcpy(c.h_ids.p, ids, (size_t)n * t * 4);
     for (int i = 0; i < n; ++i) {
@@ -1598,6 +1601,19 @@ FL_EXPORT int fl_cache_slot_len(fl_cache* c, int slot, int* out) {
     FL_CHECK(c && out, FL_ERR_INVALID, "NULL argument");
     FL_CHECK(slot >= 0 && slot < c->max_batch, FL_ERR_INVALID, "slot index out of range");
     *out = c->slot_len[slot];
+    FL_API_END
+}
+
+FL_EXPORT int fl_cache_moe_routing(fl_cache* c, int rows, int32_t* experts, float* margins) {
+    FL_API_BEGIN
+    FL_CHECK(c && experts && margins, FL_ERR_INVALID, "NULL argument");
+    const Weights& w = *c->w;
+    FL_CHECK(w.cfg.arch == FL_ARCH_MIXTRAL, FL_ERR_UNSUPPORTED, "routing records exist for the MoE architecture only");
+    FL_CHECK(!c->poisoned, FL_ERR_CUDA, "cache poisoned by an earlier CUDA error");
+    FL_CHECK(rows >= 1 && rows == c->dw.route_rows, FL_ERR_INVALID, "rows must equal batch x t of the last forward on this cache");
+    FL_CUDA(cudaStreamSynchronize(c->stream));
+    FL_CUDA(cudaMemcpy(experts, c->dw.route_sel.p, (size_t)w.L * rows * w.top_k * 4, cudaMemcpyDeviceToHost));
+    FL_CUDA(cudaMemcpy(margins, c->dw.route_margin.p, (size_t)w.L * rows * 4, cudaMemcpyDeviceToHost));
     FL_API_END
 }
 

@@ -83,6 +83,9 @@ struct DenseWs {
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
     DevBuf<float> moe_out, route_w;
+    DevBuf<int> route_sel;          // [L][rows of the call][top_k] picked experts of the last forward (fl_cache_moe_routing)
+    DevBuf<float> route_margin;     // [L][rows of the call]
+    int route_rows = 0;             // rows of the last Mixtral forward
     // grouped expert GEMMs (decode batches): per-expert blocks of gathered rows, their counts, and the row -> slot map
     int grp_cap = 0;                 // rows per expert block (the GEMM's N tile: 16 / 32 / 64 / 128)
     DevBuf<uint16_t> gx_hi, gx_lo;   // [E_local * grp_cap, H]

@@ -169,6 +169,14 @@ class DeviceCache:
         _lib.check(self.lib.fl_cache_slot_len(self.h, slot, C.byref(n)))
         return n.value
 
+    def moe_routing(self, rows: int):
+        """Router decisions of the last forward (Mixtral): experts [layers, rows, top_k] int32 in pick order, margins [layers, rows] f32."""
+        cfg = self.model.cfg
+        ex = np.empty((cfg.num_hidden_layers, rows, cfg.num_experts_per_tok), dtype=np.int32)
+        mg = np.empty((cfg.num_hidden_layers, rows), dtype=np.float32)
+        _lib.check(self.lib.fl_cache_moe_routing(self.h, rows, ex.ctypes.data_as(C.c_void_p), mg.ctypes.data_as(C.c_void_p)))
+        return ex, mg
+
     def decode_greedy_loop(self, first_ids: np.ndarray, rope_offset: int, steps: int):
         first = np.ascontiguousarray(first_ids, dtype=np.uint32).reshape(-1)
         b = first.shape[0]

@@ -148,6 +148,14 @@ FL_EXPORT int fl_forward_slots(fl_model* m, fl_cache* c, const int* slots, const
 FL_EXPORT int fl_cache_slot_reset(fl_cache* c, int slot);        /* the slot's sequence is finished: length := 0 */
 FL_EXPORT int fl_cache_slot_len(fl_cache* c, int slot, int* out);
 
+/* Diagnostics (no reference counterpart): the router's decisions in the LAST forward on this cache (Mixtral only) -- experts
+ * [layers][rows][num_experts_per_tok] in pick order (MixtralSparseMoeBlock's sort, models/mixtral.rs via candle-transformers) and
+ * margins [layers][rows] = softmax-probability gap between the last picked expert and the best one left out; rows = batch x t of
+ * that forward.  top-k routing is discontinuous: a sharded run whose hidden state differs in the last f32 bits can pick another
+ * expert where the margin is ~0, so the sharded-vs-single-GPU checks (bench.py, tests/test_tp.py) compare logits only where the
+ * routing agrees and require every disagreement to sit on such a near-tie. */
+FL_EXPORT int fl_cache_moe_routing(fl_cache* c, int rows, int32_t* experts, float* margins);
+
 /* ---- sampling (host arithmetic: the reference samples on the host from every forward's logits) --- */
 /* LogitsProcessor::new(seed, Some(temperature), None): temperature < 1e-7 => arg-max (IEEE total order, LAST index among
  * equal maxima); otherwise softmax(logits * (1/T as f32)) with a sequential f32 denominator, then

@@ -36,11 +36,16 @@ def route_top_k(router_logits: np.ndarray, top_k: int = 2):
     return idx, wts
 
 
+ROUTING_LOG = None      # tests set this to a list to record the router's picks (checked against fl_cache_moe_routing)
+
+
 def sparse_moe_block(x: np.ndarray, w_gate: np.ndarray, experts, top_k: int = 2) -> np.ndarray:
     """x [b, t, H]; experts = [(w1 [I,H], w2 [H,I], w3 [I,H]), ...]."""
     b, t, H = x.shape
     xs = x.reshape(-1, H).astype(F32)
     idx, wts = route_top_k(ops.linear(xs, w_gate), top_k)
+    if ROUTING_LOG is not None:
+        ROUTING_LOG.append(idx.copy())                            # one [rows, top_k] entry per MoE block call, in layer order
     out = np.zeros_like(xs)
     for e, (w1, w2, w3) in enumerate(experts):
         rows, slot = np.nonzero(idx == e)

@@ -61,3 +61,36 @@ def test_reference_arm_times_whole_steps_with_every_core_under_a_launcher_that_p
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tinyllama_b1", "--gpus", "2"],
                         capture_output=True, text=True, timeout=120, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_compare_sharded_counts_rows_only_while_routing_agrees():
+    """bench.compare_sharded with router records: a sequence rerouted on a near-tie leaves the comparison from that step on; a
+    disagreement off a tie, or a large error in a row that was routed identically, fails the check."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(0)
+    steps, b, L, k, V = 4, 3, 2, 2, 50
+    want = rng.standard_normal((steps, b, V)).astype(np.float32)
+    sel = [np.tile(np.array([1, 4], dtype=np.int32), (b, 1, L, 1)) for _ in range(steps)]
+    mar = [np.full((b, 1, L), 0.2, dtype=np.float32) for _ in range(steps)]
+    got = want + 1e-3
+    ok = bench.compare_sharded(got, want, "x", routing=([x.copy() for x in sel], sel, mar))
+    assert ok["greedy32"] and ok["router_disagreements"] == 0 and ok["rows_compared"] == steps * b
+    # sequence 1 reroutes at step 2 on a near-tie: its rows 2.. may differ by anything, [4, 1] vs [1, 4] is the same set
+    sel_g = [x.copy() for x in sel]
+    sel_g[2][1, 0, 1] = [1, 6]
+    sel_g[0][0, 0, 0] = [4, 1]
+    mar2 = [x.copy() for x in mar]
+    mar2[2][1, 0, 1] = 2e-5
+    got2 = got.copy()
+    got2[2:, 1] += 1.5
+    r = bench.compare_sharded(got2, want, "x", routing=(sel_g, sel, mar2))
+    assert r["greedy32"] and r["router_disagreements"] == 1 and r["rows_compared"] == steps * b - 2 and r["max_abs_all_rows"] > 1
+    # the same disagreement with a wide margin is a defect
+    assert not bench.compare_sharded(got2, want, "x", routing=(sel_g, sel, mar))["greedy32"]
+    # a large error where the routing agreed is a defect
+    got3 = got.copy()
+    got3[1, 0] += 0.5
+    assert not bench.compare_sharded(got3, want, "x", routing=([x.copy() for x in sel], sel, mar))["greedy32"]
+    assert not bench.compare_sharded(got3, want, "x")["greedy32"] and bench.compare_sharded(got, want, "x")["greedy32"]

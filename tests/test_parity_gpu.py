@@ -267,6 +267,37 @@ def test_tensor_core_attention_long_context(name, b, t, steps):
     assert max(errs) <= KERNEL_TOL
 
 
+def test_moe_routing_record_equals_the_oracle_router():
+    """fl_cache_moe_routing (the diagnostics the sharded-vs-single-GPU checks lean on): the router's picks of a prefill and of a
+    decode step equal the oracle's `route_top_k` picks wherever the recorded margin is not a near-tie, in pick order; margins are
+    non-negative; a wrong row count is an error."""
+    from fastllm_b200 import models
+    from fastllm_b200._lib import FastllmError
+    from oracle import mixtral as omx
+    cfg, w, g = golden_weights("mixtral")
+    model, _ = product_model(cfg, w)
+    prompts = synth.token_ids(5, cfg.vocab_size, (3, 10))
+    oracle = ocl.CausalLM(cfg, w, kv_dtype="bf16")
+    cache = models.DeviceCache(model.dev, 3, 64)
+    nxt = np.array([[7], [9], [11]], dtype=np.uint32)
+    for ids, pos in ((prompts, 0), (nxt, 10)):
+        omx.ROUTING_LOG = []
+        try:
+            oracle.forward(ids, pos)
+            want = np.stack(omx.ROUTING_LOG)                       # [L, rows, k]
+        finally:
+            omx.ROUTING_LOG = None
+        cache.forward(ids, pos)
+        got, margins = cache.moe_routing(ids.size)
+        assert got.shape == want.shape and margins.shape == want.shape[:2]
+        assert (margins >= 0).all() and (got >= 0).all() and (got < cfg.num_local_experts).all()
+        clear = margins > 1e-3
+        assert clear.mean() > 0.9
+        assert np.array_equal(got[clear], want[clear])
+    with pytest.raises(FastllmError):
+        cache.moe_routing(2)
+
+
 def test_mixtral_masked_prefill_and_grouped_decode_agree(monkeypatch):
     """The MoE block has two execution plans: calls with more than 128 expert rows (prefill) stream every expert over all rows
     with the routing weight as a mask; decode batches gather per-expert row lists and run ONE grouped GEMM pair.  A 150-row
