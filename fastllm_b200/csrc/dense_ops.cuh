@@ -141,8 +141,11 @@ struct QkvEpiArgs {
 
 // bias + RoPE (rotate-half) + q store + paged KV append; thread per column pair, grid.y = row
 static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
-    pdl_launch_dependents();
+    // the dependent (attention) kernel is released only AFTER this kernel's own wait: when it starts, the q|k|v GEMM -- and by
+    // induction every earlier kernel of the stream -- has completed, so its preamble may read the step state, the page table and
+    // every K/V page except the rows appended here before its own griddepcontrol.wait (attn_sk_decode_kernel streams them early)
     pdl_wait();
+    pdl_launch_dependents();
     const int row = blockIdx.y;
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair * 2 >= a.nqkv) return;

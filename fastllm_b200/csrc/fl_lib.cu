@@ -119,30 +119,77 @@ static void launch_attn(LaunchCtx& lc, int d, int nsplit, int nkv, int rows, siz
 
 // tensor-core attention of the dense path (attn_mma.cuh): batched decode (one CTA per split x kv head x sequence) or prefill
 // (one CTA per 64-query tile x q head x sequence)
-static size_t attn_mma_smem_bytes(int d, bool decode) {
-    return (size_t)((decode ? 32 + 2 * kDecStages * kKvPage : 2 * kPrefillBM + 4 * kKvPage)) * d * 2;
+static size_t attn_prefill_smem_bytes(int d) {
+    return (size_t)(2 * kPrefillBM + 4 * kKvPage) * d * 2;
+}
+
+// stream-K batched decode (attn_sk_decode_kernel): q tiles / merge scratch in front, then the K|V ring
+static size_t attn_sk_smem_bytes(int d, int n_rep, int stages) {
+    const size_t front = std::max<size_t>((size_t)2 * 16 * d * 2, (size_t)kSkConsumerWarps * n_rep * d * 4);
+    return ((front + 1023) & ~(size_t)1023) + (size_t)stages * 2 * kKvPage * d * 2;
+}
+struct SkPlan { int stages = 0, ctas = 0; size_t smem = 0; };
+// ring depth and resident CTAs per SM: 2 stages x 3 CTAs (the runtime's occupancy answer caps the CTAs).  Measured on Mistral-7B
+// at 2k context: batch 64 is the same with 3 stages x 2 CTAs (6.83 vs 6.84 ms/step), batch 8 is better with more, smaller ranges
+// (4.07 vs 4.17 ms/step); 4 stages x 1 CTA loses 14 %.  FL_ATTN_SK_STAGES / FL_ATTN_SK_CTAS override (dev knobs).
+template <int D>
+static SkPlan attn_sk_plan_d(int n_rep) {
+    static const int env_st = std::getenv("FL_ATTN_SK_STAGES") ? std::atoi(std::getenv("FL_ATTN_SK_STAGES")) : 0;
+    static const int env_ct = std::getenv("FL_ATTN_SK_CTAS") ? std::atoi(std::getenv("FL_ATTN_SK_CTAS")) : 0;
+    static std::map<int, SkPlan> memo;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = memo.find(n_rep);
+    if (it != memo.end()) return it->second;
+    auto fit = [&](int st) {
+        int n = 0;
+        FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_sk_decode_kernel<D>, kSkThreads, attn_sk_smem_bytes(D, n_rep, st)));
+        return n;
+    };
+    SkPlan p;
+    p.stages = env_st >= 1 && env_st <= kSkMaxStages ? env_st : 2;
+    p.ctas = std::min(3, fit(p.stages));
+    if (env_ct >= 1) p.ctas = std::min(p.ctas, env_ct);
+    FL_CHECK(p.ctas >= 1, FL_ERR_UNSUPPORTED, "stream-K attention does not fit an SM");
+    p.smem = attn_sk_smem_bytes(D, n_rep, p.stages);
+    memo[n_rep] = p;
+    return p;
+}
+static SkPlan attn_sk_plan(int d, int n_rep) {
+    switch (d) {
+        case 16: return attn_sk_plan_d<16>(n_rep);
+        case 32: return attn_sk_plan_d<32>(n_rep);
+        case 64: return attn_sk_plan_d<64>(n_rep);
+        case 128: return attn_sk_plan_d<128>(n_rep);
+        default: throw Error(FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
+    }
+}
+static void launch_attn_sk(LaunchCtx& lc, int d, const SkPlan& pl, uint64_t bytes, const CUtensorMap& tmk, const CUtensorMap& tmv, const SkArgs& k) {
+    const dim3 g(pl.ctas * kNumSMs), b(kSkThreads);
+    switch (d) {
+        case 16: launch(lc, "attn_sk_decode", bytes, attn_sk_decode_kernel<16>, g, b, pl.smem, tmk, tmv, k); break;
+        case 32: launch(lc, "attn_sk_decode", bytes, attn_sk_decode_kernel<32>, g, b, pl.smem, tmk, tmv, k); break;
+        case 64: launch(lc, "attn_sk_decode", bytes, attn_sk_decode_kernel<64>, g, b, pl.smem, tmk, tmv, k); break;
+        default: launch(lc, "attn_sk_decode", bytes, attn_sk_decode_kernel<128>, g, b, pl.smem, tmk, tmv, k); break;
+    }
 }
 
 template <int D>
 static void attn_mma_set_attrs() {
-    FL_CUDA(cudaFuncSetAttribute(attn_gqa_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_mma_smem_bytes(D, true)));
-    FL_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_mma_smem_bytes(D, false)));
+    FL_CUDA(cudaFuncSetAttribute(attn_sk_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FL_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_prefill_smem_bytes(D)));
 }
 
-static void launch_attn_mma(LaunchCtx& lc, int d, bool decode, dim3 g, uint64_t bytes, const AttnArgs& a) {
-    const size_t smem = attn_mma_smem_bytes(d, decode);
+static void launch_attn_prefill(LaunchCtx& lc, int d, dim3 g, uint64_t bytes, const AttnArgs& a) {
+    const size_t smem = attn_prefill_smem_bytes(d);
     const dim3 b(kMmaAttnThreads);
-    const char* tag = decode ? "attn_gqa_decode" : "attn_prefill";
-#define FL_ATTN_CASE(D)                                                             \
-    case D:                                                                         \
-        if (decode) launch(lc, tag, bytes, attn_gqa_decode_kernel<D>, g, b, smem, a); \
-        else launch(lc, tag, bytes, attn_prefill_kernel<D>, g, b, smem, a);         \
-        break;
     switch (d) {
-        FL_ATTN_CASE(16) FL_ATTN_CASE(32) FL_ATTN_CASE(64) FL_ATTN_CASE(128)
+        case 16: launch(lc, "attn_prefill", bytes, attn_prefill_kernel<16>, g, b, smem, a); break;
+        case 32: launch(lc, "attn_prefill", bytes, attn_prefill_kernel<32>, g, b, smem, a); break;
+        case 64: launch(lc, "attn_prefill", bytes, attn_prefill_kernel<64>, g, b, smem, a); break;
+        case 128: launch(lc, "attn_prefill", bytes, attn_prefill_kernel<128>, g, b, smem, a); break;
         default: throw Error(FL_ERR_UNSUPPORTED, "head_dim must be 16, 32, 64 or 128");
     }
-#undef FL_ATTN_CASE
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -741,6 +788,14 @@ static void cache_create(fl_cache& c, int max_batch, int max_seq) {
     c.layer_pool_elems = (size_t)max_batch * c.pages_per_seq * w.nkv * kKvPage * w.d;
     c.kpool.alloc(c.layer_pool_elems * w.L, true);
     c.vpool.alloc(c.layer_pool_elems * w.L, true);
+    {
+        const uint64_t rows = (uint64_t)c.layer_pool_elems / w.d * w.L;
+        c.kv_tmaps = rows < (1ull << 31) && (w.d == 16 || w.d == 32 || w.d == 64 || w.d == 128);
+        if (c.kv_tmaps) {
+            c.tm_kpool = make_tmap_kv(c.kpool.p, rows, (uint32_t)w.d);
+            c.tm_vpool = make_tmap_kv(c.vpool.p, rows, (uint32_t)w.d);
+        }
+    }
     int ns = (2 * kNumSMs + w.nkv * kPassRows - 1) / (w.nkv * kPassRows);
     if (ns > c.pages_per_seq) ns = c.pages_per_seq;
     if (ns < 1) ns = 1;
@@ -984,9 +1039,9 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
         }
     }
     d.chunk = std::min(rows, kMaxBatch);            // split partials of the batched-decode attention: one row per sequence
-    d.part_acc.alloc((size_t)d.chunk * w.nh * c.nsplit * w.d);
-    d.part_ml.alloc((size_t)d.chunk * w.nh * c.nsplit * 2);
     d.counters.alloc((size_t)d.chunk * w.nkv, true);
+    d.sk_acc.alloc((size_t)4 * kNumSMs * 2 * (w.nh / w.nkv) * w.d);
+    d.sk_ml.alloc((size_t)4 * kNumSMs * 2 * (w.nh / w.nkv) * 2);
     d.rows = R;
 }
 
@@ -1156,28 +1211,22 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
         {   // K7-K11 on tensor cores; the output lands as the hi/lo bf16 operands of the o_proj GEMM
             AttnArgs at{};
             at.q = d.q.p; at.kpool = kpool; at.vpool = vpool; at.page_table = c.page_table.p; at.pt_stride = c.pages_per_seq;
-            at.state = c.state.p; at.part_acc = d.part_acc.p; at.part_ml = d.part_ml.p; at.counters = d.counters.p;
+            at.state = c.state.p; at.counters = d.counters.p;
             at.out_hi = d.xhi.p; at.out_lo = d.xlo.p; at.nh = w.nh; at.nkv = w.nkv; at.t = t; at.row_base = 0;
             at.sliding_window = windowed ? w.cfg.sliding_window : 0; at.qscale = qscale;
             const uint64_t kv_bytes = (uint64_t)b * (c.kv_len + t) * w.nkv * w.d * 4;
             if (t == 1) {
-                // Few (sequence, kv head) pairs: ONE wave, as many splits as fit (every CTA pays the same load -> softmax -> merge
-                // latency chain once; a second, mostly empty wave would double it).  Many pairs: ~3 waves -- measured at batch 64:
-                // 3 / 4 / 6 / 8 / 12 waves = 112 / 113 / 124 / 131 / 157 us per layer, the per-CTA set-up and merge outweigh a shorter
-                // tail.  A split streams at least one 64-token page.
-                // The grid must NOT depend on the current KV length: this launch is captured into the step's CUDA graph, which is
-                // keyed by (batch, loop mode) only and replayed as the context grows (a serve flow captures at a one-page prompt
-                // and then decodes to thousands of tokens).  Splits beyond the last page are empty (p0 >= p1) and the merge skips
-                // them, so a fixed split count is correct at every length.
-                // resident CTAs per SM: bounded by the K|V page ring in shared memory (106 KB at head_dim 128: two CTAs)
-                const int cps = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)232448 / (attn_mma_smem_bytes(w.d, true) + 1024)));
-                const int pairs = b * w.nkv, slots = cps * kNumSMs;
-                static const int waves = std::getenv("FL_ATTN_WAVES") ? std::max(1, std::atoi(std::getenv("FL_ATTN_WAVES"))) : 3;   // dev knob
-                const int want = pairs <= slots ? slots / pairs : (waves * slots + pairs - 1) / pairs;
-                const int nsp = std::max(1, std::min(c.nsplit, want));
-                launch_attn_mma(lc, w.d, true, dim3(nsp, w.nkv, b), kv_bytes, at);
+                // stream-K: a fixed grid of resident CTAs, each an equal share of the step's page stream.  The grid does NOT depend
+                // on the KV length: this launch is captured into the step's CUDA graph, which is keyed by (batch, mode) only and
+                // replayed as the context grows.
+                FL_CHECK(c.kv_tmaps && w.nh / w.nkv <= 16, FL_ERR_UNSUPPORTED, "batched decode attention: GQA group > 16 heads or KV pool beyond 2^31 rows");
+                const SkPlan pl = attn_sk_plan(w.d, w.nh / w.nkv);
+                SkArgs sk{};
+                sk.a = at; sk.sk_acc = d.sk_acc.p; sk.sk_ml = d.sk_ml.p; sk.b = b; sk.nstages = pl.stages;
+                sk.layer_row0 = (int)((size_t)l * (c.layer_pool_elems / w.d));
+                launch_attn_sk(lc, w.d, pl, kv_bytes, c.tm_kpool, c.tm_vpool, sk);
             } else {
-                launch_attn_mma(lc, w.d, false, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
+                launch_attn_prefill(lc, w.d, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
             }
         }
         ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p);

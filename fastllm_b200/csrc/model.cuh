@@ -82,6 +82,7 @@ struct DenseWs {
     DevBuf<float> resid, q;
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
+    DevBuf<float> sk_acc, sk_ml;    // stream-K decode attention: [CTAs][2][n_rep][d] / [CTAs][2][n_rep][2] partials of shared pairs
     DevBuf<float> moe_out, route_w;
     DevBuf<int> route_sel;          // [L][rows of the call][top_k] picked experts of the last forward (fl_cache_moe_routing)
     DevBuf<float> route_margin;     // [L][rows of the call]
@@ -95,7 +96,7 @@ struct DenseWs {
     DevBuf<uint16_t> g_xhi, g_xlo;   // [ep * rows, H] gathered block inputs
     DevBuf<float> g_route;           // [ep * rows, E]
     DevBuf<float> comb;              // [ep sources][rows, H] expert outputs returned to this rank
-    DevBuf<float> part_acc, part_ml;
+    // (batched-decode attention partials: sk_acc / sk_ml above)
     DevBuf<int> counters;
 };
 
@@ -132,6 +133,8 @@ struct fl_cache {
     fl::DevBuf<int> page_table;           // [max_batch, pages_per_seq]
     fl::DevBuf<uint16_t> kpool, vpool;    // [L][pages][nkv][kKvPage][d]
     size_t layer_pool_elems = 0;
+    CUtensorMap tm_kpool{}, tm_vpool{};   // the pools as [rows, d] matrices (stream-K decode attention); valid when kv_tmaps
+    bool kv_tmaps = false;
     fl::DevBuf<uint32_t> ids, next_ids, trace;
     fl::DevBuf<int> trace_pos;
     fl::DevBuf<float> resid, q, attn_out, act, logits, part_acc, part_ml, amax_val;

@@ -44,9 +44,13 @@ def test_persistent_decode_kernel_streams_by_tma_into_tensor_cores(kernels):
 
 
 def test_attention_kernels_use_tensor_cores(kernels):
-    for prefix in ("attn_prefill_kernel<", "attn_gqa_decode_kernel<", "bert_attn_kernel"):
-        for name, c in _family(kernels, prefix).items():
+    for prefix in ("attn_prefill_kernel<", "attn_sk_decode_kernel<", "bert_attn_kernel"):
+        fam = _family(kernels, prefix)
+        assert fam, prefix
+        for name, c in fam.items():
             assert c["HMMA.16816.F32.BF16"] >= 8 and c["LDSM"] >= 4, name
+    for name, c in _family(kernels, "attn_sk_decode_kernel<").items():
+        assert c["UTMALDG.2D"] >= 2 and c["SYNCS"] >= 4, name      # K|V pages arrive by 2-D TMA, completion on mbarriers
 
 
 def test_spills_only_where_known():
