@@ -137,6 +137,8 @@ struct QkvEpiArgs {
     const float* rope_cos;
     const float* rope_sin;
     int nh, nkv, d, max_pos, t, nqkv;
+    uint16_t* vt;              // optional (prefill on the tcgen05 attention kernel): V of this call TRANSPOSED per 64-token page,
+    int vt_pages;              // [sequence][kv head][vt_pages][d][64 tokens] -- the K-major B operand of O += P . V
 };
 
 // bias + RoPE (rotate-half) + q store + paged KV append; thread per column pair, grid.y = row
@@ -176,6 +178,11 @@ static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
     } else {
         uint16_t* vp = a.vpool + (((size_t)page * a.nkv + (hh - a.nh - a.nkv)) * kKvPage + slot % kKvPage) * d;
         *reinterpret_cast<uint32_t*>(vp + 2 * j) = (uint32_t)f32_to_bf16_rne(va) | ((uint32_t)f32_to_bf16_rne(vb) << 16);
+        if (a.vt != nullptr) {
+            uint16_t* tp = a.vt + ((((size_t)seq * a.nkv + (hh - a.nh - a.nkv)) * a.vt_pages + irel / kKvPage) * d + 2 * j) * kKvPage + irel % kKvPage;
+            tp[0] = f32_to_bf16_rne(va);
+            tp[kKvPage] = f32_to_bf16_rne(vb);
+        }
     }
 }
 

@@ -177,6 +177,8 @@ static void launch_attn_sk(LaunchCtx& lc, int d, const SkPlan& pl, uint64_t byte
 template <int D>
 static void attn_mma_set_attrs() {
     FL_CUDA(cudaFuncSetAttribute(attn_sk_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if constexpr (D == 64 || D == 128)
+        FL_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_prefill_tc_smem_bytes(D)));
     FL_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_prefill_smem_bytes(D)));
 }
 
@@ -1042,6 +1044,12 @@ static void ensure_dense_ws(fl_cache& c, int rows) {
     d.counters.alloc((size_t)d.chunk * w.nkv, true);
     d.sk_acc.alloc((size_t)4 * kNumSMs * 2 * (w.nh / w.nkv) * w.d);
     d.sk_ml.alloc((size_t)4 * kNumSMs * 2 * (w.nh / w.nkv) * 2);
+    d.vt_pages_cap = 0;
+    if ((w.d == 64 || w.d == 128) && R > (size_t)kKvPage) {
+        d.vt_pages_cap = R / kKvPage + std::min<size_t>(R, kMaxBatch);
+        d.vt.alloc(d.vt_pages_cap * w.nkv * w.d * kKvPage, true);        // zero: the last page's tail multiplies P = 0 and must stay finite
+        d.tm_vt = make_tmap_bf16(d.vt.p, d.vt_pages_cap * w.nkv * w.d, kKvPage, kKvPage, (uint32_t)w.d);
+    }
     d.rows = R;
 }
 
@@ -1189,6 +1197,12 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
     const float qscale = (float)(1.0 / std::sqrt((double)w.d));
     const bool windowed = (w.cfg.arch != FL_ARCH_LLAMA) && w.cfg.sliding_window > 0 && t > 1;
     const size_t attn_smem = attn_smem_bytes(w.d, w.nh / w.nkv);
+    // multi-token calls on empty sequences with head_dim 64 / 128 and more than one page of keys: attention on tcgen05
+    // (attn_prefill_tc_kernel; FL_ATTN_PREFILL_MMA=1 keeps the mma.sync kernel, the A/B knob)
+    const int vt_pages = (t + kKvPage - 1) / kKvPage;
+    const bool prefill_mma = env_flag("FL_ATTN_PREFILL_MMA");
+    const bool tc_prefill = t > kKvPage && (w.d == 64 || w.d == 128) && c.kv_tmaps && c.fresh_call && !prefill_mma &&
+                            (size_t)b * vt_pages <= d.vt_pages_cap;
 
     auto prep = [&](const char* tag, PrepArgs pa, int rows_out) {
         pa.xhi = d.xhi.p; pa.xlo = d.xlo.p; pa.eps = w.cfg.norm_eps; pa.t = t;
@@ -1206,7 +1220,7 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
         uint16_t* vpool = c.vpool.p + (size_t)l * c.layer_pool_elems;
         int ks = dense_gemm(c, lc, "gemm_tc_qkv", R, w.nqkv, w.H, lw.tm_wqkv, d.y.p);
         QkvEpiArgs qa{ks, (long long)R * w.nqkv, d.y.p, lw.bqkv, d.q.p, kpool, vpool, c.page_table.p, c.pages_per_seq, c.state.p, w.rope_cos,
-                      w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t, w.nqkv};
+                      w.rope_sin, w.nh, w.nkv, w.d, w.max_pos, t, w.nqkv, tc_prefill ? d.vt.p : nullptr, vt_pages};
         launch(lc, "dense_qkv_rope_append", 0, dense_qkv_epi_kernel, dim3((w.nqkv / 2 + 255) / 256, R), dim3(256), 0, qa);
         {   // K7-K11 on tensor cores; the output lands as the hi/lo bf16 operands of the o_proj GEMM
             AttnArgs at{};
@@ -1226,7 +1240,16 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
                 sk.layer_row0 = (int)((size_t)l * (c.layer_pool_elems / w.d));
                 launch_attn_sk(lc, w.d, pl, kv_bytes, c.tm_kpool, c.tm_vpool, sk);
             } else {
-                launch_attn_prefill(lc, w.d, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
+                if (tc_prefill) {
+                    TcPrefillArgs tp{};
+                    tp.a = at; tp.layer_row0 = (int)((size_t)l * (c.layer_pool_elems / w.d)); tp.vt_pages = vt_pages;
+                    tp.tau = std::getenv("FL_ATTN_TC_TAU") ? (float)std::atof(std::getenv("FL_ATTN_TC_TAU")) : 8.f;      // 0: O is rescaled on every new row max (tests)
+                    const dim3 g((t + kTcQ - 1) / kTcQ, w.nh, b), blk(kTcThreads);
+                    if (w.d == 64) launch(lc, "attn_prefill_tc", kv_bytes, attn_prefill_tc_kernel<64>, g, blk, attn_prefill_tc_smem_bytes(64), c.tm_kpool, d.tm_vt, tp);
+                    else launch(lc, "attn_prefill_tc", kv_bytes, attn_prefill_tc_kernel<128>, g, blk, attn_prefill_tc_smem_bytes(128), c.tm_kpool, d.tm_vt, tp);
+                } else {
+                    launch_attn_prefill(lc, w.d, dim3((t + kPrefillBM - 1) / kPrefillBM, w.nh, b), kv_bytes, at);
+                }
             }
         }
         ks = dense_gemm(c, lc, "gemm_tc_o", R, w.H, nq, lw.tm_wo, d.y.p);
@@ -1394,6 +1417,7 @@ static void run_forward(fl_cache& c, const uint32_t* ids, int b, int t, size_t r
     g_launches.fetch_add(1);
     const bool use_graph = (t == 1) && !g_prof.on && !env_flag("FL_NO_GRAPH");
     c.dw.route_rows = b * t;
+    c.fresh_call = c.kv_len == 0 && !c.slots_used;
     if (b == 1 && t == 1 && c.pk.ok) {
         launch_persistent(c, 1, false);
     } else if (use_graph) {
@@ -1433,6 +1457,8 @@ static void run_forward_slots(fl_cache& c, const int* slots, const uint32_t* ids
     for (int i = 0; i < n * t; ++i) FL_CHECK(ids[i] < (uint32_t)w.Vfull, FL_ERR_INVALID, "token id out of range");
     ensure_dense_ws(c, n * t);
     c.dw.route_rows = n * t;
+    c.fresh_call = true;
+    for (int i = 0; i < n; ++i) c.fresh_call = c.fresh_call && c.slot_len[slots[i]] == 0;
     c.slots_used = true;
     std::memcpy(c.h_ids.p, ids, (size_t)n * t * 4);
     for (int i = 0; i < n; ++i) {

@@ -82,6 +82,9 @@ struct DenseWs {
     DevBuf<float> resid, q;
     DevBuf<float> tp_buf;       // [rows, H] reduced partial sums awaiting the all-reduce (tp > 1)
     DevBuf<uint16_t> xhi2, xlo2; // Mixtral: expert activations (the block input xhi/xlo is shared by all experts)
+    DevBuf<uint16_t> vt;            // V of the current multi-token call transposed per page: [seq][kv head][page][d][64] (tcgen05 prefill attention)
+    size_t vt_pages_cap = 0;        // pages the scratch holds (over all sequences of a call)
+    CUtensorMap tm_vt{};
     DevBuf<float> sk_acc, sk_ml;    // stream-K decode attention: [CTAs][2][n_rep][d] / [CTAs][2][n_rep][2] partials of shared pairs
     DevBuf<float> moe_out, route_w;
     DevBuf<int> route_sel;          // [L][rows of the call][top_k] picked experts of the last forward (fl_cache_moe_routing)
@@ -135,6 +138,7 @@ struct fl_cache {
     size_t layer_pool_elems = 0;
     CUtensorMap tm_kpool{}, tm_vpool{};   // the pools as [rows, d] matrices (stream-K decode attention); valid when kv_tmaps
     bool kv_tmaps = false;
+    bool fresh_call = false;              // the forward being enqueued starts on empty sequences (every row's KV length is 0)
     fl::DevBuf<uint32_t> ids, next_ids, trace;
     fl::DevBuf<int> trace_pos;
     fl::DevBuf<float> resid, q, attn_out, act, logits, part_acc, part_ml, amax_val;

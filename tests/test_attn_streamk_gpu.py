@@ -2,7 +2,8 @@
 stream into equal ranges, so a (sequence, kv head) pair may lie inside one CTA's range, start in one and end in the next, or span
 many.  These cases need MORE pages than resident CTAs (296-444), which the tiny parity configs never reach: here 96-192 ragged
 sequences of 1 .. 15 pages decode together, at head dims 32 (unswizzled box), 64 and 128 (one / two swizzled TMA boxes per page).
-Every row against a per-sequence oracle with the same bf16 KV rounding (8f-3)."""
+The prompts (up to 960 tokens, prefilled on empty slots) also run the tcgen05 prefill attention (attn_prefill_tc_kernel: head dims 64 /
+128, several 128-query tiles, a 100-token sliding window in one case).  Every row against a per-sequence oracle with the same bf16 KV rounding (8f-3)."""
 import numpy as np
 import pytest
 
@@ -17,13 +18,22 @@ CASES = {
     # name: (config, sequences, lengths cycled over the sequences)
     "d32_gqa2": (ocl.CausalLMConfig("mistral", 128, 224, 320, 2, 4, 2, 1e-5, 1e4, 1024, 4096), 120, [20, 64, 65, 700, 130, 900, 1, 333]),
     "d64_gqa2": (ocl.CausalLMConfig("llama", 256, 352, 384, 2, 4, 2, 1e-5, 1e4, 1024), 96, [900, 3, 64, 129, 500, 65]),
+    "d64_window": (ocl.CausalLMConfig("mistral", 256, 352, 384, 2, 4, 2, 1e-5, 1e4, 1024, 100), 96, [900, 3, 64, 129, 500, 65]),
     "d128_gqa4": (ocl.CausalLMConfig("qwen2", 512, 704, 384, 2, 4, 1, 1e-6, 1e6, 1024, 4096, qkv_bias=True), 192, [64, 777, 5, 130, 960, 33]),
 }
 
 
-@pytest.mark.parametrize("name", list(CASES))
-def test_stream_k_decode_attention_over_more_pages_than_ctas(name):
+@pytest.mark.parametrize("name", list(CASES) + ["d128_gqa4/tau0", "d64_window/mma"])
+def test_stream_k_decode_attention_over_more_pages_than_ctas(name, monkeypatch):
     from fastllm_b200 import models
+    # the tcgen05 prefill kernel moves a row's exponent offset lazily (O in TMEM is rescaled only on a jump of > 2^8, which random
+    # weights never produce): FL_ATTN_TC_TAU=0 rescales on every new row max, so that path is covered too; FL_ATTN_PREFILL_MMA=1
+    # keeps the mma.sync prefill kernel (the path of calls on non-empty caches) on the same inputs
+    name, _, variant = name.partition("/")
+    if variant == "tau0":
+        monkeypatch.setenv("FL_ATTN_TC_TAU", "0")
+    if variant == "mma":
+        monkeypatch.setenv("FL_ATTN_PREFILL_MMA", "1")
     cfg, nseq, cycle = CASES[name]
     w = ocl.synth_weights(cfg, 29, 0.06)
     model, _ = product_model(cfg, w)
