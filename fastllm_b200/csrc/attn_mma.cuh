@@ -594,12 +594,12 @@ __global__ void __launch_bounds__(kMmaAttnThreads) attn_prefill_kernel(const Att
 //               for this call ([d][64 keys]: K-major, so O += P.V is the same operand form as every GEMM of the library);
 //   warp 1      allocates TMEM (S double-buffered 2 x 64 columns, O d columns), one thread issues S = Q.K^T (q = hi + lo: two
 //               accumulating MMA groups against the same K tile) and, one tile behind, O += P.V (P = hi + lo likewise);
-//   warps 2-5   softmax: thread == query row (tcgen05.ld 32x32b), scale / causal + window mask / running max and sum in the
+//   warps 2-9   softmax: thread == query row and half of a page's keys (tcgen05.ld 32x32b), scale / causal + window mask / running max and sum in the
 //               exp2 domain, P written hi | lo into shared memory in the swizzled operand layout; when a row's max moved, the warp
 //               rescales its 32 TMEM lanes of O in place (tcgen05.ld / st) after the previous P.V has completed.
 // Same arithmetic contract as attn_prefill_kernel (f32 scores and probabilities carried as hi + lo bf16 pairs, f32 accumulation).
 constexpr int kTcQ = 128;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 352;
 
 struct TcPrefillArgs {
     AttnArgs a;
@@ -608,9 +608,16 @@ struct TcPrefillArgs {
     float tau;           // a row's reference max moves only when the tile's max exceeds it by more than this (exp2 domain)
 };
 
-// K|V^T stages: as many as fit next to Q (hi | lo) and the two P buffers
-__host__ __device__ constexpr int attn_prefill_tc_stages(int d) { return d == 128 ? 3 : 4; }
-inline size_t attn_prefill_tc_smem_bytes(int d) { return (size_t)2 * (d / 64) * 16384 + 65536 + (size_t)attn_prefill_tc_stages(d) * d * 256 + 1024; }
+// K and V^T pages travel through separate rings: a K page is free again as soon as its S = Q.K^T has completed, a V^T page only after
+// the O += P.V a whole softmax later, so with one shared ring the K loads could run only ~1.5 tiles ahead and the MMA warp waited for
+// them (ncu: the softmax warps stalled 25 % of their time on S).  Three K stages + two (d = 128) or three V^T stages sit next to Q
+// (hi | lo) and the two P buffers.
+constexpr int kTcKStages = 3;
+constexpr int kTcSBufs = 4;          // S accumulators in TMEM (64 columns each): S = Q.K^T runs up to four pages ahead of the softmax
+__host__ __device__ constexpr int attn_prefill_tc_vstages(int d) { return d == 128 ? 2 : 3; }
+inline size_t attn_prefill_tc_smem_bytes(int d) {
+    return (size_t)2 * (d / 64) * 16384 + 65536 + (size_t)(kTcKStages + attn_prefill_tc_vstages(d)) * d * 128 + 1024;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {      // one MUFU op; -inf -> 0
     float y;
@@ -629,13 +636,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
     constexpr int HALF = D / 64;
     constexpr uint32_t kQBytes = HALF * 16384;              // one of q_hi / q_lo: HALF k-blocks of [128 rows][128 B]
     constexpr uint32_t kPOff = 2 * kQBytes;                 // P: [2 buffers][hi | lo][128 rows][128 B]
-    constexpr uint32_t kStageOff = kPOff + 65536;
-    constexpr uint32_t kKBytes = D * 128, kStageBytes = 2 * D * 128;      // K page (HALF boxes of 8 KB) + V^T page ([D][128 B])
+    constexpr int NK = kTcKStages, NV = attn_prefill_tc_vstages(D);
+    constexpr uint32_t kTile = D * 128;                    // a K page (HALF boxes of [64 keys][128 B]) or a V^T page ([D][128 B])
+    constexpr uint32_t kKOff = kPOff + 65536, kVOff = kKOff + NK * kTile;
     extern __shared__ __align__(1024) uint8_t tcsm_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tcsm_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int NSTG = attn_prefill_tc_stages(D);
-    __shared__ __align__(8) uint64_t kv_full[NSTG], kv_empty[NSTG], s_full[2], s_free[2], p_ready[2], p_free[2], o_done, q_ready;
+    __shared__ __align__(8) uint64_t k_full[NK], k_empty[NK], v_full[NV], v_empty[NV], s_full[kTcSBufs], s_free[kTcSBufs], p_ready[2], p_free[2], o_done, q_ready;
     __shared__ uint32_t s_tmem;
+    __shared__ float xmax[2][2][kTcQ];      // [page parity][column half][row]: page maxima of the two halves of a row
+    __shared__ float xsum[2][kTcQ];         // their row sums (epilogue)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qt = gridDim.x - 1 - blockIdx.x, head = blockIdx.y, seq = blockIdx.z;      // heaviest (latest) query tiles first
@@ -646,15 +655,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
     const int nkt = (kend + kKvPage - 1) / kKvPage - kt0;
 
     if (tid == 0) {
-        for (int i = 0; i < NSTG; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_ready[i], 4); mbar_init(&p_free[i], 1);
-        }
+        for (int i = 0; i < NK; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < NV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        for (int i = 0; i < kTcSBufs; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 8); mbar_init(&p_free[i], 1); }
         mbar_init(&o_done, 1);
-        mbar_init(&q_ready, 4);
+        mbar_init(&q_ready, 8);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(&s_tmem, 256);
+    if (warp == 1) tmem_alloc(&s_tmem, 512);
     pdl_launch_dependents();
     pdl_wait();
     tc_fence_before();
@@ -662,72 +671,89 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t sm_s = smem_u32(sm);
-    const uint32_t tO = tmem + 128;
+    const uint32_t tO = tmem + kTcSBufs * 64;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0) {      // K pages: the pool's own rows
             const int cslot = st_slot(a.state, seq);
             const int* pt = a.page_table + (size_t)cslot * a.pt_stride;
             for (int j = 0; j < nkt; ++j) {
-                const int kt = kt0 + j, st = j % NSTG;
-                const int row = k.layer_row0 + (pt[kt] * a.nkv + kvh) * kKvPage;
-                mbar_wait(&kv_empty[st], ((j / NSTG) & 1) ^ 1);
-                mbar_expect_tx(&kv_full[st], kStageBytes);
-                uint8_t* dst = sm + kStageOff + st * kStageBytes;
+                const int st = j % NK;
+                const int row = k.layer_row0 + (pt[kt0 + j] * a.nkv + kvh) * kKvPage;
+                mbar_wait(&k_empty[st], ((j / NK) & 1) ^ 1);
+                mbar_expect_tx(&k_full[st], kTile);
 #pragma unroll
-                for (int hf = 0; hf < HALF; ++hf) tma_load_2d(dst + hf * 8192, &tmk, hf * 64, row, &kv_full[st]);
-                tma_load_2d(dst + kKBytes, &tmvt, 0, ((seq * a.nkv + kvh) * k.vt_pages + kt) * D, &kv_full[st]);
+                for (int hf = 0; hf < HALF; ++hf) tma_load_2d(sm + kKOff + st * kTile + hf * 8192, &tmk, hf * 64, row, &k_full[st]);
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {      // V^T pages of this call (written by dense_qkv_epi_kernel)
+            for (int j = 0; j < nkt; ++j) {
+                const int st = j % NV;
+                mbar_wait(&v_empty[st], ((j / NV) & 1) ^ 1);
+                mbar_expect_tx(&v_full[st], kTile);
+                tma_load_2d(sm + kVOff + st * kTile, &tmvt, 0, ((seq * a.nkv + kvh) * k.vt_pages + kt0 + j) * D, &v_full[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64), idesc_o = umma_idesc_bf16(128, D);
-            auto pv = [&](int i) {
-                const int b = i & 1;
-                mbar_wait(&p_ready[b], (i >> 1) & 1);
-                tc_fence_after();
-                const uint64_t vdesc = umma_smem_desc_sw128(sm + kStageOff + (i % NSTG) * kStageBytes + kKBytes);
-#pragma unroll
-                for (int hl = 0; hl < 2; ++hl) {
-                    const uint64_t pdesc = umma_smem_desc_sw128(sm + kPOff + (b * 2 + hl) * 16384);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_bf16(tO, pdesc + 2 * kk, vdesc + 2 * kk, idesc_o, (i > 0 || hl > 0 || kk > 0) ? 1u : 0u);
-                }
-                umma_commit(&kv_empty[i % NSTG]);
-                umma_commit(&p_free[b]);
-                umma_commit(&o_done);
-            };
+            // S = Q.K^T is issued as far ahead as K pages and free S buffers allow, O += P.V as soon as a page's probabilities are
+            // in shared memory: neither waits for the other (in lock step the issue -> commit -> softmax -> issue round trip of a
+            // page was the critical path: ~3100 clocks per page against ~700 of tensor work).
+            int qi = 0, pi = 0;
             mbar_wait(&q_ready, 0);
             tc_fence_after();
-            for (int j = 0; j < nkt; ++j) {
-                const int st = j % NSTG, sb = j & 1;
-                mbar_wait(&kv_full[st], (j / NSTG) & 1);
-                mbar_wait(&s_free[sb], ((j >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tS = tmem + sb * 64;
+            while (pi < nkt) {
+                if (pi < qi && mbar_test(&p_ready[pi & 1], (pi >> 1) & 1) && mbar_test(&v_full[pi % NV], (pi / NV) & 1)) {
+                    const int b = pi & 1;
+                    tc_fence_after();
+                    const uint64_t vdesc = umma_smem_desc_sw128(sm + kVOff + (pi % NV) * kTile);
 #pragma unroll
-                for (int hl = 0; hl < 2; ++hl)
+                    for (int hl = 0; hl < 2; ++hl) {
+                        const uint64_t pdesc = umma_smem_desc_sw128(sm + kPOff + (b * 2 + hl) * 16384);
 #pragma unroll
-                    for (int hf = 0; hf < HALF; ++hf) {
-                        const uint64_t qdesc = umma_smem_desc_sw128(sm + hl * kQBytes + hf * 16384);
-                        const uint64_t kdesc = umma_smem_desc_sw128(sm + kStageOff + st * kStageBytes + hf * 8192);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) umma_bf16(tS, qdesc + 2 * kk, kdesc + 2 * kk, idesc_s, (hl > 0 || hf > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk) umma_bf16(tO, pdesc + 2 * kk, vdesc + 2 * kk, idesc_o, (pi > 0 || hl > 0 || kk > 0) ? 1u : 0u);
                     }
-                umma_commit(&s_full[sb]);
-                if (j > 0) pv(j - 1);
+                    umma_commit(&v_empty[pi % NV]);
+                    umma_commit(&p_free[b]);
+                    umma_commit(&o_done);
+                    ++pi;
+                } else if (qi < nkt && mbar_test(&k_full[qi % NK], (qi / NK) & 1) &&
+                           mbar_test(&s_free[qi % kTcSBufs], ((qi / kTcSBufs) & 1) ^ 1)) {
+                    const int st = qi % NK, sb = qi % kTcSBufs;
+                    tc_fence_after();
+                    const uint32_t tS = tmem + sb * 64;
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                        for (int hf = 0; hf < HALF; ++hf) {
+                            const uint64_t qdesc = umma_smem_desc_sw128(sm + hl * kQBytes + hf * 16384);
+                            const uint64_t kdesc = umma_smem_desc_sw128(sm + kKOff + st * kTile + hf * 8192);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) umma_bf16(tS, qdesc + 2 * kk, kdesc + 2 * kk, idesc_s, (hl > 0 || hf > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    umma_commit(&s_full[sb]);
+                    umma_commit(&k_empty[st]);
+                    ++qi;
+                }
             }
-            pv(nkt - 1);
         }
-    } else {
-        const int quarter = warp & 3, r = quarter * 32 + lane;
+    } else if (warp < 10) {
+        // softmax: warps 2-5 own key columns 0-31 of every page, warps 6-9 columns 32-63 (same TMEM lanes: warp & 3 selects the
+        // quarter).  One warp per scheduler could not hide its own issue latencies (ncu: ~0.4 instructions per clock, the softmax
+        // warps were the critical path at ~3400 clocks per page); two per scheduler overlap one's MUFU / TMEM waits with the other's
+        // arithmetic.  The halves of a row exchange their page maxima through shared memory (one 256-thread named barrier per page).
+        const int grp = (warp - 2) >> 2, quarter = warp & 3, r = quarter * 32 + lane;
         const int irow = min(q0 + r, a.t - 1);               // rows past t are clamped: computed, never stored
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        auto gsync = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
         // ---- q row -> hi / lo bf16, swizzled operand layout: 16-byte chunk c of row r at chunk (c & 7) ^ (r & 7) of k-block c >> 3 ----
         {
             const float* qsrc = a.q + (((size_t)seq * a.t + irow) * a.nh + head) * D;
-#pragma unroll 4
-            for (int c = 0; c < D / 8; ++c) {
+#pragma unroll
+            for (int cc = 0; cc < D / 16; ++cc) {
+                const int c = grp * (D / 16) + cc;
                 const float4 x = *reinterpret_cast<const float4*>(qsrc + c * 8), y = *reinterpret_cast<const float4*>(qsrc + c * 8 + 4);
                 uint4 h, l;
                 h.x = pack_bf16x2(x.x, x.y); h.y = pack_bf16x2(x.z, x.w); h.z = pack_bf16x2(y.x, y.y); h.w = pack_bf16x2(y.z, y.w);
@@ -743,38 +769,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
         }
         const float c2 = a.qscale * 1.4426950408889634f;      // scores are carried in the exp2 domain
         const int lo_key = (sw > 0 && irow - sw > 0) ? irow - sw : 0;
-        float m = -INFINITY, l = 0.f;
+        float m = -INFINITY, l = 0.f;                         // l: this thread's half of the row sum
         for (int j = 0; j < nkt; ++j) {
-            const int b = j & 1, key0 = (kt0 + j) * kKvPage;
-            mbar_wait(&s_full[b], (j >> 1) & 1);
+            const int b = j & 1, sb = j % kTcSBufs, key0 = (kt0 + j) * kKvPage + grp * 32;
+            mbar_wait(&s_full[sb], (j / kTcSBufs) & 1);
             tc_fence_after();
-            float sc[64];
+            float sc[32];
             {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(tmem + lane_addr + b * 64, r0);
-                tmem_ld32(tmem + lane_addr + b * 64 + 32, r1);
+                uint32_t r0[32];
+                tmem_ld32(tmem + lane_addr + sb * 64 + grp * 32, r0);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) { sc[e] = __uint_as_float(r0[e]); sc[32 + e] = __uint_as_float(r1[e]); }
+                for (int e = 0; e < 32; ++e) sc[e] = __uint_as_float(r0[e]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[b]);
+            if (lane == 0) mbar_arrive(&s_free[sb]);
             float mx = -INFINITY;
-            if (key0 + kKvPage - 1 <= q0 && (sw <= 0 || key0 + sw >= q0 + kTcQ - 1)) {      // every key of the page is visible to every row
+            if (key0 + 31 <= q0 && (sw <= 0 || key0 + sw >= q0 + kTcQ - 1)) {      // every key of this half page is visible to every row
 #pragma unroll
-                for (int e = 0; e < 64; ++e) mx = fmaxf(mx, sc[e]);
+                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, sc[e]);
             } else {
 #pragma unroll
-                for (int e = 0; e < 64; ++e) {
+                for (int e = 0; e < 32; ++e) {
                     const int key = key0 + e;
                     sc[e] = (key <= irow && key >= lo_key) ? sc[e] : -INFINITY;
                     mx = fmaxf(mx, sc[e]);
                 }
             }
-            mx *= c2;
-            // The exponent offset m follows the running max lazily: it moves only when a tile's max exceeds it by more than tau, so
+            xmax[b][grp][r] = mx;
+            gsync();
+            mx = fmaxf(mx, xmax[b][grp ^ 1][r]) * c2;
+            // The exponent offset m follows the running max lazily: it moves only when a page's max exceeds it by more than tau, so
             // probabilities reach at most 2^tau (the final O / l does not depend on the offset) and the O accumulator in TMEM needs
-            // a rescale only on such a jump -- rare after the first pages -- instead of in every tile.
+            // a rescale only on such a jump -- rare after the first pages -- instead of in every page.  Both halves of a row see
+            // the same maxima, so they take the same decisions.
             const bool bump = mx > m + k.tau;              // m = -inf until the row has seen a visible key
             const float mn = bump ? mx : m;
             const float mu = mn == -INFINITY ? 0.f : mn;
@@ -782,36 +810,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
             m = mn;
             float ps = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; ++e) {
+            for (int e = 0; e < 32; ++e) {
                 sc[e] = ex2_approx(fmaf(sc[e], c2, -mu));
                 ps += sc[e];
             }
             l = l * alpha + ps;
             if (j > 0 && __any_sync(0xFFFFFFFFu, bump)) {
-                // O may be touched only when the previous P.V has completed; the warp rescales its own 32 TMEM lanes
+                // O may be touched only when the previous P.V has completed; the warp rescales its half of the columns of its 32 lanes
                 mbar_wait(&o_done, (j - 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c4 = 0; c4 < D / 32; ++c4) {
+                for (int c4 = 0; c4 < D / 64; ++c4) {
                     uint32_t o[32];
-                    tmem_ld32(tO + lane_addr + c4 * 32, o);
+                    tmem_ld32(tO + lane_addr + grp * (D / 2) + c4 * 32, o);
 #pragma unroll
                     for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                    tmem_st32(tO + lane_addr + c4 * 32, o);
+                    tmem_st32(tO + lane_addr + grp * (D / 2) + c4 * 32, o);
                 }
             }
-            mbar_wait(&p_free[b], ((j >> 1) & 1) ^ 1);       // the P.V two tiles back has finished reading this P buffer
+            mbar_wait(&p_free[b], ((j >> 1) & 1) ^ 1);       // the P.V two pages back has finished reading this P buffer
             const uint32_t ph = sm_s + kPOff + (b * 2) * 16384 + (uint32_t)r * 128u;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int cc = 0; cc < 4; ++cc) {
                 uint4 h, lo4;
-                h.x = pack_bf16x2(sc[8 * c], sc[8 * c + 1]); h.y = pack_bf16x2(sc[8 * c + 2], sc[8 * c + 3]);
-                h.z = pack_bf16x2(sc[8 * c + 4], sc[8 * c + 5]); h.w = pack_bf16x2(sc[8 * c + 6], sc[8 * c + 7]);
-                lo4.x = pack_bf16x2(sc[8 * c] - bf16lo(h.x), sc[8 * c + 1] - bf16hi(h.x));
-                lo4.y = pack_bf16x2(sc[8 * c + 2] - bf16lo(h.y), sc[8 * c + 3] - bf16hi(h.y));
-                lo4.z = pack_bf16x2(sc[8 * c + 4] - bf16lo(h.z), sc[8 * c + 5] - bf16hi(h.z));
-                lo4.w = pack_bf16x2(sc[8 * c + 6] - bf16lo(h.w), sc[8 * c + 7] - bf16hi(h.w));
-                const uint32_t off = (uint32_t)((c ^ (r & 7)) << 4);
+                h.x = pack_bf16x2(sc[8 * cc], sc[8 * cc + 1]); h.y = pack_bf16x2(sc[8 * cc + 2], sc[8 * cc + 3]);
+                h.z = pack_bf16x2(sc[8 * cc + 4], sc[8 * cc + 5]); h.w = pack_bf16x2(sc[8 * cc + 6], sc[8 * cc + 7]);
+                lo4.x = pack_bf16x2(sc[8 * cc] - bf16lo(h.x), sc[8 * cc + 1] - bf16hi(h.x));
+                lo4.y = pack_bf16x2(sc[8 * cc + 2] - bf16lo(h.y), sc[8 * cc + 3] - bf16hi(h.y));
+                lo4.z = pack_bf16x2(sc[8 * cc + 4] - bf16lo(h.z), sc[8 * cc + 5] - bf16hi(h.z));
+                lo4.w = pack_bf16x2(sc[8 * cc + 6] - bf16lo(h.w), sc[8 * cc + 7] - bf16hi(h.w));
+                const uint32_t off = (uint32_t)(((grp * 4 + cc) ^ (r & 7)) << 4);
                 sts128(ph + off, h);
                 sts128(ph + 16384 + off, lo4);
             }
@@ -820,15 +848,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[b]);
         }
-        // ---- epilogue: O / l -> hi | lo bf16 operands of the o_proj GEMM ----
+        // ---- epilogue: O / l -> hi | lo bf16 operands of the o_proj GEMM; each half writes its half of the head's columns ----
+        xsum[grp][r] = l;
+        gsync();
+        const float inv = 1.f / (l + xsum[grp ^ 1][r]);
         mbar_wait(&o_done, (nkt - 1) & 1);
         tc_fence_after();
-        const float inv = 1.f / l;
-        const size_t obase = (((size_t)seq * a.t + irow) * a.nh + head) * D;
+        const size_t obase = (((size_t)seq * a.t + irow) * a.nh + head) * D + grp * (D / 2);
 #pragma unroll 1
-        for (int c4 = 0; c4 < D / 32; ++c4) {
+        for (int c4 = 0; c4 < D / 64; ++c4) {
             uint32_t o[32];
-            tmem_ld32(tO + lane_addr + c4 * 32, o);
+            tmem_ld32(tO + lane_addr + grp * (D / 2) + c4 * 32, o);
             if (q0 + r < a.t) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -849,7 +879,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_prefill_tc_kernel(const __
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem, 256);
+        tmem_dealloc(tmem, 512);
     }
 }
 

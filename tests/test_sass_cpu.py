@@ -51,6 +51,11 @@ def test_attention_kernels_use_tensor_cores(kernels):
             assert c["HMMA.16816.F32.BF16"] >= 8 and c["LDSM"] >= 4, name
     for name, c in _family(kernels, "attn_sk_decode_kernel<").items():
         assert c["UTMALDG.2D"] >= 2 and c["SYNCS"] >= 4, name      # K|V pages arrive by 2-D TMA, completion on mbarriers
+    fam = _family(kernels, "attn_prefill_tc_kernel<")
+    assert sorted(fam) == ["attn_prefill_tc_kernel<128>", "attn_prefill_tc_kernel<64>"]
+    for name, c in fam.items():                                    # prefill attention on the 5th-gen tensor cores
+        assert c["UTCHMMA"] >= 16 and c["LDTM"] >= 2 and c["UTMALDG.2D"] >= 2, name
+        assert c["HMMA.16816.F32.BF16"] == 0, name
 
 
 def test_spills_only_where_known():
