@@ -102,7 +102,8 @@ struct PkArgs {
     float* peer_logits[8];           // rank r's full-vocabulary logits [Vfull]
     unsigned int ar_epoch0;          // exchanges completed on this communicator before this launch
     int* comm_err;                   // set to 1 when a peer did not show up within the spin budget
-    int flags;            // dev knob (FL_PK_FLAGS) bit 0: prefetch this CTA's KV pages into L2 at the top of P1
+    int flags;            // dev knob (FL_PK_FLAGS) bit 0: prefetch this CTA's KV pages into L2 at the top of P1; bits 1-3: timing
+                          // experiments with garbage results (2: no arithmetic, 4: no attention, 8: no weight traffic)
     long long* dbg;       // optional: CTA 0 writes %globaltimer at the phase boundaries of layer L/2 (FL_PK_DEBUG=1)
 };
 
@@ -154,9 +155,12 @@ __device__ __forceinline__ uint4 ldcg_u4(const void* p) {
 }
 
 // L2 eviction-priority hint of the weight stream: weights are read exactly once per step and are dead once they are in shared
-// memory, so the demand loads carry evict_first and leave the L2 to the KV cache and the activations.  (An L2 lookahead
-// cursor ahead of the ring was measured and removed: it cannot buy bandwidth -- the L2->SM delivery rate is the limit -- and
-// deep lookahead makes the prefetched-but-unused lines the oldest in an LRU-like L2: 512 KB/CTA = 1.13x the HBM traffic.)
+// memory, so the demand loads carry evict_first and leave the L2 to the KV cache and the activations.
+// Prefetching the NEXT phase's weights into the L2 while the consumers sit between two weight phases (HBM idles there, and the L2
+// feeds these boxes at 14.3 TB/s against 6.4-7.5 TB/s from HBM, tools/tma_stream_bench.cu) was built twice in round 2 -- a
+// prefetch warp walking the CTA's static share N chunks ahead of the producer, with `cp.async.bulk.prefetch.tensor` and with
+// plain `prefetch.global.L2`, all the time or only inside the gaps -- and measured SLOWER every time (N = 4: -4 %, 8: -10 %,
+// 16: -15 %; DRAM bytes +1.4 %, only a third of the demand sectors turned into L2 hits): profiles/r02_persistent_limits.md.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -246,7 +250,11 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // =================================================================================================================
     if (warp == kPkConsumerWarps) {
         if (lane != 0) return;
-        unsigned int c = 0;   // running stage counter -> stage = c % NS, use = c / NS
+        int pst = 0;             // next ring stage
+        uint32_t pph = 1;        // parity to wait for on empty[pst]: the first pass over the ring finds every stage free
+        auto advance = [&]() {
+            if (++pst == NS) { pst = 0; pph ^= 1u; }
+        };
         const uint64_t pol_first = l2_policy_evict_first();
         const bool dynamic = a.tp == 1 && a.pool != nullptr;
         for (int step = 0; step < a.nsteps; ++step) {
@@ -255,11 +263,25 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 int N, K;
                 pk_phase(a, g, W, N, K);
                 const PkSplit sp = pk_split(N, K, cta, ncta, dynamic, a.static_num);
+                const bool pdbg = a.dbg != nullptr && cta == 0 && g < 4 * a.L && (g >> 2) == a.L / 2;
+                int pn = 0;
                 auto fetch_block = [&](int blk) {
-                    for (int cc = 0; cc < sp.ncc; ++cc, ++c) {
-                        const int st = c % NS;
-                        mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
+                    for (int cc = 0; cc < sp.ncc; ++cc) {
+                        const int st = pst;
+                        mbar_wait(&empty[st], pph);
+                        advance();
+                        if (pdbg) {      // issue times of this phase's first 8 chunks and of its last one (FL_PK_DEBUG)
+                            long long t;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                            if (pn < 8) a.dbg[660 + (g & 3) * 10 + pn] = t;
+                            a.dbg[660 + (g & 3) * 10 + 8] = t;
+                            a.dbg[660 + (g & 3) * 10 + 9] = ++pn;
+                        }
                         meta[st] = make_int2(blk * kPkBlockRows, cc | (cc == sp.ncc - 1 ? 1 << 16 : 0));
+                        if (a.flags & 8) {      // timing experiment: no weight traffic at all (results are garbage)
+                            mbar_arrive(&full[st]);
+                            continue;
+                        }
                         mbar_expect_tx(&full[st], kPkStageBytes);      // the whole box always arrives (out-of-range columns as zeros)
                         // weights are dead once staged: evict_first keeps the L2 for the KV cache and the activations
                         asm volatile(
@@ -277,11 +299,11 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                     if (t >= sp.npool) break;
                     fetch_block(sp.pool0 + t);
                 }
-                const int st = c % NS;          // end-of-phase message (no data)
-                mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
+                const int st = pst;          // end-of-phase message (no data)
+                mbar_wait(&empty[st], pph);
+                advance();
                 meta[st] = make_int2(0, kPkMetaEnd);
                 mbar_arrive(&full[st]);
-                ++c;
             }
         }
         return;
@@ -290,7 +312,9 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // =================================================================================================================
     // CONSUMERS
     // =================================================================================================================
-    unsigned int c = 0;       // chunk counter, in lock-step with the producer's
+    int cst = 0;              // ring stage of the next chunk, in lock-step with the producer's
+    uint32_t cph = 0;         // parity to wait for on full[cst]
+    const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(&full[0]), empty_s = smem_u32(&empty[0]);      // shared-space addresses, computed once
     unsigned int epoch = 0;   // grid-barrier epoch
 
     // activation vector of the current phase as two bf16 vectors (x = hi + lo), the B operand of the MMAs
@@ -306,6 +330,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     int dbg_layer = -1, dbg_phase = 0;
     auto consume = [&](int K) -> int {      // -> number of 16-row blocks this CTA processed (their first rows in blk_rows[])
         dbg_wait = 0;
+
         // ldmatrix row addresses of this lane: A = weight tile rows (lane & 15), +8 columns for lanes 16-31;
         // B = [n = lane & 7][8 consecutive k]: n == 1 -> x_lo, every other n -> x_hi (columns 2-7 of D are never read, so those
         // rows need not be zero: re-reading x_hi is a broadcast and keeps the load bank-conflict-free); lanes 8-15 take k + 8
@@ -315,50 +340,67 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         const int ar = lane & 15;
         const uint32_t a_off = (uint32_t)(warp >> 2) * 2048u + (uint32_t)ar * 128u + (uint32_t)(((((warp & 3) << 1) | (lane >> 4)) ^ (ar & 7)) << 4);
         const int bn = lane & 7, bk = ((lane >> 3) & 1) * 8;
-        const uint16_t* xrow = bn == 1 ? xl : xh;
-        float acc[2][4];
+        const uint32_t xcol_s = smem_u32(bn == 1 ? xl : xh) + (uint32_t)(bk + warp * 16) * 2u;
+        constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
+        // four accumulator chains: the 8 MMAs of a chunk are 2 deep instead of 4 (this loop is a latency chain per warp: wait -> message
+        // -> fragment loads -> MMAs -> release, with no overlap between chunks, so its length bounds how fast a full ring can be drained)
+        float acc[4][4];
         int nslots = 0, nch = 0;
         while (true) {
-            const int st = c % NS;
+            const int st = cst;
             const long long tw0 = a.dbg ? clock64() : 0;
-            mbar_wait(&full[st], (c / NS) & 1);
+            {
+                uint32_t done;
+                do {
+                    asm volatile(
+                        "{\n"
+                        ".reg .pred p;\n"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                        "selp.u32 %0, 1, 0, p;\n"
+                        "}\n"
+                        : "=r"(done)
+                        : "r"(full_s + (uint32_t)st * 8u), "r"(cph)
+                        : "memory");
+                } while (!done);
+            }
+            if (++cst == NS) { cst = 0; cph ^= 1u; }
             if (a.dbg) dbg_wait += clock64() - tw0;
             const int2 m = meta[st];
-            ++c;
             if (m.y & kPkMetaEnd) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[st]);
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + (uint32_t)st * 8u) : "memory");
                 break;
             }
             const int cc = m.y & 0xFFFF;
             if (cc == 0) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = 0.f;
+                for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = acc[2][q] = acc[3][q] = 0.f;
             }
-            const uint8_t* tile = ring + (size_t)st * kPkStageBytes + a_off;
-            const int col0 = cc * kPkChunkCols;
-            // all fragment loads of a half chunk first (independent, in flight together), then the MMAs (two accumulator chains)
-            constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
-            const uint16_t* xcol = xrow + (col0 + bk + warp * 16);
+            if (!(a.flags & 2)) {      // (timing experiment: bit 1 skips the arithmetic)
+                const uint32_t tile = ring_s + (uint32_t)st * (uint32_t)kPkStageBytes + a_off;
+                const uint32_t xc = xcol_s + (uint32_t)cc * (uint32_t)(kPkChunkCols * 2);
+                // all fragment loads of the chunk first (independent, in flight together), then the MMAs
+                uint32_t af[KPW][4], bf[KPW][2];
 #pragma unroll
-            for (int h = 0; h < KPW; h += 4) {
-                uint32_t af[4][4], bf[4][2];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ldmatrix_x4(af[j], tile + (h + j) * 4096);
-                    ldmatrix_x2(bf[j], xcol + (h + j) * kPkConsumerWarps * 16);
+                for (int j = 0; j < KPW; ++j) {
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3])
+                                 : "r"(tile + (uint32_t)j * 4096u));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+                                 : "=r"(bf[j][0]), "=r"(bf[j][1])
+                                 : "r"(xc + (uint32_t)j * (uint32_t)(kPkConsumerWarps * 16 * 2)));
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j & 1], af[j], bf[j]);
+                for (int j = 0; j < KPW; ++j) mma_bf16_16816(acc[j & 3], af[j], bf[j]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + (uint32_t)st * 8u) : "memory");
             ++nch;
             if (m.y & (1 << 16)) {      // last column chunk of the block: the row sums are complete
                 if (tq == 0) {
                     float* pr = partial + (size_t)(nslots * kPkBlockRows + g) * kPkConsumerWarps + warp;
-                    pr[0] = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
-                    pr[8 * kPkConsumerWarps] = (acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3]);
+                    pr[0] = ((acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1])) + ((acc[2][0] + acc[2][1]) + (acc[3][0] + acc[3][1]));
+                    pr[8 * kPkConsumerWarps] = ((acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3])) + ((acc[2][2] + acc[2][3]) + (acc[3][2] + acc[3][3]));
                 }
                 if (tid == 0) blk_rows[nslots] = m.x;
                 ++nslots;
@@ -603,7 +645,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 const int per = (npages + a.nsplit - 1) / a.nsplit;
                 float* gacc = xs;                            // [NG][HG][D]
                 float* gml = xs + NG * HG * D;               // [NG][HG][2]
-                for (int item = cta; item < a.nkv * a.nsplit; item += ncta) {
+                for (int item = (a.flags & 4) ? a.nkv * a.nsplit : cta; item < a.nkv * a.nsplit; item += ncta) {      // (bit 2: timing experiment without attention)
                     const int kvh = item / a.nsplit, split = item % a.nsplit;
                     const int tok0 = split * per * kKvPage, tok1 = min(min((split + 1) * per, npages) * kKvPage, len);
                     const int gidx = warp * TPW + grp;

@@ -662,7 +662,8 @@ static void plan_persistent(fl_cache& c) {
     const size_t fixed = (size_t)p.xs_floats * 4 + (size_t)p.partial_rows * kPkConsumerWarps * 4 + (size_t)kAttnMaxRep * kKvPage * 4 + 64 * 4;
     const size_t avail = 232448 - 2048;   // 227 KB opt-in limit minus static shared memory and slack
     if (fixed + 2 * (size_t)kPkStageBytes > avail) return;
-    p.nstages = (int)std::min<size_t>(kPkMaxStages, (avail - fixed) / kPkStageBytes);
+    static const int max_stages = std::getenv("FL_PK_MAXSTAGES") ? std::max(2, std::atoi(std::getenv("FL_PK_MAXSTAGES"))) : kPkMaxStages;      // dev knob
+    p.nstages = (int)std::min<size_t>(std::min(max_stages, kPkMaxStages), (avail - fixed) / kPkStageBytes);
     p.smem = (size_t)p.nstages * kPkStageBytes + fixed;
     p.nsplit = std::max(1, std::min(c.pages_per_seq, kNumSMs / w.nkv));
     if (p.nsplit > c.nsplit) p.nsplit = c.nsplit;            // partial buffers are sized for c.nsplit
@@ -728,7 +729,10 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
     }
     static long long* dbg_buf = nullptr;
     const bool dbg = env_flag("FL_PK_DEBUG");
-    if (dbg && !dbg_buf) FL_CUDA(cudaMalloc(&dbg_buf, (64 + 4 * kNumSMs) * sizeof(long long)));
+    if (dbg && !dbg_buf) {
+        FL_CUDA(cudaMalloc(&dbg_buf, (64 + 4 * kNumSMs + 64) * sizeof(long long)));
+        FL_CUDA(cudaMemset(dbg_buf, 0, (64 + 4 * kNumSMs + 64) * sizeof(long long)));
+    }
     a.dbg = dbg ? dbg_buf : nullptr;
     FL_CUDA(cudaMemsetAsync(c.gbar.p, 0, sizeof(unsigned int), c.stream));
     FL_CUDA(cudaMemsetAsync(c.pk_pool.p, 0, (4 * (size_t)w.L + 1) * sizeof(unsigned int), c.stream));   // the kernel re-arms them itself; this covers an aborted launch
@@ -762,6 +766,18 @@ static void launch_persistent(fl_cache& c, int nsteps, bool feedback) {
         fprintf(stderr, "[FL_PK_DEBUG] layer %d, CTA 0 phase times (us):", w.L / 2);
         for (int i = 0; i < 18; ++i) fprintf(stderr, " %s=%.2f;", names[i], (h[i + 1] - h[i]) / 1000.0);
         fprintf(stderr, " layer total=%.2f\n", (h[18] - h[0]) / 1000.0);
+        {      // the producer's view: when (relative to the consumers' phase boundaries) it issued the first chunks of each phase
+            long long pr[40];
+            FL_CUDA(cudaMemcpy(pr, dbg_buf + 660, sizeof(pr), cudaMemcpyDeviceToHost));
+            static const char* pn[] = {"qkv", "o", "gate|up", "down"};
+            const int cons_start[] = {1, 7, 11, 15};      // stamp index at which the consumers start consuming the phase
+            for (int ph = 0; ph < 4; ++ph) {
+                fprintf(stderr, "[FL_PK_DEBUG] producer, %s: chunk issue times relative to the consumers' start of the phase (us):", pn[ph]);
+                for (int i = 0; i < 8 && i < pr[ph * 10 + 9]; ++i) fprintf(stderr, " %.2f", (pr[ph * 10 + i] - h[cons_start[ph]]) / 1000.0);
+                fprintf(stderr, " ... last of %lld at %.2f (consume ends at %.2f)\n", pr[ph * 10 + 9], (pr[ph * 10 + 8] - h[cons_start[ph]]) / 1000.0,
+                        (h[cons_start[ph] + 1] - h[cons_start[ph]]) / 1000.0);
+            }
+        }
         if (env_flag("FL_PK_DEBUG_CTAS")) {      // per-CTA start / end of the gate|up weight phase: who is the barrier waiting for?
             std::vector<long long> pc(4 * kNumSMs);
             FL_CUDA(cudaMemcpy(pc.data(), dbg_buf + 64, pc.size() * sizeof(long long), cudaMemcpyDeviceToHost));

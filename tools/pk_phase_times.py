@@ -1,6 +1,6 @@
 import numpy as np, os, sys
 sys.path.insert(0, '/root/repo')
-os.environ["FL_PK_DEBUG"]="1"
+os.environ.setdefault("FL_PK_DEBUG", "0")
 from fastllm_b200 import models, presets
 cls, cf = presets.PRESETS["mistral7b"]
 model,_ = cls.initialize_model(cf, None, "bf16", 0, random_seed=0)

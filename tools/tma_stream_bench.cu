@@ -30,7 +30,7 @@ constexpr int kStagesMax = 12;
 // every CTA streams a contiguous range of stages (column block fastest, like the k loop of a GEMM tile / a row block of the
 // persistent kernel); the stage -> address mapping covers the matrix exactly once
 __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ CUtensorMap tm, const uint16_t* W, int mode, int nstages, int stage_bytes,
-                                                        long long total_stages, int K, int N) {
+                                                        long long total_stages, int K, int N, int passes = 1) {
     extern __shared__ __align__(1024) uint8_t ring[];
     __shared__ __align__(8) uint64_t full[kStagesMax], empty[kStagesMax];
     if (threadIdx.x == 0) {
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ C
     if (threadIdx.x == 0) {            // producer
         unsigned c = 0;
         const long long i0 = total_stages * blockIdx.x / gridDim.x, i1 = total_stages * (blockIdx.x + 1) / gridDim.x;
+        for (int pass = 0; pass < passes; ++pass)
         for (long long i = i0; i < i1; ++i, ++c) {
             const int st = c % nstages;
             mbar_wait(&empty[st], ((c / nstages) & 1) ^ 1);
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ C
     } else if (threadIdx.x == 32) {    // consumer: release the stage as soon as it has landed
         unsigned c = 0;
         const long long i0 = total_stages * blockIdx.x / gridDim.x, i1 = total_stages * (blockIdx.x + 1) / gridDim.x;
+        for (int pass = 0; pass < passes; ++pass)
         for (long long i = i0; i < i1; ++i, ++c) {
             const int st = c % nstages;
             mbar_wait(&full[st], (c / nstages) & 1);
@@ -134,6 +136,38 @@ int main() {
                 if (rep > 0 && ms < best) best = ms;
             }
             printf("%-62s in flight %3d KB/SM (%2d stages): %7.1f us  %6.0f GB/s\n", names[mode], inflight_kb, nstages, best * 1e3, (double)N * K * 2 / (best * 1e-3) / 1e9);
+        }
+    }
+    // L2-resident variant (round 2): the same 3-D 32 KB boxes over a 33.5 MB matrix (Mistral o_proj) re-read by every launch, so all
+    // but the first launch hit the L2.  Answers: can the L2 feed the SMs faster than HBM does (would an L2 prefetch of the next
+    // phase's weights during the persistent kernel's grid barriers buy anything)?
+    {
+        const int N2 = 4096, K2 = 4096;
+        CUtensorMap tm;
+        const cuuint32_t es[3] = {1, 1, 1};
+        const cuuint64_t dims[3] = {64, (cuuint64_t)N2, (cuuint64_t)K2 / 64};
+        const cuuint64_t str[2] = {(cuuint64_t)K2 * 2, 128};
+        const cuuint32_t box2[3] = {64, 16, 16};
+        enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Wall, dims, str, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const int stage_bytes = 32768;
+        for (int inflight_kb : {64, 96, 128, 192}) {
+            const int nstages = inflight_kb * 1024 / stage_bytes;
+            const size_t smem = (size_t)nstages * stage_bytes;
+            CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long total = (long long)N2 * K2 * 2 / stage_bytes;
+            float best = 1e9f;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaEventRecord(e0));
+                for (int it = 0; it < 10; ++it) stream_kernel<<<148, 64, smem>>>(tm, Wall, 2, nstages, stage_bytes, total, K2, N2, 50);
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                ms /= 500;
+                if (rep > 0 && ms < best) best = ms;
+            }
+            printf("L2-resident 33.5 MB, 3-D box 32 KB, in flight %3d KB/SM (%2d stages): %7.1f us per pass  %6.0f GB/s (50 passes per launch)\n", inflight_kb, nstages,
+                   best * 1e3, (double)N2 * K2 * 2 / (best * 1e-3) / 1e9);
         }
     }
     return 0;
