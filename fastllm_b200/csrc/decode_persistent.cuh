@@ -250,11 +250,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // =================================================================================================================
     if (warp == kPkConsumerWarps) {
         if (lane != 0) return;
-        int pst = 0;             // next ring stage
-        uint32_t pph = 1;        // parity to wait for on empty[pst]: the first pass over the ring finds every stage free
-        auto advance = [&]() {
-            if (++pst == NS) { pst = 0; pph ^= 1u; }
-        };
+        unsigned int c = 0;   // running stage counter -> stage = c % NS, use = c / NS
         const uint64_t pol_first = l2_policy_evict_first();
         const bool dynamic = a.tp == 1 && a.pool != nullptr;
         for (int step = 0; step < a.nsteps; ++step) {
@@ -267,9 +263,10 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                 int pn = 0;
                 auto fetch_block = [&](int blk) {
                     for (int cc = 0; cc < sp.ncc; ++cc) {
-                        const int st = pst;
-                        mbar_wait(&empty[st], pph);
-                        advance();
+                        const int st = c % NS;
+                        mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
+                        ++c;
+                        meta[st] = make_int2(blk * kPkBlockRows, cc | (cc == sp.ncc - 1 ? 1 << 16 : 0));
                         if (pdbg) {      // issue times of this phase's first 8 chunks and of its last one (FL_PK_DEBUG)
                             long long t;
                             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -277,7 +274,6 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                             a.dbg[660 + (g & 3) * 10 + 8] = t;
                             a.dbg[660 + (g & 3) * 10 + 9] = ++pn;
                         }
-                        meta[st] = make_int2(blk * kPkBlockRows, cc | (cc == sp.ncc - 1 ? 1 << 16 : 0));
                         if (a.flags & 8) {      // timing experiment: no weight traffic at all (results are garbage)
                             mbar_arrive(&full[st]);
                             continue;
@@ -299,11 +295,11 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
                     if (t >= sp.npool) break;
                     fetch_block(sp.pool0 + t);
                 }
-                const int st = pst;          // end-of-phase message (no data)
-                mbar_wait(&empty[st], pph);
-                advance();
+                const int st = c % NS;          // end-of-phase message (no data)
+                mbar_wait(&empty[st], ((c / NS) & 1) ^ 1);
                 meta[st] = make_int2(0, kPkMetaEnd);
                 mbar_arrive(&full[st]);
+                ++c;
             }
         }
         return;
@@ -312,9 +308,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     // =================================================================================================================
     // CONSUMERS
     // =================================================================================================================
-    int cst = 0;              // ring stage of the next chunk, in lock-step with the producer's
-    uint32_t cph = 0;         // parity to wait for on full[cst]
-    const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(&full[0]), empty_s = smem_u32(&empty[0]);      // shared-space addresses, computed once
+    unsigned int c = 0;       // chunk counter, in lock-step with the producer's
     unsigned int epoch = 0;   // grid-barrier epoch
 
     // activation vector of the current phase as two bf16 vectors (x = hi + lo), the B operand of the MMAs
@@ -330,7 +324,6 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
     int dbg_layer = -1, dbg_phase = 0;
     auto consume = [&](int K) -> int {      // -> number of 16-row blocks this CTA processed (their first rows in blk_rows[])
         dbg_wait = 0;
-
         // ldmatrix row addresses of this lane: A = weight tile rows (lane & 15), +8 columns for lanes 16-31;
         // B = [n = lane & 7][8 consecutive k]: n == 1 -> x_lo, every other n -> x_hi (columns 2-7 of D are never read, so those
         // rows need not be zero: re-reading x_hi is a broadcast and keeps the load bank-conflict-free); lanes 8-15 take k + 8
@@ -340,67 +333,53 @@ __global__ void __launch_bounds__(kPkThreads, 1) decode_persistent_kernel(const 
         const int ar = lane & 15;
         const uint32_t a_off = (uint32_t)(warp >> 2) * 2048u + (uint32_t)ar * 128u + (uint32_t)(((((warp & 3) << 1) | (lane >> 4)) ^ (ar & 7)) << 4);
         const int bn = lane & 7, bk = ((lane >> 3) & 1) * 8;
-        const uint32_t xcol_s = smem_u32(bn == 1 ? xl : xh) + (uint32_t)(bk + warp * 16) * 2u;
-        constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
-        // four accumulator chains: the 8 MMAs of a chunk are 2 deep instead of 4 (this loop is a latency chain per warp: wait -> message
-        // -> fragment loads -> MMAs -> release, with no overlap between chunks, so its length bounds how fast a full ring can be drained)
-        float acc[4][4];
+        const uint16_t* xrow = bn == 1 ? xl : xh;
+        float acc[2][4];
         int nslots = 0, nch = 0;
         while (true) {
-            const int st = cst;
+            const int st = c % NS;
             const long long tw0 = a.dbg ? clock64() : 0;
-            {
-                uint32_t done;
-                do {
-                    asm volatile(
-                        "{\n"
-                        ".reg .pred p;\n"
-                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                        "selp.u32 %0, 1, 0, p;\n"
-                        "}\n"
-                        : "=r"(done)
-                        : "r"(full_s + (uint32_t)st * 8u), "r"(cph)
-                        : "memory");
-                } while (!done);
-            }
-            if (++cst == NS) { cst = 0; cph ^= 1u; }
+            mbar_wait(&full[st], (c / NS) & 1);
             if (a.dbg) dbg_wait += clock64() - tw0;
             const int2 m = meta[st];
+            ++c;
             if (m.y & kPkMetaEnd) {
                 __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + (uint32_t)st * 8u) : "memory");
+                if (lane == 0) mbar_arrive(&empty[st]);
                 break;
             }
             const int cc = m.y & 0xFFFF;
             if (cc == 0) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = acc[2][q] = acc[3][q] = 0.f;
+                for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = 0.f;
             }
-            if (!(a.flags & 2)) {      // (timing experiment: bit 1 skips the arithmetic)
-                const uint32_t tile = ring_s + (uint32_t)st * (uint32_t)kPkStageBytes + a_off;
-                const uint32_t xc = xcol_s + (uint32_t)cc * (uint32_t)(kPkChunkCols * 2);
-                // all fragment loads of the chunk first (independent, in flight together), then the MMAs
-                uint32_t af[KPW][4], bf[KPW][2];
+            const uint8_t* tile = ring + (size_t)st * kPkStageBytes + a_off;
+            const int col0 = cc * kPkChunkCols;
+            // all fragment loads of a half chunk first (independent, in flight together), then the MMAs (two accumulator chains).
+            // (Round 2 tried the whole chunk's 16 loads ahead of four chains, with the stage index kept incrementally instead of
+            // c % NS: faster with the weight traffic switched off, 0.8-3.6 % SLOWER in the real run on all three models: dropped.)
+            constexpr int KPW = kPkChunkCols / 16 / kPkConsumerWarps;      // k-steps per warp per full chunk (8)
+            const uint16_t* xcol = xrow + (col0 + bk + warp * 16);
+            if (!(a.flags & 2))      // (timing experiment: bit 1 skips the arithmetic)
 #pragma unroll
-                for (int j = 0; j < KPW; ++j) {
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3])
-                                 : "r"(tile + (uint32_t)j * 4096u));
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
-                                 : "=r"(bf[j][0]), "=r"(bf[j][1])
-                                 : "r"(xc + (uint32_t)j * (uint32_t)(kPkConsumerWarps * 16 * 2)));
+            for (int h = 0; h < KPW; h += 4) {
+                uint32_t af[4][4], bf[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ldmatrix_x4(af[j], tile + (h + j) * 4096);
+                    ldmatrix_x2(bf[j], xcol + (h + j) * kPkConsumerWarps * 16);
                 }
 #pragma unroll
-                for (int j = 0; j < KPW; ++j) mma_bf16_16816(acc[j & 3], af[j], bf[j]);
+                for (int j = 0; j < 4; ++j) mma_bf16_16816(acc[j & 1], af[j], bf[j]);
             }
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s + (uint32_t)st * 8u) : "memory");
+            if (lane == 0) mbar_arrive(&empty[st]);
             ++nch;
             if (m.y & (1 << 16)) {      // last column chunk of the block: the row sums are complete
                 if (tq == 0) {
                     float* pr = partial + (size_t)(nslots * kPkBlockRows + g) * kPkConsumerWarps + warp;
-                    pr[0] = ((acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1])) + ((acc[2][0] + acc[2][1]) + (acc[3][0] + acc[3][1]));
-                    pr[8 * kPkConsumerWarps] = ((acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3])) + ((acc[2][2] + acc[2][3]) + (acc[3][2] + acc[3][3]));
+                    pr[0] = (acc[0][0] + acc[0][1]) + (acc[1][0] + acc[1][1]);
+                    pr[8 * kPkConsumerWarps] = (acc[0][2] + acc[0][3]) + (acc[1][2] + acc[1][3]);
                 }
                 if (tid == 0) blk_rows[nslots] = m.x;
                 ++nslots;

@@ -123,6 +123,70 @@ static __global__ void __launch_bounds__(1024) dense_prep_kernel(const PrepArgs 
     }
 }
 
+// Many-row variant (prefill): 256 threads per row with the row held in registers between the sum-of-squares and the scaling pass
+// (NV float4 per thread: K <= 1024 NV), so a row is read once and more rows are resident per SM.  Same arithmetic as
+// dense_prep_kernel (slices summed in order, then added to the residual); only the residual-add + RMSNorm form.
+constexpr int kPrepRowsThreads = 256;
+template <int NV>
+static __global__ void __launch_bounds__(kPrepRowsThreads) dense_prep_rows_kernel(const PrepArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float red[32];
+    const int orow = blockIdx.x;
+    const int row = a.last_only ? (orow + 1) * a.t - 1 : orow;
+    const int K = a.K, K4 = K >> 2;
+    uint2* xh = reinterpret_cast<uint2*>(a.xhi + (size_t)orow * K);
+    uint2* xl = reinterpret_cast<uint2*>(a.xlo + (size_t)orow * K);
+    float4* r = reinterpret_cast<float4*>(a.resid + (size_t)row * K);
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = threadIdx.x + j * kPrepRowsThreads;
+        v[j] = i < K4 ? r[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (a.delta) {
+        float4 ds[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) ds[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < a.nsl; ++s) {         // fixed order: deterministic split-K reduction
+            const float4* dp = reinterpret_cast<const float4*>(a.delta + (size_t)s * a.sl_stride + (size_t)row * a.ldd);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int i = threadIdx.x + j * kPrepRowsThreads;
+                if (i < K4) {
+                    const float4 p = dp[i];
+                    ds[j].x += p.x; ds[j].y += p.y; ds[j].z += p.z; ds[j].w += p.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = threadIdx.x + j * kPrepRowsThreads;
+            v[j].x += ds[j].x; v[j].y += ds[j].y; v[j].z += ds[j].z; v[j].w += ds[j].w;
+            if (i < K4) r[i] = v[j];
+        }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {      // elements past K are zeros
+        ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+    }
+    const float tot = block_sum_256(ss, red);
+    const float m = sqrtf(tot / (float)K + a.eps);       // candle rms_norm: x / sqrt(mean(x^2) + eps) * w
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = threadIdx.x + j * kPrepRowsThreads;
+        if (i < K4) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(a.norm_w) + i);
+            const float4 x = make_float4(v[j].x / m * wv.x, v[j].y / m * wv.y, v[j].z / m * wv.z, v[j].w / m * wv.w);
+            uint16_t h0, l0, h1, l1, h2, l2, h3, l3;
+            split_hi_lo(x.x, h0, l0); split_hi_lo(x.y, h1, l1); split_hi_lo(x.z, h2, l2); split_hi_lo(x.w, h3, l3);
+            xh[i] = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+            xl[i] = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+        }
+    }
+}
+
 struct QkvEpiArgs {
     int nsl;                   // split-K slices of y
     long long sl_stride;

@@ -1222,6 +1222,15 @@ static void enqueue_forward_dense(fl_cache& c, LaunchCtx& lc, int b, int t, bool
 
     auto prep = [&](const char* tag, PrepArgs pa, int rows_out) {
         pa.xhi = d.xhi.p; pa.xlo = d.xlo.p; pa.eps = w.cfg.norm_eps; pa.t = t;
+        // many rows (prefill): the register-resident 256-thread kernel (dense_prep_rows_kernel); FL_PREP_ROWS=0 keeps the one-CTA-per-row kernel
+        static const bool rows_kernel = !std::getenv("FL_PREP_ROWS") || std::atoi(std::getenv("FL_PREP_ROWS")) != 0;
+        if (rows_kernel && rows_out >= 512 && pa.norm_w != nullptr && pa.embed == nullptr && pa.K <= 8192 && pa.K % 4 == 0) {
+            if (pa.K <= 4096)
+                launch(lc, tag, 0, dense_prep_rows_kernel<4>, dim3(rows_out), dim3(kPrepRowsThreads), 0, pa);
+            else
+                launch(lc, tag, 0, dense_prep_rows_kernel<8>, dim3(rows_out), dim3(kPrepRowsThreads), 0, pa);
+            return;
+        }
         const int threads = std::min(1024, std::max(32, (pa.K / 4 + 31) / 32 * 32));
         launch(lc, tag, 0, dense_prep_kernel, dim3(rows_out), dim3(threads), 0, pa);
     };
