@@ -89,6 +89,25 @@ def test_compare_sharded_counts_rows_only_while_routing_agrees():
     assert r["greedy32"] and r["router_disagreements"] == 1 and r["rows_compared"] == steps * b - 2 and r["max_abs_all_rows"] > 1
     # the same disagreement with a wide margin is a defect
     assert not bench.compare_sharded(got2, want, "x", routing=(sel_g, sel, mar))["greedy32"]
+    # consequences of a reroute are not defects: after the near-tie reroute of sequence 1 (step 2, layer 1) its picks in the following
+    # calls -- and, inside one call, the picks of later layers at the same or later positions -- are made on different hidden states
+    # and may differ at ANY margin; a wide-margin disagreement that nothing earlier can have caused (sequence 2, layer 0) stays a defect
+    sel_c = [x.copy() for x in sel_g]
+    sel_c[3][1, 0, 0] = [2, 7]
+    r = bench.compare_sharded(got2, want, "x", routing=(sel_c, sel, mar2))
+    assert r["greedy32"] and r["router_disagreements"] == 2 and r["consequences_of_an_earlier_reroute"] == 1 and r["disagreements_off_a_tie"] == 0
+    sel_p = [np.tile(np.array([1, 4], dtype=np.int32), (b, 3, L, 1))] + [x.copy() for x in sel[1:]]      # a 3-token first call
+    mar_p = [np.full((b, 3, L), 0.2, dtype=np.float32)] + [x.copy() for x in mar[1:]]
+    sel_pg = [x.copy() for x in sel_p]
+    sel_pg[0][0, 1, 0] = [1, 5]
+    mar_p[0][0, 1, 0] = 1e-5            # root: position 1, layer 0, on a tie
+    sel_pg[0][0, 2, 1] = [3, 4]         # later position, later layer, wide margin: a consequence
+    got4 = got.copy()
+    got4[:, 0] += 2.0
+    r = bench.compare_sharded(got4, want, "x", routing=(sel_pg, sel_p, mar_p))
+    assert r["greedy32"] and r["consequences_of_an_earlier_reroute"] == 1 and r["rows_compared"] == steps * (b - 1)
+    sel_pg[0][2, 0, 1] = [3, 4]         # position 0 of another sequence at a wide margin: nothing precedes it
+    assert not bench.compare_sharded(got4, want, "x", routing=(sel_pg, sel_p, mar_p))["greedy32"]
     # a large error where the routing agreed is a defect
     got3 = got.copy()
     got3[1, 0] += 0.5
