@@ -595,10 +595,14 @@ def run_ours(args, rank, world, local_rank):
             solo, _ = cls.initialize_model(cf1, None, "bf16", local_rank, random_seed=0, std=0.02)
             what = (f"{'tp' if use_tp else 'ep'}{world} logits vs single-GPU logits (same synthetic weights; real {ptoks}-token "
                     f"prefill + {steps_p} teacher-forced decode steps, batch {batch})")
-            if use_ep:
-                want, sel_w, mar_w = teacher_forced_logits(solo.dev, allp, feed, routing=True)
-                parity = compare_sharded(got, want, what + "; rows compared while both runs routed the sequence to the same experts",
-                                         routing=(sel_g, sel_w, mar_w))
+            if use_ep:      # the single-GPU run takes the sequences in the ranks' groups (see moe_leg: the dense path is not batch-invariant)
+                solo_parts = [teacher_forced_logits(solo.dev, allp[r * local_batch:(r + 1) * local_batch],
+                                                    feed[:, r * local_batch:(r + 1) * local_batch], routing=True) for r in range(world)]
+                want = np.concatenate([p[0] for p in solo_parts], axis=1)
+                sel_w = [np.concatenate([p[1][s] for p in solo_parts], axis=0) for s in range(steps_p + 1)]
+                mar_w = [np.concatenate([p[2][s] for p in solo_parts], axis=0) for s in range(steps_p + 1)]
+                parity = compare_sharded(got, want, what + f", taken in the ranks' groups of {local_batch}; rows compared while both runs routed "
+                                                           "the sequence to the same experts", routing=(sel_g, sel_w, mar_w))
             else:
                 parity = compare_sharded(got, teacher_forced_logits(solo.dev, allp, feed), what)
             del solo
@@ -744,11 +748,20 @@ def moe_leg(args, rank, world, local_rank, dist, peak):
             dist.barrier()
             if rank == 0:
                 solo, _ = cls.initialize_model(cf1, None, "bf16", local_rank, random_seed=0, std=0.02)
-                want, sel_w, mar_w = teacher_forced_logits(solo.dev, allp, feed, routing=True)
+                # the single-GPU run takes the sequences in the SAME groups the ranks own (lb sequences per call): the dense path is not
+                # batch-invariant (the stream-K attention cuts the step's page stream by the batch it sees, many-row calls pick other
+                # kernels), and with a bf16 KV cache every summation-order difference flips roundings that top-2 routing then amplifies
+                # -- measured at EP-8 against ONE batch-32 run: 46 near-tie reroutes in 53 k decisions, 89 % of the rows rerouted.
+                # Group for group the two runs differ only by what expert parallelism changes (dispatch, per-expert row blocks, combine).
+                solo_parts = [teacher_forced_logits(solo.dev, allp[r * lb:(r + 1) * lb], feed[:, r * lb:(r + 1) * lb], routing=True)
+                              for r in range(world)]
                 del solo
-                rec["parity"] = compare_sharded(got, want, f"ep{world} logits vs single-GPU logits (real {ptoks}-token prefill + {steps_p} "
-                                                            f"teacher-forced decode steps, batch {batch}); rows compared while both runs "
-                                                            "routed the sequence to the same experts", routing=(sel_g, sel_w, mar_w))
+                want = np.concatenate([p[0] for p in solo_parts], axis=1)
+                sel_w = [np.concatenate([p[1][s] for p in solo_parts], axis=0) for s in range(steps_p + 1)]
+                mar_w = [np.concatenate([p[2][s] for p in solo_parts], axis=0) for s in range(steps_p + 1)]
+                rec["parity"] = compare_sharded(got, want, f"ep{world} logits vs single-GPU logits of the same sequence groups (real {ptoks}-token "
+                                                            f"prefill + {steps_p} teacher-forced decode steps, {world} x batch {lb}); rows compared "
+                                                            "while both runs routed the sequence to the same experts", routing=(sel_g, sel_w, mar_w))
             dist.barrier()
         return rec if rank == 0 else None
     except Exception as ex:
