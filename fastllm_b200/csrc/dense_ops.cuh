@@ -250,6 +250,88 @@ static __global__ void dense_qkv_epi_kernel(const QkvEpiArgs a) {
     }
 }
 
+// Prefill variant (t % 8 == 0): one thread takes a column pair of EIGHT consecutive rows (tokens) of one sequence.  The one-row kernel
+// is a chain of dependent small loads per thread (step state -> KV length -> page table -> store address, RoPE position -> cos / sin)
+// repeated by 36 k CTAs of a 4096-token call, and its V^T scratch writes are 2-byte stores 128 bytes apart (126 us per layer against a
+// 25 us memory floor on Qwen2.5-7B); here the chain is paid once per eight rows, their loads travel together, and the eight tokens of
+// a V^T row are one 16-byte store.  Same arithmetic per element.
+constexpr int kQkvRowsPerThread = 8;
+static __global__ void __launch_bounds__(256) dense_qkv_epi_rows_kernel(const QkvEpiArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
+    constexpr int RPT = kQkvRowsPerThread;
+    const int row0 = blockIdx.y * RPT;
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair * 2 >= a.nqkv) return;
+    const int ra = pair * 2;
+    const int d = a.d, half = d >> 1;
+    const int hh = ra / d, j = (ra % d) >> 1;
+    float2 y[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {      // (0 + first slice: the same additions as sum_slices2, so a -0.0 comes out the same way)
+        const float2 p = *reinterpret_cast<const float2*>(a.y + (size_t)(row0 + r) * a.nqkv + ra);
+        y[r] = make_float2(0.f + p.x, 0.f + p.y);
+    }
+    for (int s = 1; s < a.nsl; ++s) {      // further split-K slices, in slice order
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const float2 p = *reinterpret_cast<const float2*>(a.y + (size_t)s * a.sl_stride + (size_t)(row0 + r) * a.nqkv + ra);
+            y[r].x += p.x;
+            y[r].y += p.y;
+        }
+    }
+    if (a.bias) {
+        const float b0 = a.bias[ra], b1 = a.bias[ra + 1];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) { y[r].x += b0; y[r].y += b1; }
+    }
+    const int seq = row0 / a.t, irel0 = row0 % a.t;             // t % 8 == 0: the eight rows belong to one sequence
+    const int cslot = st_slot(a.state, seq);
+    const int slot0 = a.state->kv_base[cslot] + irel0;
+    if (hh < a.nh + a.nkv) {
+        const int pos0 = st_rope(a.state, seq) + irel0;
+        float cs[RPT], sn[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int pos = min(pos0 + r, a.max_pos - 1);
+            cs[r] = a.rope_cos[(size_t)pos * half + j];
+            sn[r] = a.rope_sin[(size_t)pos * half + j];
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const float o1 = y[r].x * cs[r] - y[r].y * sn[r], o2 = y[r].x * sn[r] + y[r].y * cs[r];
+            if (hh < a.nh) {
+                float* q = a.q_out + ((size_t)(row0 + r) * a.nh + hh) * d;
+                q[j] = o1;
+                q[j + half] = o2;
+            } else {
+                const int slot = slot0 + r;
+                const int page = a.page_table[cslot * a.pt_stride + slot / kKvPage];
+                uint16_t* kp = a.kpool + (((size_t)page * a.nkv + (hh - a.nh)) * kKvPage + slot % kKvPage) * d;
+                kp[j] = f32_to_bf16_rne(o1);
+                kp[j + half] = f32_to_bf16_rne(o2);
+            }
+        }
+    } else {
+        const int hv = hh - a.nh - a.nkv;
+        uint32_t va[RPT / 2], vb[RPT / 2];      // bf16 of column 2j / 2j + 1 for the eight tokens, packed in token order
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int slot = slot0 + r;
+            const int page = a.page_table[cslot * a.pt_stride + slot / kKvPage];
+            uint16_t* vp = a.vpool + (((size_t)page * a.nkv + hv) * kKvPage + slot % kKvPage) * d;
+            const uint32_t ba = f32_to_bf16_rne(y[r].x), bb = f32_to_bf16_rne(y[r].y);
+            *reinterpret_cast<uint32_t*>(vp + 2 * j) = ba | (bb << 16);
+            if (r & 1) { va[r >> 1] |= ba << 16; vb[r >> 1] |= bb << 16; } else { va[r >> 1] = ba; vb[r >> 1] = bb; }
+        }
+        if (a.vt != nullptr) {      // irel0 % 8 == 0: the eight tokens are 16 aligned bytes of one V^T row
+            uint16_t* tp = a.vt + ((((size_t)seq * a.nkv + hv) * a.vt_pages + irel0 / kKvPage) * d + 2 * j) * kKvPage + irel0 % kKvPage;
+            *reinterpret_cast<uint4*>(tp) = make_uint4(va[0], va[1], va[2], va[3]);
+            *reinterpret_cast<uint4*>(tp + kKvPage) = make_uint4(vb[0], vb[1], vb[2], vb[3]);
+        }
+    }
+}
+
 // act = silu(gate) * up from the interleaved gate|up GEMM output, written directly as the hi/lo split the down GEMM reads
 // (grouped expert GEMMs: rows are blocks of `grp_cap` per expert, of which grp_cnt[block] are valid; the rest is skipped)
 static __global__ void dense_silu_split_kernel(const float* __restrict__ y, int nsl, long long sl_stride, int I, uint16_t* __restrict__ xhi,
