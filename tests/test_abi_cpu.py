@@ -23,6 +23,15 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared, "ctypes binding table out of sync with the header"
 
 
+def test_reference_side_bindings_declare_every_symbol():
+    """The Rust `extern "C"` block a maintainer would add and the C++ host mirror name every entry point of
+    the header: the three sides of the boundary cannot drift apart silently."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    rust = doc[doc.index('extern "C" {'):doc.index("pub fn check(")]
+    for name in _declared_symbols():
+        assert re.search(r"pub fn %s\(" % name, rust), f"{name} missing from the Rust extern block in INTEGRATION.md"
+
+
 def test_fl_config_layout_matches_header():
     from fastllm_b200._lib import FlConfig
     # 12 x int32, float, (pad), double, 2 x int32, 6 x int32
